@@ -1,0 +1,965 @@
+// manette_b200 -- device-side Atari 2600 + ALE environment core (sm_100a).
+//
+// One lane owns one environment.  This header holds the machine itself; the kernels that
+// drive it (lock-step next(), FiGAR repeat loop, reset) live in kernels.cu.
+//
+// Replaces, for the reference, the external `ALEInterface.act/reset_game/game_over/lives`
+// calls made from atari_emulator.py:72-77,94-97,121,128,133 (ALE = Stella 2.x fork).
+// Formulation differs from the CPU oracle on purpose: object graphics are built as 32-pixel
+// words of 160-bit line masks (collisions = word ANDs), the 6502 is decoded from a packed
+// 16-bit descriptor per opcode into {address phase, read phase, operate phase, write phase},
+// and all state is kept in a compact bit-packed record.
+//
+// The file is also compilable by a host C++ compiler (MN_HD expands to nothing): tests/ build
+// it that way ONLY to pre-check the logic against the oracle on machines without a GPU.
+// The product never runs the host build.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define MN_HD __host__ __device__
+#define MN_NOINLINE __noinline__
+#define MN_INLINE __forceinline__
+#else
+#define MN_HD
+#define MN_NOINLINE
+#define MN_INLINE inline
+#endif
+
+namespace mn {
+
+// ------------------------------------------------------------------ constants
+enum { CART_2K = 0, CART_4K = 1, CART_F8 = 2, CART_F6 = 3, CART_E0 = 4 };
+enum { CTRL_JOYSTICK = 0, CTRL_PADDLES = 1, CTRL_PADDLES_SWAPPED = 2 };
+enum { G_GENERIC = 0, G_PONG, G_BREAKOUT, G_SEAQUEST, G_SPACE_INVADERS, G_MS_PACMAN, G_ASTERIX, G_ASTEROIDS,
+       G_ENDURO, G_GOPHER, G_GRAVITAR, G_MONTEZUMA, G_YARS, G_NUM_GAMES };
+
+#define MN_SCREEN_W 160
+#define MN_SCREEN_H 210
+#define MN_FRAME_BYTES (MN_SCREEN_W * MN_SCREEN_H)
+#define MN_HBLANK 68
+#define MN_YSTART 34
+#define MN_MAX_SCANLINES 290
+#define MN_NEVER 0x7FFFFFFF
+#define MN_RES_MIN 0
+#define MN_RES_MAX 0x7FFFFFFF
+#define MN_PADDLE_DELTA 23000
+#define MN_PADDLE_MIN 27450
+#define MN_PADDLE_MAX 790196
+#define MN_PADDLE_DEFAULT (((MN_PADDLE_MAX - MN_PADDLE_MIN) / 2) + MN_PADDLE_MIN)
+
+// object ids / enabled bits
+enum { OB_P0 = 0, OB_M0 = 1, OB_P1 = 2, OB_M1 = 3, OB_BL = 4 };
+enum { EN_P0 = 0x01, EN_M0 = 0x02, EN_P1 = 0x04, EN_M1 = 0x08, EN_BL = 0x10, EN_PF = 0x20 };
+
+// TIA flag bits
+enum : uint32_t {
+  F_REFP0 = 1u << 0, F_REFP1 = 1u << 1, F_ENAM0 = 1u << 2, F_ENAM1 = 1u << 3, F_ENABL = 1u << 4, F_DENABL = 1u << 5,
+  F_VDELP0 = 1u << 6, F_VDELP1 = 1u << 7, F_VDELBL = 1u << 8, F_RESMP0 = 1u << 9, F_RESMP1 = 1u << 10,
+  F_SUP0 = 1u << 11, F_SUP1 = 1u << 12, F_PFREFL = 1u << 13, F_HMBLANK = 1u << 14, F_DUMP = 1u << 15,
+  F_PARTIAL = 1u << 16, F_CURFB = 1u << 17, F_STOP = 1u << 18, F_INPT4 = 1u << 19, F_INPT5 = 1u << 20,
+  F_TIMER_IRQ_READ = 1u << 21, F_TERMINAL = 1u << 22, F_STARTED = 1u << 23 };
+
+// addressing modes / operation classes of the packed decode descriptor
+enum { AM_IMP = 0, AM_ACC, AM_IMM, AM_ZP, AM_ZPX, AM_ZPY, AM_ABS, AM_ABX, AM_ABY, AM_IZX, AM_IZY, AM_REL, AM_IND };
+enum { OC_NONE = 0, OC_READ = 1, OC_WRITE = 2, OC_RMW = 3 };   // what the operate phase needs from memory
+enum {  // operations
+  O_NOP = 0, O_ORA, O_AND, O_EOR, O_ADC, O_SBC, O_CMP, O_CPX, O_CPY, O_BIT, O_LDA, O_LDX, O_LDY, O_LAX, O_LXA, O_ANC,
+  O_ALR, O_ARR, O_XAA, O_AXS, O_LAS,                                   // read class
+  O_STA, O_STX, O_STY, O_SAX, O_AHX, O_SHY, O_SHX, O_TAS,              // write class
+  O_ASL, O_LSR, O_ROL, O_ROR, O_INC, O_DEC, O_SLO, O_RLA, O_SRE, O_RRA, O_DCP, O_ISC,   // rmw class
+  O_BRANCH, O_JMP, O_JSR, O_RTS, O_RTI, O_BRK, O_PHA, O_PHP, O_PLA, O_PLP,
+  O_TAX, O_TAY, O_TXA, O_TYA, O_TSX, O_TXS, O_INX, O_INY, O_DEX, O_DEY, O_FLAG, O_KIL };
+// descriptor: [3:0] mode  [5:4] class  [11:6] op  [14:12] base cycles  [15] unused
+// branches keep their condition in a second table byte; flag ops likewise.
+#define MN_DESC(mode, cls, op, cyc) uint16_t((mode) | ((cls) << 4) | ((op) << 6) | ((cyc) << 12))
+
+struct Tables {          // read-only, staged in shared memory by the kernels
+  uint16_t desc[256];
+  uint8_t aux[256];      // branch: [7:6]=flag selector (0 N,1 V,2 C,3 Z) [0]=wanted value ; flag op: [7:1]=bit index in P [0]=set
+};
+
+// ------------------------------------------------------------------ per-environment record
+struct EnvState {
+  // 6502
+  uint8_t A, X, Y, SP;
+  uint16_t PC;
+  uint8_t P;            // C(0x01) I(0x04) D(0x08) B(0x10) V(0x40); N/Z live in nz
+  uint8_t dbus;
+  uint16_t nz;          // Z <=> (nz & 0xFF)==0 ; N <=> nz & 0x180
+  uint8_t bank, slice0, slice1, slice2;
+  int32_t cycles;
+  // RIOT
+  uint8_t timer, tshift, ddra, ddrb;
+  int32_t timer_set_cycle, irq_reset_cycle;
+  uint8_t swcha, swchb, pad0, pad1;
+  int32_t analog[4];
+  // TIA
+  int32_t clk_frame_start, clk_last_update, clks_to_eol, vsync_finish_clk, fb_pos, last_hmove_clk, dump_disabled_cycle;
+  uint32_t pf;
+  uint32_t flags;
+  uint16_t collision;
+  uint8_t vsync, vblank, nusiz0, nusiz1, ctrlpf, enabled;
+  uint8_t col[4];       // P0, P1, PF, BK
+  uint8_t grp0, grp1, dgrp0, dgrp1, cur_grp0, cur_grp1;
+  uint8_t pos[5];       // P0 M0 P1 M1 BL
+  uint8_t hm[5];
+  // ALE layer
+  uint32_t rng[4];
+  int32_t left_paddle, right_paddle;
+  int32_t score, reward, lives;
+  int32_t frame_number, episode_frame_number;
+  // AtariEmulator layer
+  int32_t host_lives;   // atari_emulator.py:121 self.lives
+  uint8_t ring_head;    // ObservationPool.current_observation_index
+  uint8_t game, cart, ctrl;
+  uint8_t ram[128];
+};
+
+// per-lane working context (pointers to where the pieces live while a kernel runs)
+struct Ctx {
+  EnvState* s;          // working copy (local / shared memory)
+  const uint8_t* rom;   // cartridge image (shared memory)
+  uint8_t* ram;         // 128 bytes, byte j at ram[(j >> 2) * ram_stride + (j & 3)]
+  int ram_stride;       // bytes between consecutive 4-byte RAM words of this lane
+  uint8_t* fb;          // this env's two frame buffers (global memory), 2 * MN_FRAME_BYTES
+  const Tables* tab;
+};
+
+MN_HD MN_INLINE uint8_t& ram_at(const Ctx& c, int j) { return c.ram[(j >> 2) * c.ram_stride + (j & 3)]; }
+
+// ------------------------------------------------------------------ small bit helpers
+MN_HD MN_INLINE uint32_t brev32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+  return __brev(v);
+#else
+  v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+  v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+  v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
+  v = ((v >> 8) & 0x00FF00FFu) | ((v & 0x00FF00FFu) << 8);
+  return (v >> 16) | (v << 16);
+#endif
+}
+MN_HD MN_INLINE uint32_t rev8(uint32_t b) { return brev32(b) >> 24; }
+// every bit of an 8-bit value -> 2 / 4 adjacent bits
+MN_HD MN_INLINE uint32_t widen2(uint32_t b) {
+  b = (b | (b << 4)) & 0x0F0Fu; b = (b | (b << 2)) & 0x3333u; b = (b | (b << 1)) & 0x5555u;
+  return b * 3u;
+}
+MN_HD MN_INLINE uint32_t widen4(uint32_t b) {
+  b = (b | (b << 12)) & 0x000F000Fu; b = (b | (b << 6)) & 0x03030303u; b = (b | (b << 3)) & 0x11111111u;
+  return b * 15u;
+}
+// bits of a <=32-pixel pattern (bit 0 = leftmost pixel) whose left edge sits at line position
+// `start` (0..159, wraps at 160) that fall into the 32-pixel word `w` of the line
+MN_HD MN_INLINE uint32_t place(uint32_t pattern, int start, int w) {
+  int rel = start - (w << 5);
+  if (rel < 0) rel += 160;
+  if (rel < 32) return pattern << rel;
+  if (rel > 128) return pattern >> (160 - rel);
+  return 0u;
+}
+
+// ------------------------------------------------------------------ TIA: line words
+MN_HD MN_INLINE uint32_t pf_word(const EnvState& s, int w) {
+  uint32_t left = (s.pf & 0xFu) | (rev8((s.pf >> 4) & 0xFFu) << 4) | (s.pf & 0xFF000u);
+  uint32_t right = (s.flags & F_PFREFL) ? (brev32(left) >> 12) : left;
+  uint32_t cells = (w < 4) ? (((left | (right << 20)) >> (w << 3)) & 0xFFu) : (right >> 12);
+  return widen4(cells);
+}
+MN_HD MN_INLINE uint32_t copies_word(uint32_t pattern, int pos, int mode, bool skip_first, int w) {
+  uint32_t m = skip_first ? 0u : place(pattern, pos, w);
+  // NUSIZ copy spacing: 1 -> +16 ; 2 -> +32 ; 3 -> +16,+32 ; 4 -> +64 ; 6 -> +32,+64
+  int a = -1, b = -1;
+  switch (mode) {
+    case 1: a = 16; break;
+    case 2: a = 32; break;
+    case 3: a = 16; b = 32; break;
+    case 4: a = 64; break;
+    case 6: a = 32; b = 64; break;
+    default: break;
+  }
+  if (a >= 0) { int p = pos + a; if (p >= 160) p -= 160; m |= place(pattern, p, w); }
+  if (b >= 0) { int p = pos + b; if (p >= 160) p -= 160; m |= place(pattern, p, w); }
+  return m;
+}
+MN_HD MN_INLINE uint32_t player_word(uint32_t grp, int nusiz, int pos, bool suppress, int w) {
+  int mode = nusiz & 7;
+  if (mode == 5 || mode == 7) {        // double / quad sized single copy, drawn one pixel late
+    if (suppress) return 0u;
+    uint32_t pattern = (mode == 5) ? widen2(rev8(grp)) : widen4(rev8(grp));
+    int p = pos + 1; if (p >= 160) p -= 160;
+    return place(pattern, p, w);
+  }
+  return copies_word(rev8(grp), pos, mode, suppress, w);
+}
+MN_HD MN_INLINE uint32_t missile_word(int nusiz, int pos, int w) {
+  int mode = nusiz & 7;
+  uint32_t pattern = (1u << (1 << ((nusiz >> 4) & 3))) - 1u;
+  if (mode == 5 || mode == 7) mode = 0;
+  return copies_word(pattern, pos, mode, false, w);
+}
+MN_HD MN_INLINE uint32_t ball_word(const EnvState& s, int w) {
+  uint32_t pattern = (1u << (1 << ((s.ctrlpf >> 4) & 3))) - 1u;
+  return place(pattern, s.pos[OB_BL], w);
+}
+
+// render `n` visible pixels of the current line starting at pixel `hpos`
+MN_HD MN_NOINLINE void tia_render(Ctx& c, int n, int hpos) {
+  EnvState& s = *c.s;
+  uint8_t* out = c.fb + ((s.flags & F_CURFB) ? MN_FRAME_BYTES : 0) + s.fb_pos;
+  s.fb_pos += n;
+  if (s.vblank & 0x02) { for (int i = 0; i < n; ++i) out[i] = 0; return; }
+  const uint32_t en = s.enabled;
+  const uint8_t bk = s.col[3];
+  if (en == 0) { for (int i = 0; i < n; ++i) out[i] = bk; return; }
+  const int x0 = hpos, x1 = hpos + n;
+  const bool prio = (s.ctrlpf & 0x04) != 0, score = (s.ctrlpf & 0x02) != 0;
+  uint32_t cx = 0;
+  for (int w = x0 >> 5; w <= ((x1 - 1) >> 5); ++w) {
+    const int base = w << 5;
+    const int lo = (x0 > base) ? (x0 - base) : 0;
+    const int hi = (x1 < base + 32) ? (x1 - base) : 32;
+    const uint32_t span = ((hi == 32) ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+    uint32_t pf = (en & EN_PF) ? (pf_word(s, w) & span) : 0u;
+    uint32_t bl = (en & EN_BL) ? (ball_word(s, w) & span) : 0u;
+    uint32_t p0 = (en & EN_P0) ? (player_word(s.cur_grp0, s.nusiz0, s.pos[OB_P0], (s.flags & F_SUP0) != 0, w) & span) : 0u;
+    uint32_t m0 = (en & EN_M0) ? (missile_word(s.nusiz0, s.pos[OB_M0], w) & span) : 0u;
+    uint32_t p1 = (en & EN_P1) ? (player_word(s.cur_grp1, s.nusiz1, s.pos[OB_P1], (s.flags & F_SUP1) != 0, w) & span) : 0u;
+    uint32_t m1 = (en & EN_M1) ? (missile_word(s.nusiz1, s.pos[OB_M1], w) & span) : 0u;
+    // collision latches: any common pixel inside the span
+    cx |= (m0 & p1) ? 0x0001u : 0u; cx |= (m0 & p0) ? 0x0002u : 0u;
+    cx |= (m1 & p0) ? 0x0004u : 0u; cx |= (m1 & p1) ? 0x0008u : 0u;
+    cx |= (p0 & pf) ? 0x0010u : 0u; cx |= (p0 & bl) ? 0x0020u : 0u;
+    cx |= (p1 & pf) ? 0x0040u : 0u; cx |= (p1 & bl) ? 0x0080u : 0u;
+    cx |= (m0 & pf) ? 0x0100u : 0u; cx |= (m0 & bl) ? 0x0200u : 0u;
+    cx |= (m1 & pf) ? 0x0400u : 0u; cx |= (m1 & bl) ? 0x0800u : 0u;
+    cx |= (bl & pf) ? 0x1000u : 0u; cx |= (p0 & p1) ? 0x2000u : 0u; cx |= (m0 & m1) ? 0x4000u : 0u;
+    const uint32_t g0 = p0 | m0, g1 = p1 | m1, gf = pf | bl;
+    uint8_t* o = out + (base - x0);
+    if ((g0 | g1 | gf) == 0u) { for (int x = lo; x < hi; ++x) o[x] = bk; continue; }
+    for (int x = lo; x < hi; ++x) {
+      const uint32_t bit = 1u << x;
+      uint8_t colr;
+      if (prio) {
+        if (gf & bit) colr = s.col[2];
+        else if (g0 & bit) colr = s.col[0];
+        else if (g1 & bit) colr = s.col[1];
+        else colr = bk;
+      } else {
+        if (g0 & bit) colr = s.col[0];
+        else if (g1 & bit) colr = s.col[1];
+        else if (pf & bit) colr = score ? s.col[(base + x) < 80 ? 0 : 1] : s.col[2];
+        else if (bl & bit) colr = s.col[2];
+        else colr = bk;
+      }
+      o[x] = colr;
+    }
+  }
+  s.collision |= uint16_t(cx);
+}
+
+// bring the picture up to colour clock `clock`
+MN_HD MN_NOINLINE void tia_advance(Ctx& c, int32_t clock) {
+  EnvState& s = *c.s;
+  const int32_t start = s.clk_frame_start + 228 * MN_YSTART;
+  const int32_t stop = start + 228 * MN_SCREEN_H;
+  if (clock < start || s.clk_last_update >= stop || s.clk_last_update >= clock) return;
+  if (clock > stop) clock = stop;
+  do {
+    int32_t from_sol = 228 - s.clks_to_eol;
+    int32_t n;
+    if (clock > s.clk_last_update + s.clks_to_eol) { n = s.clks_to_eol; s.clks_to_eol = 228; s.clk_last_update += n; }
+    else { n = clock - s.clk_last_update; s.clks_to_eol -= n; s.clk_last_update = clock; }
+    if (from_sol < MN_HBLANK) {
+      int32_t skip = MN_HBLANK - from_sol; if (skip > n) skip = n;
+      from_sol += skip; n -= skip;
+    }
+    const int32_t old_pos = s.fb_pos;
+    if (n != 0) tia_render(c, n, from_sol - MN_HBLANK);
+    if ((s.flags & F_HMBLANK) && from_sol < MN_HBLANK + 8) {
+      int32_t blanks = (MN_HBLANK + 8) - from_sol;
+      const int32_t room = MN_FRAME_BYTES - old_pos; if (blanks > room) blanks = room;
+      uint8_t* p = c.fb + ((s.flags & F_CURFB) ? MN_FRAME_BYTES : 0) + old_pos;
+      for (int i = 0; i < blanks; ++i) p[i] = 0;
+      if (n + from_sol >= MN_HBLANK + 8) s.flags &= ~F_HMBLANK;
+    }
+    if (s.clks_to_eol == 228) {   // line finished: playfield mirror latches, first-copy suppression ends
+      s.flags = (s.flags & ~(F_SUP0 | F_SUP1 | F_PFREFL)) | ((s.ctrlpf & 1) ? F_PFREFL : 0u);
+    }
+  } while (s.clk_last_update < clock);
+}
+
+MN_HD MN_INLINE void tia_refresh_grp(EnvState& s) {
+  uint32_t g0 = (s.flags & F_VDELP0) ? s.dgrp0 : s.grp0;
+  uint32_t g1 = (s.flags & F_VDELP1) ? s.dgrp1 : s.grp1;
+  s.cur_grp0 = uint8_t((s.flags & F_REFP0) ? rev8(g0) : g0);
+  s.cur_grp1 = uint8_t((s.flags & F_REFP1) ? rev8(g1) : g1);
+  s.enabled = uint8_t((s.enabled & ~(EN_P0 | EN_P1)) | (s.cur_grp0 ? EN_P0 : 0) | (s.cur_grp1 ? EN_P1 : 0));
+}
+MN_HD MN_INLINE void tia_refresh_misc(EnvState& s) {
+  bool bl = (s.flags & F_VDELBL) ? (s.flags & F_DENABL) != 0 : (s.flags & F_ENABL) != 0;
+  bool m0 = (s.flags & F_ENAM0) && !(s.flags & F_RESMP0);
+  bool m1 = (s.flags & F_ENAM1) && !(s.flags & F_RESMP1);
+  s.enabled = uint8_t((s.enabled & ~(EN_BL | EN_M0 | EN_M1 | EN_PF)) | (bl ? EN_BL : 0) | (m0 ? EN_M0 : 0) |
+                      (m1 ? EN_M1 : 0) | (s.pf ? EN_PF : 0));
+}
+MN_HD MN_INLINE void set_flag(EnvState& s, uint32_t f, bool on) { s.flags = on ? (s.flags | f) : (s.flags & ~f); }
+
+// number of the 15 HMOVE extra clocks that still count, as a movement in pixels (+ = right)
+MN_HD MN_INLINE int hmove_delta(int cyc, int hm) {
+  const int want = hm ^ 8;
+  if (cyc <= 22) {
+    int fit = (70 - 3 * cyc) >> 2; if (70 - 3 * cyc < 0) fit = 0;
+    return 8 - (want < fit ? want : fit);
+  }
+  if (cyc == 75) return 8 - want;
+  int first = (226 - 3 * cyc) >> 2; if (first < 1) first = 1;
+  int cnt = want - (first - 1);
+  return cnt > 0 ? -cnt : 0;
+}
+// where a RESPx strobe falls relative to the copies of the player being drawn: 1 inside a copy,
+// -1 in the 4-clock start-up of a copy, 0 elsewhere
+MN_HD MN_INLINE int resp_zone(int nusiz, int oldx, int newx) {
+  const int mode = nusiz & 7;
+  const int width = (mode == 5) ? 16 : (mode == 7) ? 32 : 8;
+  int res = 0;
+  // candidates newx and newx+160 cover the table's 0..236 sweep (later assignments win)
+  for (int k = 0; k < 2; ++k) {
+    const int nx = newx + 160 * k;
+    if (nx >= 160 + 72 + 5) break;
+    for (int cidx = 0; cidx < 3; ++cidx) {
+      int off;
+      switch (mode) {
+        case 1: off = (cidx == 0) ? 0 : (cidx == 1) ? 16 : -1; break;
+        case 2: off = (cidx == 0) ? 0 : (cidx == 1) ? 32 : -1; break;
+        case 3: off = cidx * 16; break;
+        case 4: off = (cidx == 0) ? 0 : (cidx == 1) ? 64 : -1; break;
+        case 6: off = cidx * 32; break;
+        default: off = (cidx == 0) ? 0 : -1; break;
+      }
+      if (off < 0) continue;
+      const int d = nx - (oldx + off);
+      if (d >= 0 && d < 4) res = -1;
+      else if (d >= 4 && d < 4 + width) res = 1;
+    }
+  }
+  return res;
+}
+
+MN_HD MN_NOINLINE void tia_poke(Ctx& c, uint32_t addr, uint32_t v) {
+  EnvState& s = *c.s;
+  addr &= 0x3F;
+  const int32_t clock = s.cycles * 3;
+  const int32_t hpos = (clock - s.clk_frame_start) % 228;
+  int32_t delay;
+  // colour clocks before a write shows: VBLANK/REFPx/GRPx/HMM1../VDELxx/RESMP0 1, NUSIZx/RESMx 8,
+  // PFx 2..5 depending on the phase within the playfield cell, everything else immediate
+  if (addr >= 0x0D && addr <= 0x0F) delay = 2 + (((hpos / 3) + 2) & 3);
+  else if (addr == 0x04 || addr == 0x05 || addr == 0x12 || addr == 0x13) delay = 8;
+  else if (addr == 0x01 || addr == 0x0B || addr == 0x0C || addr == 0x1B || addr == 0x1C || (addr >= 0x23 && addr <= 0x28)) delay = 1;
+  else delay = 0;
+  tia_advance(c, clock + delay);
+  if (((clock - s.clk_frame_start) / 228) > MN_MAX_SCANLINES) s.flags = (s.flags | F_STOP) & ~F_PARTIAL;
+  switch (addr) {
+    case 0x00:
+      s.vsync = uint8_t(v);
+      if (v & 0x02) s.vsync_finish_clk = clock + 228;
+      else if (clock >= s.vsync_finish_clk) { s.vsync_finish_clk = MN_NEVER; s.flags = (s.flags | F_STOP) & ~F_PARTIAL; }
+      break;
+    case 0x01:
+      if (!(s.vblank & 0x80) && (v & 0x80)) s.flags |= F_DUMP;
+      if ((s.vblank & 0x80) && !(v & 0x80)) { s.flags &= ~F_DUMP; s.dump_disabled_cycle = s.cycles; }
+      s.vblank = uint8_t(v);
+      break;
+    case 0x02: {
+      int32_t rest = 76 - ((s.cycles - (s.clk_frame_start / 3)) % 76);
+      if (rest < 76) s.cycles += rest;
+      break;
+    }
+    case 0x03: {
+      int32_t rest = 76 - ((s.cycles - (s.clk_frame_start / 3)) % 76);
+      s.cycles += rest - 1;
+      break;
+    }
+    case 0x04: s.nusiz0 = uint8_t(v); s.flags &= ~F_SUP0; break;
+    case 0x05: s.nusiz1 = uint8_t(v); s.flags &= ~F_SUP1; break;
+    case 0x06: case 0x07: case 0x08: case 0x09: s.col[addr - 0x06] = uint8_t(v & 0xFE); break;
+    case 0x0A:
+      s.ctrlpf = uint8_t(v);
+      if (hpos < (68 + 79)) set_flag(s, F_PFREFL, (v & 1) != 0);
+      break;
+    case 0x0B: set_flag(s, F_REFP0, (v & 0x08) != 0); tia_refresh_grp(s); break;
+    case 0x0C: set_flag(s, F_REFP1, (v & 0x08) != 0); tia_refresh_grp(s); break;
+    case 0x0D: s.pf = (s.pf & 0x000FFFF0u) | ((v >> 4) & 0x0Fu); tia_refresh_misc(s); break;
+    case 0x0E: s.pf = (s.pf & 0x000FF00Fu) | (v << 4); tia_refresh_misc(s); break;
+    case 0x0F: s.pf = (s.pf & 0x00000FFFu) | (v << 12); tia_refresh_misc(s); break;
+    case 0x10: case 0x11: {
+      const int p = (addr == 0x10) ? OB_P0 : OB_P1;
+      const int newx = (hpos < MN_HBLANK) ? 3 : ((hpos - MN_HBLANK + 5) % 160);
+      const int zone = resp_zone((p == OB_P0) ? s.nusiz0 : s.nusiz1, s.pos[p], newx);
+      if (zone == 1) tia_advance(c, clock + 11);
+      s.pos[p] = uint8_t(newx);
+      set_flag(s, (p == OB_P0) ? F_SUP0 : F_SUP1, zone >= 0);
+      break;
+    }
+    case 0x12: s.pos[OB_M0] = uint8_t((hpos < MN_HBLANK) ? 2 : ((hpos - MN_HBLANK + 4) % 160)); break;
+    case 0x13: s.pos[OB_M1] = uint8_t((hpos < MN_HBLANK) ? 2 : ((hpos - MN_HBLANK + 4) % 160)); break;
+    case 0x14: s.pos[OB_BL] = uint8_t((hpos < MN_HBLANK) ? 2 : ((hpos - MN_HBLANK + 4) % 160)); break;
+    case 0x1B: s.grp0 = uint8_t(v); s.dgrp1 = s.grp1; tia_refresh_grp(s); break;
+    case 0x1C:
+      s.grp1 = uint8_t(v); s.dgrp0 = s.grp0; set_flag(s, F_DENABL, (s.flags & F_ENABL) != 0);
+      tia_refresh_grp(s); tia_refresh_misc(s);
+      break;
+    case 0x1D: set_flag(s, F_ENAM0, (v & 2) != 0); tia_refresh_misc(s); break;
+    case 0x1E: set_flag(s, F_ENAM1, (v & 2) != 0); tia_refresh_misc(s); break;
+    case 0x1F: set_flag(s, F_ENABL, (v & 2) != 0); tia_refresh_misc(s); break;
+    case 0x20: s.hm[OB_P0] = uint8_t(v >> 4); break;
+    case 0x21: s.hm[OB_P1] = uint8_t(v >> 4); break;
+    case 0x22: s.hm[OB_M0] = uint8_t(v >> 4); break;
+    case 0x23: s.hm[OB_M1] = uint8_t(v >> 4); break;
+    case 0x24: s.hm[OB_BL] = uint8_t(v >> 4); break;
+    case 0x25: set_flag(s, F_VDELP0, (v & 1) != 0); tia_refresh_grp(s); break;
+    case 0x26: set_flag(s, F_VDELP1, (v & 1) != 0); tia_refresh_grp(s); break;
+    case 0x27: set_flag(s, F_VDELBL, (v & 1) != 0); tia_refresh_misc(s); break;
+    case 0x28: case 0x29: {
+      const bool one = (addr == 0x29);
+      const uint32_t f = one ? F_RESMP1 : F_RESMP0;
+      if ((s.flags & f) && !(v & 2)) {
+        const int ns = (one ? s.nusiz1 : s.nusiz0) & 7;
+        const int middle = (ns == 5) ? 8 : (ns == 7) ? 16 : 4;
+        s.pos[one ? OB_M1 : OB_M0] = uint8_t((s.pos[one ? OB_P1 : OB_P0] + middle) % 160);
+      }
+      set_flag(s, f, (v & 2) != 0);
+      tia_refresh_misc(s);
+      break;
+    }
+    case 0x2A: {
+      const int cyc = hpos / 3;
+      if (cyc <= 20 || cyc == 75) s.flags |= F_HMBLANK;
+      for (int k = 0; k < 5; ++k) {
+        int p = int(s.pos[k]) + hmove_delta(cyc, s.hm[k]);
+        if (p >= 160) p -= 160; else if (p < 0) p += 160;
+        s.pos[k] = uint8_t(p);
+      }
+      s.flags &= ~(F_SUP0 | F_SUP1);
+      s.last_hmove_clk = clock;
+      break;
+    }
+    case 0x2B: for (int k = 0; k < 5; ++k) s.hm[k] = 0; break;
+    case 0x2C: s.collision = 0; break;
+    default: break;
+  }
+}
+
+MN_HD MN_NOINLINE uint32_t tia_peek(Ctx& c, uint32_t addr) {
+  EnvState& s = *c.s;
+  tia_advance(c, s.cycles * 3);
+  const uint32_t noise = s.dbus & 0x3Fu;
+  const uint32_t reg = addr & 0x0F;
+  if (reg < 8) {
+    // latch pairs in read order: CXM0P CXM1P CXP0FB CXP1FB CXM0FB CXM1FB CXBLPF CXPPMM
+    const uint32_t hi = (reg == 6) ? 0x1000u : (reg == 7) ? 0x2000u : (1u << (2 * reg));
+    const uint32_t lo = (reg == 6) ? 0u : (reg == 7) ? 0x4000u : (2u << (2 * reg));
+    return ((s.collision & hi) ? 0x80u : 0u) | ((s.collision & lo) ? 0x40u : 0u) | noise;
+  }
+  if (reg < 12) {
+    const int32_t r = s.analog[reg - 8];
+    if (r == MN_RES_MIN) return 0x80u | noise;
+    if (r == MN_RES_MAX || (s.flags & F_DUMP)) return noise;
+#ifdef __CUDA_ARCH__
+    const double t = __dmul_rn(__dmul_rn(1.6, double(r)), 0.01E-6);
+    const uint32_t needed = uint32_t(__dmul_rn(t, 1.19E6));
+#else
+    const double t = (1.6 * r * 0.01E-6);
+    const uint32_t needed = uint32_t(t * 1.19E6);
+#endif
+    return (uint32_t(s.cycles) > uint32_t(s.dump_disabled_cycle + int32_t(needed))) ? (0x80u | noise) : noise;
+  }
+  if (reg == 12) return ((s.flags & F_INPT4) ? 0x80u : 0u) | noise;
+  if (reg == 13) return ((s.flags & F_INPT5) ? 0x80u : 0u) | noise;
+  return noise;
+}
+
+// ------------------------------------------------------------------ RIOT
+MN_HD MN_NOINLINE uint32_t riot_peek(Ctx& c, uint32_t addr) {
+  EnvState& s = *c.s;
+  switch (addr & 7) {
+    case 0: return s.swcha;
+    case 1: return s.ddra;
+    case 2: return s.swchb;
+    case 3: return s.ddrb;
+    default: break;
+  }
+  const uint32_t delta = uint32_t((s.cycles - 1) - s.timer_set_cycle);
+  int32_t t = int32_t(s.timer) - int32_t(delta >> s.tshift) - 1;
+  if (addr & 1) return (t >= 0 || (s.flags & F_TIMER_IRQ_READ)) ? 0x00u : 0x80u;   // interrupt flag
+  if (t >= 0) return uint32_t(t) & 0xFFu;
+  t = int32_t(uint32_t(s.timer) << s.tshift) - int32_t(delta) - 1;
+  if (t <= -2 && !(s.flags & F_TIMER_IRQ_READ)) { s.flags |= F_TIMER_IRQ_READ; s.irq_reset_cycle = s.cycles; }
+  if (s.flags & F_TIMER_IRQ_READ) {
+    const int32_t offset = s.irq_reset_cycle - (s.timer_set_cycle + int32_t(uint32_t(s.timer) << s.tshift));
+    t = int32_t(s.timer) - int32_t(delta >> s.tshift) - offset;
+  }
+  return uint32_t(t) & 0xFFu;
+}
+MN_HD MN_NOINLINE void riot_poke(Ctx& c, uint32_t addr, uint32_t v) {
+  EnvState& s = *c.s;
+  if ((addr & 7) == 1) s.ddra = uint8_t(v);
+  else if ((addr & 7) == 3) s.ddrb = uint8_t(v);
+  else if ((addr & 0x14) == 0x14) {
+    const uint32_t sel = addr & 3;
+    s.timer = uint8_t(v); s.tshift = uint8_t(sel == 0 ? 0 : sel == 1 ? 3 : sel == 2 ? 6 : 10);
+    s.timer_set_cycle = s.cycles; s.flags &= ~F_TIMER_IRQ_READ;
+  }
+}
+
+// ------------------------------------------------------------------ bus
+MN_HD MN_INLINE void cart_touch(EnvState& s, uint32_t a) {   // a = addr & 0xFFF, banked carts only
+  if (s.cart == CART_F8) { if (a == 0xFF8) s.bank = 0; else if (a == 0xFF9) s.bank = 1; }
+  else if (s.cart == CART_F6) { if (a >= 0xFF6 && a <= 0xFF9) s.bank = uint8_t(a - 0xFF6); }
+  else if (s.cart == CART_E0) {
+    if (a >= 0xFE0 && a <= 0xFF7) {
+      const uint8_t sl = uint8_t(a & 7);
+      if (a < 0xFE8) s.slice0 = sl; else if (a < 0xFF0) s.slice1 = sl; else s.slice2 = sl;
+    }
+  }
+}
+MN_HD MN_INLINE uint32_t bus_read(Ctx& c, uint32_t addr) {
+  EnvState& s = *c.s;
+  uint32_t v;
+  if (addr & 0x1000) {
+    const uint32_t a = addr & 0x0FFF;
+    if (s.cart <= CART_4K) v = c.rom[(s.cart == CART_2K) ? (a & 0x7FF) : a];
+    else {
+      if (a >= 0xFE0) cart_touch(s, a);
+      if (s.cart == CART_E0) {
+        const uint32_t seg = a >> 10;
+        const uint32_t sl = (seg == 0) ? s.slice0 : (seg == 1) ? s.slice1 : (seg == 2) ? s.slice2 : 7u;
+        v = c.rom[(sl << 10) + (a & 0x3FF)];
+      } else v = c.rom[(uint32_t(s.bank) << 12) + a];
+    }
+  } else if (addr & 0x80) {
+    if (addr & 0x200) v = riot_peek(c, addr); else v = ram_at(c, addr & 0x7F);
+  } else v = tia_peek(c, addr);
+  s.dbus = uint8_t(v);
+  return v;
+}
+MN_HD MN_INLINE void bus_write(Ctx& c, uint32_t addr, uint32_t v) {
+  EnvState& s = *c.s;
+  v &= 0xFF;
+  if (addr & 0x1000) { if (s.cart > CART_4K) cart_touch(s, addr & 0x0FFF); }
+  else if (addr & 0x80) { if (addr & 0x200) riot_poke(c, addr, v); else ram_at(c, addr & 0x7F) = uint8_t(v); }
+  else tia_poke(c, addr, v);
+  s.dbus = uint8_t(v);
+}
+
+// ------------------------------------------------------------------ 6502
+MN_HD MN_INLINE uint32_t pack_ps(const EnvState& s) {
+  return 0x20u | (s.P & 0x5Du) | ((s.nz & 0x180) ? 0x80u : 0u) | ((s.nz & 0xFF) ? 0u : 0x02u);
+}
+MN_HD MN_INLINE void unpack_ps(EnvState& s, uint32_t p) {
+  s.P = uint8_t(p & 0x5D);
+  s.nz = uint16_t(((p & 0x80) << 1) | ((p & 0x02) ? 0 : 1));
+}
+MN_HD MN_INLINE uint32_t bcd_bin(uint32_t v) { return (v >> 4) * 10 + (v & 15); }
+MN_HD MN_INLINE void op_adc(EnvState& s, uint32_t m) {
+  const uint32_t a = s.A, cin = s.P & 1;
+  if (!(s.P & 0x08)) {
+    const uint32_t sum = a + m + cin;
+    const bool v = ((~(a ^ m)) & (a ^ sum) & 0x80) != 0;
+    s.A = uint8_t(sum); s.nz = uint8_t(sum);
+    s.P = uint8_t((s.P & ~0x41) | (sum > 0xFF ? 1 : 0) | (v ? 0x40 : 0));
+  } else {
+    const uint32_t sum = bcd_bin(a) + bcd_bin(m) + cin;
+    const uint32_t low = sum & 0xFF;
+    const uint32_t r = (((low % 100) / 10) << 4) | (low % 10);
+    const bool v = ((a ^ r) & 0x80) && ((r ^ m) & 0x80);
+    s.A = uint8_t(r); s.nz = uint8_t(r);
+    s.P = uint8_t((s.P & ~0x41) | (sum > 99 ? 1 : 0) | (v ? 0x40 : 0));
+  }
+}
+MN_HD MN_INLINE void op_sbc(EnvState& s, uint32_t m) {
+  const uint32_t a = s.A, cin = s.P & 1;
+  if (!(s.P & 0x08)) {
+    const uint32_t nm = (~m) & 0xFF;
+    const uint32_t sum = a + nm + cin;
+    const bool v = ((~(a ^ nm)) & (a ^ sum) & 0x80) != 0;
+    s.A = uint8_t(sum); s.nz = uint8_t(sum);
+    s.P = uint8_t((s.P & ~0x41) | (sum > 0xFF ? 1 : 0) | (v ? 0x40 : 0));
+  } else {
+    int32_t diff = int32_t(bcd_bin(a)) - int32_t(bcd_bin(m)) - int32_t(1 - cin);
+    if (diff < 0) diff += 100;
+    const uint32_t r = ((uint32_t(diff % 100) / 10) << 4) | uint32_t(diff % 10);
+    const bool carry = a >= (m + (1 - cin));
+    const bool v = ((a ^ r) & 0x80) && ((r ^ m) & 0x80);
+    s.A = uint8_t(r); s.nz = uint8_t(r);
+    s.P = uint8_t((s.P & ~0x41) | (carry ? 1 : 0) | (v ? 0x40 : 0));
+  }
+}
+MN_HD MN_INLINE void op_cmp(EnvState& s, uint32_t r, uint32_t m) {
+  const uint32_t d = (r - m) & 0x1FF;
+  s.nz = uint8_t(d);
+  s.P = uint8_t((s.P & ~1) | ((d & 0x100) ? 0 : 1));
+}
+MN_HD MN_INLINE void stk_push(Ctx& c, uint32_t v) { bus_write(c, 0x0100u | c.s->SP, v); c.s->SP--; }
+MN_HD MN_INLINE uint32_t stk_pull(Ctx& c) { c.s->SP++; return bus_read(c, 0x0100u | c.s->SP); }
+
+// one instruction
+MN_HD MN_INLINE void cpu_step(Ctx& c) {
+  EnvState& s = *c.s;
+  const uint32_t ir = bus_read(c, s.PC); s.PC++;
+  const uint32_t d = c.tab->desc[ir];
+  const uint32_t mode = d & 15, cls = (d >> 4) & 3, op = (d >> 6) & 63;
+  { const uint32_t cy = (d >> 12) & 7; s.cycles += int32_t(cy ? cy : 8u); }   // 0 encodes the 8-cycle forms
+  // ---- address phase
+  uint32_t ea = 0, b1 = 0;
+  if (mode >= AM_IMM) {
+    b1 = bus_read(c, s.PC);   // every mode from IMM on has at least one operand byte
+    uint32_t base;
+    switch (mode) {
+      case AM_IMM: case AM_REL: ea = s.PC; s.PC++; break;
+      case AM_ZP: ea = b1; s.PC++; break;
+      case AM_ZPX: ea = (b1 + s.X) & 0xFF; s.PC++; break;
+      case AM_ZPY: ea = (b1 + s.Y) & 0xFF; s.PC++; break;
+      case AM_ABS: case AM_ABX: case AM_ABY: case AM_IND: {
+        const uint32_t b2 = bus_read(c, uint16_t(s.PC + 1)); s.PC += 2;
+        base = b1 | (b2 << 8);
+        if (mode == AM_ABS) ea = base;
+        else if (mode == AM_IND) {
+          const uint32_t hi_addr = ((base & 0xFF) == 0xFF) ? (base & 0xFF00) : ((base + 1) & 0xFFFF);
+          const uint32_t tl = bus_read(c, base);
+          ea = tl | (bus_read(c, hi_addr) << 8);
+        } else {
+          ea = (base + ((mode == AM_ABX) ? s.X : s.Y)) & 0xFFFF;
+          if (cls == OC_READ && ((base ^ ea) & 0xFF00)) s.cycles += 1;
+        }
+        break;
+      }
+      case AM_IZX: {
+        s.PC++;
+        const uint32_t p = (b1 + s.X) & 0xFF;
+        const uint32_t lo = bus_read(c, p);
+        ea = lo | (bus_read(c, (p + 1) & 0xFF) << 8);
+        break;
+      }
+      default: {   // AM_IZY
+        s.PC++;
+        const uint32_t lo = bus_read(c, b1);
+        base = lo | (bus_read(c, (b1 + 1) & 0xFF) << 8);
+        ea = (base + s.Y) & 0xFFFF;
+        if (cls == OC_READ && ((base ^ ea) & 0xFF00)) s.cycles += 1;
+        break;
+      }
+    }
+  }
+  // ---- read phase
+  uint32_t m = 0;
+  if (cls == OC_READ) m = (mode == AM_IMM) ? b1 : bus_read(c, ea);
+  else if (cls == OC_RMW) m = (mode == AM_ACC) ? s.A : bus_read(c, ea);
+  // ---- operate phase
+  uint32_t w = 0;
+  switch (op) {
+    case O_NOP: break;
+    case O_ORA: s.A |= uint8_t(m); s.nz = s.A; break;
+    case O_AND: s.A &= uint8_t(m); s.nz = s.A; break;
+    case O_EOR: s.A ^= uint8_t(m); s.nz = s.A; break;
+    case O_ADC: op_adc(s, m); break;
+    case O_SBC: op_sbc(s, m); break;
+    case O_CMP: op_cmp(s, s.A, m); break;
+    case O_CPX: op_cmp(s, s.X, m); break;
+    case O_CPY: op_cmp(s, s.Y, m); break;
+    case O_BIT: s.nz = uint16_t(((m & 0x80) << 1) | ((s.A & m) ? 1 : 0)); s.P = uint8_t((s.P & ~0x40) | (m & 0x40)); break;
+    case O_LDA: s.A = uint8_t(m); s.nz = s.A; break;
+    case O_LDX: s.X = uint8_t(m); s.nz = s.X; break;
+    case O_LDY: s.Y = uint8_t(m); s.nz = s.Y; break;
+    case O_LAX: s.A = s.X = uint8_t(m); s.nz = s.A; break;
+    case O_LXA: s.A = s.X = uint8_t((s.A | 0xEE) & m); s.nz = s.A; break;
+    case O_ANC: s.A &= uint8_t(m); s.nz = s.A; s.P = uint8_t((s.P & ~1) | (s.A >> 7)); break;
+    case O_ALR: s.A &= uint8_t(m); s.P = uint8_t((s.P & ~1) | (s.A & 1)); s.A >>= 1; s.nz = s.A; break;
+    case O_ARR: {
+      uint32_t a = s.A & m; a = ((a >> 1) & 0x7F) | ((s.P & 1) << 7);
+      s.A = uint8_t(a); s.nz = s.A;
+      s.P = uint8_t((s.P & ~0x41) | ((a >> 6) & 1) | ((((a >> 6) ^ (a >> 5)) & 1) ? 0x40 : 0));
+      break;
+    }
+    case O_XAA: s.A = uint8_t(s.X & m); s.nz = s.A; break;
+    case O_AXS: { const uint32_t dd = ((s.X & s.A) - m) & 0x1FF; s.X = uint8_t(dd); s.nz = s.X; s.P = uint8_t((s.P & ~1) | ((dd & 0x100) ? 0 : 1)); break; }
+    case O_LAS: s.A = s.X = s.SP = uint8_t(m & s.SP); s.nz = s.A; break;
+    case O_STA: w = s.A; break;
+    case O_STX: w = s.X; break;
+    case O_STY: w = s.Y; break;
+    case O_SAX: w = s.A & s.X; break;
+    case O_AHX: w = s.A & s.X & (((ea >> 8) + 1) & 0xFF); break;
+    case O_SHY: w = s.Y & (((ea >> 8) + 1) & 0xFF); break;
+    case O_SHX: w = s.X & (((ea >> 8) + 1) & 0xFF); break;
+    case O_TAS: s.SP = s.A & s.X; w = s.SP & (((ea >> 8) + 1) & 0xFF); break;
+    case O_ASL: case O_SLO: s.P = uint8_t((s.P & ~1) | (m >> 7)); w = (m << 1) & 0xFF; if (op == O_ASL) s.nz = uint8_t(w); else { s.A |= uint8_t(w); s.nz = s.A; } break;
+    case O_LSR: case O_SRE: s.P = uint8_t((s.P & ~1) | (m & 1)); w = m >> 1; if (op == O_LSR) s.nz = uint8_t(w); else { s.A ^= uint8_t(w); s.nz = s.A; } break;
+    case O_ROL: case O_RLA: { const uint32_t cin = s.P & 1; s.P = uint8_t((s.P & ~1) | (m >> 7)); w = ((m << 1) | cin) & 0xFF; if (op == O_ROL) s.nz = uint8_t(w); else { s.A &= uint8_t(w); s.nz = s.A; } break; }
+    case O_ROR: case O_RRA: { const uint32_t cin = s.P & 1; s.P = uint8_t((s.P & ~1) | (m & 1)); w = (m >> 1) | (cin << 7); if (op == O_ROR) s.nz = uint8_t(w); else op_adc(s, w); break; }
+    case O_INC: w = (m + 1) & 0xFF; s.nz = uint8_t(w); break;
+    case O_DEC: w = (m - 1) & 0xFF; s.nz = uint8_t(w); break;
+    case O_DCP: w = (m - 1) & 0xFF; op_cmp(s, s.A, w); break;
+    case O_ISC: w = (m + 1) & 0xFF; op_sbc(s, w); break;
+    case O_BRANCH: {
+      const uint32_t ax = c.tab->aux[ir];
+      const uint32_t sel = ax >> 6;
+      const bool flag = (sel == 0) ? ((s.nz & 0x180) != 0) : (sel == 1) ? ((s.P & 0x40) != 0) : (sel == 2) ? ((s.P & 1) != 0) : ((s.nz & 0xFF) == 0);
+      const int32_t off = int8_t(b1);
+      if (flag == ((ax & 1) != 0)) {
+        const uint32_t target = (s.PC + off) & 0xFFFF;
+        s.cycles += ((s.PC ^ target) & 0xFF00) ? 2 : 1;
+        s.PC = uint16_t(target);
+      }
+      break;
+    }
+    case O_JMP: s.PC = uint16_t(ea); break;
+    case O_JSR: { const uint32_t ret = (s.PC - 1) & 0xFFFF; stk_push(c, ret >> 8); stk_push(c, ret & 0xFF); s.PC = uint16_t(ea); break; }
+    case O_RTS: { const uint32_t lo = stk_pull(c); const uint32_t hi = stk_pull(c); s.PC = uint16_t((lo | (hi << 8)) + 1); break; }
+    case O_RTI: { unpack_ps(s, stk_pull(c)); const uint32_t lo = stk_pull(c); const uint32_t hi = stk_pull(c); s.PC = uint16_t(lo | (hi << 8)); break; }
+    case O_BRK: {
+      bus_read(c, s.PC); s.PC++; s.P |= 0x10;
+      stk_push(c, s.PC >> 8); stk_push(c, s.PC & 0xFF); stk_push(c, pack_ps(s));
+      s.P |= 0x04;
+      const uint32_t lo = bus_read(c, 0xFFFE); s.PC = uint16_t(lo | (bus_read(c, 0xFFFF) << 8));
+      break;
+    }
+    case O_PHA: stk_push(c, s.A); break;
+    case O_PHP: stk_push(c, pack_ps(s) | 0x10); break;
+    case O_PLA: s.A = uint8_t(stk_pull(c)); s.nz = s.A; break;
+    case O_PLP: unpack_ps(s, stk_pull(c)); break;
+    case O_TAX: s.X = s.A; s.nz = s.X; break;
+    case O_TAY: s.Y = s.A; s.nz = s.Y; break;
+    case O_TXA: s.A = s.X; s.nz = s.A; break;
+    case O_TYA: s.A = s.Y; s.nz = s.A; break;
+    case O_TSX: s.X = s.SP; s.nz = s.X; break;
+    case O_TXS: s.SP = s.X; break;
+    case O_INX: s.X++; s.nz = s.X; break;
+    case O_INY: s.Y++; s.nz = s.Y; break;
+    case O_DEX: s.X--; s.nz = s.X; break;
+    case O_DEY: s.Y--; s.nz = s.Y; break;
+    case O_FLAG: { const uint32_t ax = c.tab->aux[ir]; const uint8_t mask = uint8_t(1u << (ax >> 1)); s.P = (ax & 1) ? (s.P | mask) : (s.P & ~mask); break; }
+    default: break;   // O_KIL
+  }
+  // ---- write phase
+  if (cls == OC_WRITE) bus_write(c, ea, w);
+  else if (cls == OC_RMW) { if (mode == AM_ACC) { s.A = uint8_t(w); } else bus_write(c, ea, w); }
+}
+
+// ------------------------------------------------------------------ frame
+MN_HD MN_INLINE void frame_begin(EnvState& s) {
+  s.flags ^= F_CURFB;
+  const int32_t clocks = ((s.cycles * 3) - s.clk_frame_start) % 228;
+  const int32_t cy = s.cycles;
+  s.timer_set_cycle -= cy; s.irq_reset_cycle -= cy; s.dump_disabled_cycle -= cy;
+  s.last_hmove_clk -= cy * 3;
+  if (s.vsync_finish_clk != MN_NEVER) s.vsync_finish_clk -= cy * 3;
+  s.cycles = 0;
+  s.clk_frame_start = -clocks;
+  s.clk_last_update = s.clk_frame_start + 228 * MN_YSTART;
+  s.clks_to_eol = 228;
+  s.fb_pos = 0;
+}
+MN_HD MN_INLINE void run_frame(Ctx& c) {
+  EnvState& s = *c.s;
+  if (!(s.flags & F_PARTIAL)) frame_begin(s);
+  s.flags = (s.flags | F_PARTIAL) & ~F_STOP;
+  for (int n = 25000; n > 0 && !(s.flags & F_STOP); --n) cpu_step(c);
+}
+
+// ------------------------------------------------------------------ ALE layer
+MN_HD MN_INLINE void rng_advance(uint32_t* r) {
+  uint32_t y = r[3];
+  uint32_t x = (r[0] & 0x7FFFFFFFu) ^ r[1] ^ r[2];
+  x ^= (x << 1);
+  y ^= (y >> 1) ^ x;
+  r[0] = r[1]; r[1] = r[2]; r[2] = x ^ (y << 10); r[3] = y;
+  if (y & 1) { r[1] ^= 0x8f7011eeu; r[2] ^= 0xfc78ff1fu; }
+}
+MN_HD MN_INLINE uint32_t rng_next(uint32_t* r) {
+  rng_advance(r);
+  uint32_t t0 = r[3];
+  const uint32_t t1 = r[0] + (r[2] >> 8);
+  t0 ^= t1;
+  if (t1 & 1) t0 ^= 0x3793fdffu;
+  return t0;
+}
+MN_HD MN_INLINE void rng_seed(uint32_t* r, uint32_t seed) {
+  r[0] = seed; r[1] = 0x8f7011eeu; r[2] = 0xfc78ff1fu; r[3] = 0x3793fdffu;
+  for (uint32_t i = 1; i < 8; ++i) r[i & 3] ^= i + 1812433253u * (r[(i - 1) & 3] ^ (r[(i - 1) & 3] >> 30));
+  if ((r[0] & 0x7FFFFFFFu) == 0 && r[1] == 0 && r[2] == 0 && r[3] == 0) { r[0] = 'T'; r[1] = 'I'; r[2] = 'N'; r[3] = 'Y'; }
+  for (int i = 0; i < 8; ++i) rng_advance(r);
+}
+
+MN_HD MN_INLINE int32_t ram_bcd(const Ctx& c, int off) { const uint32_t b = ram_at(c, off & 0x7F); return int32_t((b >> 4) * 10 + (b & 15)); }
+
+// per-game reward / terminal / lives from RAM after every frame
+MN_HD MN_NOINLINE void game_observe(Ctx& c) {
+  EnvState& s = *c.s;
+  int32_t sc = s.score;
+  bool term = false;
+#define RB(o) int32_t(ram_at(c, (o) & 0x7F))
+  switch (s.game) {
+    case G_PONG: { const int32_t x = RB(13), y = RB(14); sc = y - x; term = (x == 21 || y == 21); break; }
+    case G_BREAKOUT: {
+      const int32_t x = RB(77), y = RB(76), b = RB(57);
+      sc = (x & 15) + 10 * (x >> 4) + 100 * (y & 15);
+      if (!(s.flags & F_STARTED) && b == 5) s.flags |= F_STARTED;
+      term = (s.flags & F_STARTED) && b == 0; s.lives = b;
+      break;
+    }
+    case G_SEAQUEST: sc = ram_bcd(c, 0xBA) + 100 * ram_bcd(c, 0xB9) + 10000 * ram_bcd(c, 0xB8); term = RB(0xA3) != 0; s.lives = RB(0xBB) + 1; break;
+    case G_SPACE_INVADERS: sc = ram_bcd(c, 0xE8) + 100 * ram_bcd(c, 0xE6); s.lives = RB(0xC9); term = (RB(0x98) & 0x80) || s.lives == 0; break;
+    case G_MS_PACMAN: {
+      sc = ram_bcd(c, 0xF8) + 100 * ram_bcd(c, 0xF9) + 10000 * ram_bcd(c, 0xFA);
+      const int32_t lb = RB(0xFB) & 15; term = (lb == 0 && RB(0xA7) == 0x53); s.lives = (lb & 7) + 1;
+      break;
+    }
+    case G_ASTERIX: {
+      sc = ram_bcd(c, 0xE0) + 100 * ram_bcd(c, 0xDF) + 10000 * ram_bcd(c, 0xDE);
+      const int32_t lv = RB(0xD3) & 15; term = (RB(0xC7) == 1 && lv == 1); s.lives = lv;
+      break;
+    }
+    case G_ASTEROIDS: sc = (ram_bcd(c, 0xBE) + 100 * ram_bcd(c, 0xBD)) * 10; s.lives = RB(0xBC) >> 4; term = (s.lives == 0); break;
+    case G_ENDURO: {
+      sc = 0;
+      const int32_t level = RB(0xAD);
+      if (level != 0) {
+        int32_t cars = ram_bcd(c, 0xAB) + 100 * ram_bcd(c, 0xAC);
+        cars = ((level == 1) ? 200 : 300) - cars;
+        if (level >= 2) sc = 200 + (level - 2) * 300;
+        sc += cars;
+      }
+      term = (RB(0xAF) == 0xFF);
+      break;
+    }
+    case G_GOPHER: {
+      sc = ram_bcd(c, 0xB2) + 100 * ram_bcd(c, 0xB1) + 10000 * ram_bcd(c, 0xB0);
+      const int32_t cb = RB(0xB4) & 7; term = (cb == 0); s.lives = (cb & 1) + ((cb >> 1) & 1) + (cb >> 2);
+      break;
+    }
+    case G_GRAVITAR: {
+      sc = ram_bcd(c, 0x09) + 100 * ram_bcd(c, 0x08) + 10000 * ram_bcd(c, 0x07);
+      const int32_t nl = RB(0x84); term = (nl == 0 && RB(0x81) == 1); s.lives = nl + 1;
+      break;
+    }
+    case G_MONTEZUMA: {
+      sc = ram_bcd(c, 0x95) + 100 * ram_bcd(c, 0x94) + 10000 * ram_bcd(c, 0x93);
+      const int32_t nl = RB(0xBA); term = (nl == 0 && RB(0xFE) == 0x60); s.lives = (nl & 7) + 1;
+      break;
+    }
+    case G_YARS: {
+      sc = ram_bcd(c, 0xE2) + 100 * ram_bcd(c, 0xE1) + 10000 * ram_bcd(c, 0xE0);
+      const int32_t lb = RB(0x9E) >> 4; term = (lb == 0); s.lives = lb;
+      break;
+    }
+    default: s.reward = 0; set_flag(s, F_TERMINAL, false); return;
+  }
+#undef RB
+  int32_t r = sc - s.score;
+  if (s.game == G_SPACE_INVADERS && r < 0) r = (10000 - s.score) + sc;
+  if (s.game == G_ASTEROIDS && r < 0) r += 100000;
+  s.reward = r; s.score = sc;
+  set_flag(s, F_TERMINAL, term);
+}
+
+MN_HD MN_INLINE int game_start_lives(int g) {
+  switch (g) { case G_BREAKOUT: return 5; case G_SEAQUEST: return 4; case G_SPACE_INVADERS: return 3; case G_MS_PACMAN: return 3;
+    case G_ASTERIX: return 3; case G_ASTEROIDS: return 4; case G_GOPHER: return 3; case G_GRAVITAR: return 6;
+    case G_MONTEZUMA: return 6; case G_YARS: return 4; default: return 0; }
+}
+MN_HD MN_INLINE int game_start_actions(int g) {   // all are FIRE
+  switch (g) { case G_ASTERIX: return 1; case G_GOPHER: return 1; case G_GRAVITAR: return 16; case G_YARS: return 1; default: return 0; }
+}
+
+// ALE action enum -> stick bits: 1 up, 2 down, 4 left, 8 right, 16 fire (actions 0..17), 32 = console reset (40)
+MN_HD MN_INLINE uint32_t action_bits(int a) {
+  if (a == 40) return 32u;
+  if (a < 0 || a > 17) return 0u;
+  // per action: nibble-free table packed as 18 x 5 bits
+  const uint8_t t[18] = {0, 16, 1, 8, 4, 2, 9, 5, 10, 6, 17, 24, 20, 18, 25, 21, 26, 22};
+  return t[a];
+}
+MN_HD MN_INLINE void latch_inputs(EnvState& s, int action) {
+  const uint32_t b = action_bits(action);
+  s.swchb = (b & 32) ? 0x3E : 0x3F;
+  if (s.ctrl == CTRL_JOYSTICK) {
+    s.swcha = uint8_t(0xFF & ~(((b & 1) ? 0x10 : 0) | ((b & 2) ? 0x20 : 0) | ((b & 4) ? 0x40 : 0) | ((b & 8) ? 0x80 : 0)));
+    s.flags = (s.flags | F_INPT5 | F_INPT4) & ~((b & 16) ? F_INPT4 : 0u);
+    s.analog[0] = s.analog[1] = s.analog[2] = s.analog[3] = MN_RES_MAX;
+  } else {
+    int32_t p = s.left_paddle + ((b & 8) ? -MN_PADDLE_DELTA : (b & 4) ? MN_PADDLE_DELTA : 0);
+    p = p < MN_PADDLE_MIN ? MN_PADDLE_MIN : p > MN_PADDLE_MAX ? MN_PADDLE_MAX : p;
+    s.left_paddle = p;
+    const bool swap = (s.ctrl == CTRL_PADDLES_SWAPPED);
+    s.analog[0] = swap ? s.right_paddle : s.left_paddle;
+    s.analog[1] = swap ? s.left_paddle : s.right_paddle;
+    s.analog[2] = MN_RES_MIN; s.analog[3] = MN_RES_MIN;
+    s.swcha = uint8_t((b & 16) ? (swap ? 0xBF : 0x7F) : 0xFF);
+    s.flags |= F_INPT4 | F_INPT5;
+  }
+}
+MN_HD MN_INLINE void ale_emulate(Ctx& c, int action, int frames) {
+  EnvState& s = *c.s;
+  if (s.ctrl == CTRL_JOYSTICK) latch_inputs(s, action);
+  for (int f = 0; f < frames; ++f) {
+    if (s.ctrl != CTRL_JOYSTICK) latch_inputs(s, action);
+    run_frame(c);
+    game_observe(c);
+  }
+}
+
+MN_HD MN_INLINE void console_reset(Ctx& c, uint32_t rnd) {
+  EnvState& s = *c.s;
+  s.cycles = 0;
+  // RIOT
+  s.timer = uint8_t(25 + (rnd % 75)); s.tshift = 6; s.timer_set_cycle = 0; s.irq_reset_cycle = 0; s.ddra = 0; s.ddrb = 0;
+  // TIA
+  s.clk_frame_start = 0; s.clk_last_update = 0; s.clks_to_eol = 228; s.vsync_finish_clk = MN_NEVER; s.fb_pos = 0;
+  s.last_hmove_clk = 0; s.dump_disabled_cycle = 0; s.pf = 0; s.collision = 0;
+  s.flags &= (F_TERMINAL | F_STARTED | F_INPT4 | F_INPT5);
+  s.vsync = s.vblank = s.nusiz0 = s.nusiz1 = s.ctrlpf = s.enabled = 0;
+  for (int k = 0; k < 4; ++k) s.col[k] = 0;
+  s.grp0 = s.grp1 = s.dgrp0 = s.dgrp1 = s.cur_grp0 = s.cur_grp1 = 0;
+  for (int k = 0; k < 5; ++k) { s.pos[k] = 0; s.hm[k] = 0; }
+  for (int i = 0; i < 2 * MN_FRAME_BYTES; ++i) c.fb[i] = 0;
+  // cartridge
+  s.bank = (s.cart == CART_F8) ? 1 : 0; s.slice0 = 4; s.slice1 = 5; s.slice2 = 6;
+  // CPU
+  s.A = s.X = s.Y = 0; s.SP = 0xFF; unpack_ps(s, 0x20);
+  const uint32_t lo = bus_read(c, 0xFFFC);
+  s.PC = uint16_t(lo | (bus_read(c, 0xFFFD) << 8));
+}
+
+// ALE reset_game(): console reset, 60 NOOP frames, 4 frames of the RESET switch, per-game start actions
+MN_HD MN_INLINE void ale_reset(Ctx& c) {
+  EnvState& s = *c.s;
+  s.episode_frame_number = 0;
+  s.left_paddle = s.right_paddle = MN_PADDLE_DEFAULT;
+  console_reset(c, rng_next(s.rng));
+  ale_emulate(c, 0, 60);
+  ale_emulate(c, 40, 4);
+  s.score = 0; s.reward = 0; s.flags &= ~(F_TERMINAL | F_STARTED); s.lives = game_start_lives(s.game);
+  const int ns = game_start_actions(s.game);
+  for (int i = 0; i < ns; ++i) ale_emulate(c, 1, 1);
+}
+// ALE act(): one frame; frozen (reward 0, nothing emulated) once the episode is over
+MN_HD MN_INLINE int32_t ale_act(Ctx& c, int action) {
+  EnvState& s = *c.s;
+  rng_advance(s.rng); rng_advance(s.rng);
+  if (s.flags & F_TERMINAL) return 0;
+  ale_emulate(c, action, 1);
+  s.frame_number++; s.episode_frame_number++;
+  return s.reward;
+}
+// first-time construction: ALE seeds its RNG, fills RIOT RAM with garbage, then resets once (loadROM)
+MN_HD MN_INLINE void ale_power_on(Ctx& c, uint32_t seed) {
+  EnvState& s = *c.s;
+  rng_seed(s.rng, seed);
+  for (int i = 0; i < 128; ++i) ram_at(c, i) = uint8_t(rng_next(s.rng));
+  s.flags = 0; s.frame_number = 0; s.ring_head = 0;
+  ale_reset(c);
+}
+
+}  // namespace mn
