@@ -1,0 +1,117 @@
+/* manette_b200 -- C ABI of the B200-native environment pool.
+ *
+ * Drop-in boundary for the reference's env pool:
+ *   runners.py:7-50          Runners(tab_rep, EmulatorRunner, emulators, workers, variables)
+ *                            start / stop / get_shared_variables / update_environments / wait_updated
+ *   emulator_runner.py:19-42 EmulatorRunner._run        (FiGAR repeat loop)
+ *   atari_emulator.py:17-136 AtariEmulator               (get_initial_state / next / get_legal_actions)
+ *   exploration_policy.py:70-116 ExplorationPolicy.choose_next_actions   (mn_sample_figar)
+ *   paac.py:176,180,226-231 + actor_learner.py:108-114   (mn_nstep)
+ *
+ * Conventions: every call returns 0 on success, <0 on error (mn_last_error() gives the text);
+ * no exceptions cross the boundary; all calls on one handle come from one host thread; device
+ * work is enqueued on the caller-supplied stream (a cudaStream_t passed as void*, NULL = default).
+ * Pointers named *_dev are device pointers, *_host host pointers.  No torch types anywhere.
+ */
+#ifndef MANETTE_B200_H
+#define MANETTE_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mn_pool* mn_handle;
+
+/* one contiguous group of environments running the same cartridge */
+typedef struct {
+  const char* name;          /* rom file stem, e.g. "breakout" (selects the per-game reward/terminal rules) */
+  const uint8_t* rom;        /* cartridge image (host) */
+  int rom_size;
+  int n_envs;                /* environments in this group */
+} mn_game;
+
+typedef struct {
+  int device;                /* CUDA device ordinal */
+  int n_games;
+  const mn_game* games;      /* groups are laid out back to back: env ids 0..N-1 */
+  int rgb;                   /* args.rgb                    (atari_emulator.py:42-44) */
+  int single_life_episodes;  /* args.single_life_episodes   (atari_emulator.py:34,126-130) */
+  int random_start;          /* args.random_start           (atari_emulator.py:33,74-77) */
+  int random_seed;           /* args.random_seed; ALE seed of env e = random_seed * (env_id_offset + e + 1) (:20) */
+  int env_id_offset;         /* global id of local env 0 when the pool is one shard of a multi-GPU job */
+  int nb_choices;            /* K = len(tab_rep), 1..32; 0 with tab_rep NULL = plain PAAC ([0]) until mn_set_tab_rep */
+  const int* tab_rep;        /* ExplorationPolicy.get_tab_repetitions() (exploration_policy.py:56-62) */
+  int envs_per_warp;         /* tuning: 1,2,4,8,16,32 lanes of a warp that own an environment (0 = default) */
+} mn_config;
+
+/* device-resident arrays (the reference's five shared variables, paac.py:97-102, + index forms) */
+typedef struct {
+  int n_envs, num_actions /* A = max over games */, nb_choices, depth /* 1 gray, 3 rgb */;
+  uint8_t* states;           /* (N, 84, 84, 4*depth) NHWC, channel c = d*4 + k, k oldest -> newest */
+  float* rewards;            /* (N,)  raw reward summed over the macro step */
+  float* terminals;          /* (N,)  0.0 / 1.0 */
+  float* actions;            /* (N, A) one-hot, written by the learner */
+  float* repetitions;        /* (N, K) one-hot, written by the learner (allocation holds K = 32) */
+  int32_t* action_idx;       /* (N,)  index form (used instead of the one-hots when use_indices != 0) */
+  int32_t* repetition_idx;   /* (N,) */
+  int32_t* next_calls;       /* (N,)  number of next() calls each env executed in the last macro step */
+  uint8_t* frames;           /* (N, 2, 210, 160) raw palette-index screens of the last two frames */
+  uint8_t* ring;             /* (N, 4, 84, 84, depth) observation ring */
+} mn_buffers;
+
+const char* mn_last_error(void);
+int mn_create(const mn_config* cfg, mn_handle* out);
+int mn_destroy(mn_handle h);
+int mn_get_buffers(mn_handle h, mn_buffers* out);
+/* Runners(tab_rep, ...) (runners.py:11): the repetition table may arrive after the emulators were built */
+int mn_set_tab_rep(mn_handle h, const int* tab_rep, int nb_choices);
+/* AtariEmulator.get_legal_actions() of the game of environment `env`; returns count, fills out[<=18] */
+int mn_legal_actions(mn_handle h, int env, int32_t* out);
+
+/* N x AtariEmulator.get_initial_state() (paac.py:98): states filled, rewards/terminals zeroed */
+int mn_reset_all(mn_handle h, void* stream);
+/* Runners.update_environments(): one FiGAR macro step of every environment, asynchronous */
+int mn_step_async(mn_handle h, int use_indices, void* stream);
+/* Runners.wait_updated(): blocks until the macro step finished; reports sticky CUDA / emulator errors */
+int mn_wait(mn_handle h);
+/* same macro step with HOST arrays, copies inside: actions (N,A) f32, repetitions (N,K) f32 in;
+ * states (N,84,84,4*depth) u8, rewards (N,) f32, terminals (N,) f32 out.  Blocking. */
+int mn_step_host(mn_handle h, const float* actions_host, const float* repetitions_host, uint8_t* states_host,
+                 float* rewards_host, float* terminals_host, void* stream);
+
+/* single-environment facade (test.py:61-109 style callers): blocking */
+int mn_env_reset(mn_handle h, int env, void* stream);                       /* get_initial_state() */
+int mn_env_next(mn_handle h, int env, int action_index, float* reward, int* terminal, void* stream); /* next(a) */
+
+/* parity taps (blocking device->host copies) */
+int mn_get_ram(mn_handle h, int env, uint8_t* out128_host);
+int mn_get_screen(mn_handle h, int env, uint8_t* out33600_host);            /* current raw frame, palette indices */
+int mn_get_cpu_state(mn_handle h, int env, int32_t* out10_host);            /* A X Y SP PC PS cycles scanlines bank timer */
+int mn_get_lives(mn_handle h, int env, int* lives, int* game_over, int* frame_number);
+int mn_total_next_calls(mn_handle h, int64_t* out);                         /* since creation */
+int mn_palette(uint8_t* gray128_host, uint8_t* rgb128x3_host);
+/* start no-ops of episode `episode` of global environment `global_env` when random_start is on.  The
+ * reference draws them from unseeded random.randint(0, 30) (atari_emulator.py:75); here they are a
+ * reproducible function so a CPU oracle can be fed the same schedule.  Returns 0..30. */
+int mn_start_noops(uint32_t seed, uint32_t global_env, uint32_t episode);
+
+/* K3 stand-alone: max of two raw index frames -> luminance/RGB -> 84x84 nearest.  frames_dev (n,2,210,160),
+ * planes_dev (n,84,84,depth) */
+int mn_preprocess(const uint8_t* frames_dev, uint8_t* planes_dev, int n, int rgb, void* stream);
+/* K4: ExplorationPolicy.choose_next_actions.  mode 0 multinomial, 1 e-greedy, 2 argmax.
+ * pi_dev (N,A) f32, rho_dev (N,K) f32; outputs may be NULL */
+int mn_sample_figar(const float* pi_dev, const float* rho_dev, int n, int a, int k, int mode, float epsilon,
+                    uint64_t seed, uint32_t step, int32_t* action_idx_dev, int32_t* rep_idx_dev,
+                    float* action_onehot_dev, float* rep_onehot_dev, void* stream);
+/* K5: reward clip + n-step return / advantage.  rewards/terminals/values (T,N) f32, bootstrap (N,) f32 */
+int mn_nstep(const float* rewards_dev, const float* terminals_dev, const float* values_dev, const float* bootstrap_dev,
+             double gamma, int clip, int t, int n, float* y_dev, float* adv_dev, void* stream);
+
+/* kernels launched since creation (bench.py's gpu_launches) */
+int mn_launch_count(mn_handle h, int64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

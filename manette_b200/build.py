@@ -1,0 +1,38 @@
+"""Builds manette_b200/libmanette_b200.so (the CUDA kernels + C ABI) in-tree with nvcc for sm_100a only."""
+import os
+import shutil
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libmanette_b200.so")
+SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("pool.cu",)]
+HEADERS = [os.path.join(_PKG, "csrc", f) for f in ("emu_core.cuh", "atari_env.cuh", "decode_tables.h", "game_db.h")] + \
+          [os.path.join(os.path.dirname(_PKG), "include", "manette_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.exists(s) and os.path.getmtime(s) > t for s in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    """Compile if the library is missing or older than its sources.  Returns the library path."""
+    if force or stale():
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+        subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

@@ -113,8 +113,7 @@ struct EnvState {
   int32_t host_lives;   // atari_emulator.py:121 self.lives
   uint8_t ring_head;    // ObservationPool.current_observation_index
   uint8_t game, cart, ctrl;
-  uint8_t ram[128];
-};
+};   // 168 bytes; the 128 bytes of RIOT RAM live beside it (Ctx::ram)
 
 // per-lane working context (pointers to where the pieces live while a kernel runs)
 struct Ctx {

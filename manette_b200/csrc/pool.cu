@@ -1,0 +1,902 @@
+// manette_b200 -- the B200-native environment pool: kernels + C ABI (include/manette_b200.h).
+//
+// Replaces the reference's multi-process ALE worker pool (runners.py:7-50, emulator_runner.py:19-42,
+// atari_emulator.py:17-136) with device-resident emulator state.  One macro step
+// (Runners.update_environments) is a short, fixed sequence of launches on the caller's stream:
+//
+//   k_begin_step     decode (action, repetition) of every env, build the round-0 work list
+//   repeat max(tab_rep)+1 times:
+//     k_round        one next() (= 4 emulated frames) for every env still on the work list; envs that
+//                    still have repetitions left and are not terminal are COMPACTED into the next
+//                    round's list, terminal ones into the reset list          (emulator_runner.py:26-40)
+//     k_push_frames  K3: max of the two pooled frames -> luminance/RGB -> 84x84 nearest -> ring slot
+//   k_round(reset)   reset_game + start no-ops for the envs on the reset list   (atari_emulator.py:70-77)
+//   4 x { k_round(initial), k_push_frames }                                     (atari_emulator.py:105-107)
+//   k_emit           ring -> stacked NHWC states (uint8x16 stores), rewards, terminals
+//
+// Work lists are per game (one cartridge image per thread block, staged in shared memory) and are
+// spread evenly over a fixed number of warps, so later FiGAR rounds -- fewer live envs -- run with
+// fewer envs per warp (less opcode divergence) instead of with idle warps.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/manette_b200.h"
+#include "atari_env.cuh"
+#include "decode_tables.h"
+#include "game_db.h"
+
+namespace mn {
+
+#define MN_MAX_GAMES 16
+#define MN_WARPS_PER_BLOCK 8
+#define MN_THREADS (MN_WARPS_PER_BLOCK * 32)
+#define MN_CORE_WORDS 43   // EnvState (42 words) padded to an odd stride: conflict-free across slots
+#define MN_PLANE (MN_IMG * MN_IMG)
+
+static_assert(sizeof(EnvState) == 168, "EnvState layout changed: update MN_CORE_WORDS");
+
+// PIL Image.resize((84,84), NEAREST) column map for a 160-wide source (atari_emulator.py:84); rows
+// are floor((y + 0.5) * 2.5).  Golden copy: tests/golden/resize_lut.npz.
+__constant__ uint8_t c_xmap[MN_IMG] = {
+    0,  2,  4,  6,  8,  10, 12, 14, 16, 18, 20,  21,  23,  25,  27,  29,  31,  33,  35,  37,  39,
+    40, 42, 44, 46, 48, 50, 52, 54, 56, 58, 60,  61,  63,  65,  67,  69,  71,  73,  75,  77,  79,
+    80, 82, 84, 86, 88, 90, 92, 94, 96, 98, 99,  101, 103, 105, 107, 109, 111, 113, 115, 117, 119,
+    120, 122, 124, 126, 128, 130, 132, 134, 136, 138, 139, 141, 143, 145, 147, 149, 151, 153, 155, 157, 159};
+
+// NTSC palette of the emulated TIA (ALE getScreenRGB), index = colour byte >> 1
+static const uint32_t h_ntsc[128] = {
+    0x000000, 0x4a4a4a, 0x6f6f6f, 0x8e8e8e, 0xaaaaaa, 0xc0c0c0, 0xd6d6d6, 0xececec, 0x484800, 0x69690f, 0x86861d,
+    0xa2a22a, 0xbbbb35, 0xd2d240, 0xe8e84a, 0xfcfc54, 0x7c2c00, 0x904811, 0xa26221, 0xb47a30, 0xc3903d, 0xd2a44a,
+    0xdfb755, 0xecc860, 0x901c00, 0xa33915, 0xb55328, 0xc66c3a, 0xd5824a, 0xe39759, 0xf0aa67, 0xfcbc74, 0x940000,
+    0xa71a1a, 0xb83232, 0xc84848, 0xd65c5c, 0xe46f6f, 0xf08080, 0xfc9090, 0x840064, 0x97197a, 0xa8308f, 0xb846a2,
+    0xc659b3, 0xd46cc3, 0xe07cd2, 0xec8ce0, 0x500084, 0x68199a, 0x7d30ad, 0x9246c0, 0xa459d0, 0xb56ce0, 0xc57cee,
+    0xd48cfc, 0x140090, 0x331aa3, 0x4e32b5, 0x6848c6, 0x7f5cd5, 0x956fe3, 0xa980f0, 0xbc90fc, 0x000094, 0x181aa7,
+    0x2d32b8, 0x4248c8, 0x545cd6, 0x656fe4, 0x7580f0, 0x8490fc, 0x001c88, 0x183b9d, 0x2d57b0, 0x4272c2, 0x548ad2,
+    0x65a0e1, 0x75b5ef, 0x84c8fc, 0x003064, 0x185080, 0x2d6d98, 0x4288b0, 0x54a0c5, 0x65b7d9, 0x75cceb, 0x84e0fc,
+    0x004030, 0x18624e, 0x2d8169, 0x429e82, 0x54b899, 0x65d1ae, 0x75e7c2, 0x84fcd4, 0x004400, 0x1a661a, 0x328432,
+    0x48a048, 0x5cba5c, 0x6fd26f, 0x80e880, 0x90fc90, 0x143c00, 0x355f18, 0x527e2d, 0x6e9c42, 0x87b754, 0x9ed065,
+    0xb4e775, 0xc8fc84, 0x303800, 0x505916, 0x6d762b, 0x88923e, 0xa0ab4f, 0xb7c25f, 0xccd86e, 0xe0ec7c, 0x482c00,
+    0x694d14, 0x866a26, 0xa28638, 0xbb9f47, 0xd2b656, 0xe8cc63, 0xfce070};
+// packed per palette entry: byte0 luminance, byte1 R, byte2 G, byte3 B
+__constant__ uint32_t c_pal[128];
+
+static void host_palette(uint8_t* gray, uint8_t* rgb) {
+  for (int i = 0; i < 128; ++i) {
+    const uint8_t r = (h_ntsc[i] >> 16) & 0xFF, g = (h_ntsc[i] >> 8) & 0xFF, b = h_ntsc[i] & 0xFF;
+    // ALE's luminance: truncation of a double sum whose terms were float products
+    gray[i] = uint8_t(((float)r * 0.2989) + ((float)g * 0.5870) + ((float)b * 0.1140));
+    rgb[3 * i] = r; rgb[3 * i + 1] = g; rgb[3 * i + 2] = b;
+  }
+}
+
+struct GameDev {
+  int32_t rom_off, rom_size, game_id, cart, ctrl;
+  int32_t env0, n_envs;      // env ids [env0, env0 + n_envs)
+  int32_t blk0, n_blks;      // blocks of a k_round launch that serve this game
+  int32_t n_actions;
+  uint8_t actions[20];
+};
+
+struct PoolDev {             // kernel argument block (by value)
+  GameDev games[MN_MAX_GAMES];
+  int32_t n_games, n_envs, slots /* env slots per warp */, depth, num_actions, nb_choices;
+  int32_t single_life, random_start, seed, env_id_offset;
+  int32_t tab_rep[32];
+  const uint8_t* roms;
+  EnvState* env;
+  uint8_t* ram;              // (N,128)
+  uint8_t* frames;           // (N,2,210,160)
+  uint8_t* ring;             // (N,4,84,84,D)
+  uint8_t* states;           // (N,84,84,4D)
+  float *rewards, *terminals, *actions, *repetitions;
+  int32_t *action_idx, *repetition_idx, *next_calls;
+  // per-step bookkeeping
+  int32_t* cur_action;       // ALE action enum of the running macro action
+  int32_t* rep_left;
+  int32_t* reward_acc;
+  uint8_t* over;
+  uint8_t* push_info;        // bits 0-1 ring slot, bits 2-3 pool mode (0 both, 1 buffer 0 only, 2 buffer 1 only)
+  uint32_t* episode;         // episodes started so far (start no-op schedule)
+  uint8_t* env_game;
+  int32_t* lists;            // 3 x N : work list A, work list B, reset list   (regions per game = env id ranges)
+  int32_t* counts;           // 3 x MN_MAX_GAMES
+  int32_t* error;            // sticky: 1 = episode over right after reset (atari_emulator.py:108-109)
+  unsigned long long* total_next;
+  const Tables* tables;
+};
+
+enum { ROUND_FIGAR = 0, ROUND_RESET = 1, ROUND_INITIAL = 2, ROUND_POWER_ON = 3, ROUND_SINGLE = 4 };
+
+// ----------------------------------------------------------------------------- kernels
+__global__ void k_begin_step(PoolDev p, int use_indices) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < MN_MAX_GAMES * 3) {
+    // list 0 starts full, list 1 and the reset list empty
+    const int which = e / MN_MAX_GAMES, g = e % MN_MAX_GAMES;
+    p.counts[e] = (which == 0 && g < p.n_games) ? p.games[g].n_envs : 0;
+  }
+  if (e >= p.n_envs) return;
+  int a = 0, r = 0;
+  if (use_indices) { a = p.action_idx[e]; r = p.repetition_idx[e]; }
+  else {   // np.argmax of the one-hot rows (exploration_policy.py:18-19): first maximum
+    const float* pa = p.actions + size_t(e) * p.num_actions;
+    float best = pa[0];
+    for (int i = 1; i < p.num_actions; ++i) if (pa[i] > best) { best = pa[i]; a = i; }
+    const float* pr = p.repetitions + size_t(e) * p.nb_choices;
+    best = pr[0];
+    for (int i = 1; i < p.nb_choices; ++i) if (pr[i] > best) { best = pr[i]; r = i; }
+  }
+  const GameDev& g = p.games[p.env_game[e]];
+  if (a < 0) a = 0; if (a >= g.n_actions) a = g.n_actions - 1;
+  if (r < 0) r = 0; if (r >= p.nb_choices) r = p.nb_choices - 1;
+  p.cur_action[e] = g.actions[a];
+  p.rep_left[e] = p.tab_rep[r];
+  p.reward_acc[e] = 0;
+  p.over[e] = 0;
+  p.next_calls[e] = 0;
+  p.lists[e] = e;
+}
+
+// fills a list with every env (reset_all / power-on)
+__global__ void k_fill_list(PoolDev p, int which) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < MN_MAX_GAMES * 3) {
+    const int w = e / MN_MAX_GAMES, g = e % MN_MAX_GAMES;
+    p.counts[e] = (w == which && g < p.n_games) ? p.games[g].n_envs : 0;
+  }
+  if (e >= p.n_envs) return;
+  p.lists[size_t(which) * p.n_envs + e] = e;
+  p.reward_acc[e] = 0; p.over[e] = 0; p.next_calls[e] = 0; p.rep_left[e] = 0; p.cur_action[e] = 0;
+}
+__global__ void k_single_list(PoolDev p, int which, int env, int ale_action) {
+  if (threadIdx.x < MN_MAX_GAMES * 3) p.counts[threadIdx.x] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int g = p.env_game[env];
+    p.counts[which * MN_MAX_GAMES + g] = 1;
+    p.lists[size_t(which) * p.n_envs + p.games[g].env0] = env;
+    p.cur_action[env] = ale_action; p.rep_left[env] = 0; p.reward_acc[env] = 0; p.over[env] = 0; p.next_calls[env] = 0;
+  }
+}
+
+// One round of emulation for the envs on list `in`.  Dynamic shared memory:
+//   [rom | tables | core slots (8 warps x slots x 43 words) | ram (8 warps x slots x 128 B, word-interleaved)]
+__global__ void __launch_bounds__(MN_THREADS, 2) k_round(PoolDev p, int mode, int in, int out) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  // ---- which game does this block serve
+  int gi = 0;
+  while (gi + 1 < p.n_games && int(blockIdx.x) >= p.games[gi + 1].blk0) ++gi;
+  const GameDev& G = p.games[gi];
+  const int count = p.counts[in * MN_MAX_GAMES + gi];
+  const int j = blockIdx.x - G.blk0;
+  const int lo = int((long long)count * j / G.n_blks), hi = int((long long)count * (j + 1) / G.n_blks);
+  if (hi <= lo) return;   // whole block idle (uniform)
+  const int rom_bytes = (G.rom_size + 15) & ~15;
+  uint8_t* s_rom = smem;
+  Tables* s_tab = reinterpret_cast<Tables*>(smem + rom_bytes);
+  uint32_t* s_core = reinterpret_cast<uint32_t*>(smem + rom_bytes + sizeof(Tables));
+  uint8_t* s_ram = reinterpret_cast<uint8_t*>(s_core + MN_WARPS_PER_BLOCK * p.slots * MN_CORE_WORDS);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.roms + G.rom_off);
+    uint4* dst = reinterpret_cast<uint4*>(s_rom);
+    for (int i = threadIdx.x; i < rom_bytes / 16; i += blockDim.x) dst[i] = src[i];
+    const uint32_t* ts = reinterpret_cast<const uint32_t*>(p.tables);
+    uint32_t* td = reinterpret_cast<uint32_t*>(s_tab);
+    for (int i = threadIdx.x; i < int(sizeof(Tables) / 4); i += blockDim.x) td[i] = ts[i];
+  }
+  __syncthreads();
+  // ---- my env
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = hi - lo;
+  const int wlo = lo + m * warp / MN_WARPS_PER_BLOCK, whi = lo + m * (warp + 1) / MN_WARPS_PER_BLOCK;
+  if (lane >= whi - wlo) return;
+  const int e = p.lists[size_t(in) * p.n_envs + G.env0 + wlo + lane];
+  const int slot = warp * p.slots + lane;
+  EnvState* s = reinterpret_cast<EnvState*>(s_core + slot * MN_CORE_WORDS);
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.env + e);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s);
+#pragma unroll 6
+    for (int i = 0; i < int(sizeof(EnvState) / 4); ++i) dst[i] = src[i];
+  }
+  Ctx c;
+  c.s = s; c.rom = s_rom; c.tab = s_tab;
+  c.ram = s_ram + warp * p.slots * 128 + lane * 4;
+  c.ram_stride = p.slots * 4;
+  c.fb = p.frames + size_t(e) * (2 * MN_FRAME_BYTES);
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.ram + size_t(e) * 128);
+    for (int i = 0; i < 32; ++i) *reinterpret_cast<uint32_t*>(c.ram + i * c.ram_stride) = src[i];
+  }
+  const bool single_life = p.single_life != 0;
+  if (mode == ROUND_POWER_ON) {
+    s->game = uint8_t(G.game_id); s->cart = uint8_t(G.cart); s->ctrl = uint8_t(G.ctrl);
+    s->host_lives = 0;
+    // atari_emulator.py:20: ALE seed = random_seed * (actor_id + 1); loadROM resets once
+    ale_power_on(c, uint32_t(p.seed) * uint32_t(p.env_id_offset + e + 1));
+    s->host_lives = s->lives;
+    p.episode[e] = 0;
+  } else if (mode == ROUND_RESET) {
+    const uint32_t ep = p.episode[e];
+    const int noops = p.random_start ? int(start_noops(uint32_t(p.seed), uint32_t(p.env_id_offset + e), ep)) : 0;
+    p.episode[e] = ep + 1;
+    env_new_game(c, noops);
+  } else {
+    const int action = (mode == ROUND_INITIAL) ? int(G.actions[0]) : p.cur_action[e];
+    const NextOut o = env_next(c, action, single_life);
+    const int head = s->ring_head;
+    s->ring_head = uint8_t((head + 1) & (MN_STACK - 1));
+    const int pool_mode = o.pool_single ? ((s->flags & F_CURFB) ? 2 : 1) : 0;
+    p.push_info[e] = uint8_t(head | (pool_mode << 2));
+    if (mode == ROUND_INITIAL) {
+      if (out < 0 && o.terminal) atomicExch(p.error, 1);   // last of the four start frames: 'This should never happen.'
+    } else {
+      p.reward_acc[e] += o.reward;
+      p.next_calls[e] += 1;
+      atomicAdd(p.total_next, 1ull);
+      if (o.terminal) {
+        p.over[e] = 1;
+        if (mode == ROUND_FIGAR) {
+          const int k = atomicAdd(&p.counts[2 * MN_MAX_GAMES + gi], 1);
+          p.lists[size_t(2) * p.n_envs + G.env0 + k] = e;
+        }
+      } else if (mode == ROUND_FIGAR) {
+        const int left = p.rep_left[e];
+        if (left > 0) {
+          p.rep_left[e] = left - 1;
+          const int k = atomicAdd(&p.counts[out * MN_MAX_GAMES + gi], 1);
+          p.lists[size_t(out) * p.n_envs + G.env0 + k] = e;
+        }
+      }
+    }
+  }
+  // ---- write the machine back
+  {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(p.env + e);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(s);
+#pragma unroll 6
+    for (int i = 0; i < int(sizeof(EnvState) / 4); ++i) dst[i] = src[i];
+    uint32_t* rd = reinterpret_cast<uint32_t*>(p.ram + size_t(e) * 128);
+    for (int i = 0; i < 32; ++i) rd[i] = *reinterpret_cast<uint32_t*>(c.ram + i * c.ram_stride);
+  }
+}
+
+__global__ void k_clear_counts(PoolDev p, int which) {
+  if (threadIdx.x < MN_MAX_GAMES) p.counts[which * MN_MAX_GAMES + threadIdx.x] = 0;
+}
+
+// K3 core: one output word = 4 horizontally adjacent pixels of one channel-interleaved plane row.
+// a, b: the two raw palette-index screens (210x160).  mode 0: max of both, 1: a only, 2: b only.
+template <int D>
+__device__ __forceinline__ void preprocess_plane(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int mode,
+                                                 uint8_t* __restrict__ plane, int tid, int nthreads) {
+  if (mode == 1) b = a; else if (mode == 2) a = b;
+  if (D == 1) {
+    uint32_t* out = reinterpret_cast<uint32_t*>(plane);
+    for (int w = tid; w < MN_PLANE / 4; w += nthreads) {
+      const int y = w / (MN_IMG / 4), xq = (w - y * (MN_IMG / 4)) * 4;
+      const int row = ((2 * y + 1) * 5) >> 2;   // floor((y + 0.5) * 2.5)
+      const uint8_t* ra = a + row * MN_SCREEN_W;
+      const uint8_t* rb = b + row * MN_SCREEN_W;
+      uint32_t v = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int x = c_xmap[xq + k];
+        const uint32_t la = c_pal[ra[x] >> 1] & 0xFF, lb = c_pal[rb[x] >> 1] & 0xFF;
+        v |= (la > lb ? la : lb) << (8 * k);
+      }
+      out[w] = v;
+    }
+  } else {
+    // 84 x 84 x 3: one thread per pixel triple pair -> handle one pixel (3 bytes) at a time, 4 pixels = 3 words
+    uint32_t* out = reinterpret_cast<uint32_t*>(plane);
+    for (int w = tid; w < MN_PLANE / 4; w += nthreads) {
+      const int y = w / (MN_IMG / 4), xq = (w - y * (MN_IMG / 4)) * 4;
+      const int row = ((2 * y + 1) * 5) >> 2;
+      const uint8_t* ra = a + row * MN_SCREEN_W;
+      const uint8_t* rb = b + row * MN_SCREEN_W;
+      uint32_t px[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int x = c_xmap[xq + k];
+        const uint32_t ca = c_pal[ra[x] >> 1] >> 8, cb = c_pal[rb[x] >> 1] >> 8;   // 0x00BBGGRR
+        px[k] = __vmaxu4(ca, cb);
+      }
+      // bytes R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+      out[3 * w + 0] = px[0] | (px[1] << 24);
+      out[3 * w + 1] = (px[1] >> 8) | (px[2] << 16);
+      out[3 * w + 2] = (px[2] >> 16) | (px[3] << 8);
+    }
+  }
+}
+
+// K3 over a work list: one block per (game, list entry)
+template <int D>
+__global__ void __launch_bounds__(256) k_push_frames(PoolDev p, int in) {
+  // block -> env through the per-game list regions: blockIdx.x is an env-id-like position
+  const int pos = blockIdx.x;
+  int gi = 0;
+  while (gi + 1 < p.n_games && pos >= p.games[gi + 1].env0) ++gi;
+  const int k = pos - p.games[gi].env0;
+  if (k >= p.counts[in * MN_MAX_GAMES + gi]) return;
+  const int e = p.lists[size_t(in) * p.n_envs + pos];
+  const uint8_t info = p.push_info[e];
+  const uint8_t* fb = p.frames + size_t(e) * (2 * MN_FRAME_BYTES);
+  uint8_t* plane = p.ring + (size_t(e) * MN_STACK + (info & 3)) * (MN_PLANE * D);
+  preprocess_plane<D>(fb, fb + MN_FRAME_BYTES, info >> 2, plane, threadIdx.x, blockDim.x);
+}
+
+// K3 stand-alone (mn_preprocess)
+template <int D>
+__global__ void __launch_bounds__(256) k_preprocess(const uint8_t* __restrict__ frames, uint8_t* __restrict__ planes, int n) {
+  for (int e = blockIdx.x; e < n; e += gridDim.x) {
+    const uint8_t* fb = frames + size_t(e) * (2 * MN_FRAME_BYTES);
+    preprocess_plane<D>(fb, fb + MN_FRAME_BYTES, 0, planes + size_t(e) * (MN_PLANE * D), threadIdx.x, blockDim.x);
+  }
+}
+
+// ring -> stacked observation (environment.py:73-76): states[e][y][x][d*4 + k] = ring[(head + k) & 3][y][x][d],
+// 4 pixels per thread, 16-byte stores.  Also publishes rewards / terminals.
+template <int D>
+__global__ void __launch_bounds__(256) k_emit(PoolDev p, int env_lo, int env_hi, int publish) {
+  const int e = env_lo + blockIdx.x;
+  if (e >= env_hi) return;
+  const int head = p.env[e].ring_head;
+  const uint8_t* ring = p.ring + size_t(e) * MN_STACK * (MN_PLANE * D);
+  uint4* out = reinterpret_cast<uint4*>(p.states + size_t(e) * (MN_PLANE * D * MN_STACK));
+  for (int q = threadIdx.x; q < MN_PLANE / 4; q += blockDim.x) {
+    uint32_t in[MN_STACK][D];   // [k][word]: 4 pixels x D bytes of ring plane (head + k)
+#pragma unroll
+    for (int k = 0; k < MN_STACK; ++k) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(ring + size_t((head + k) & 3) * (MN_PLANE * D)) + q * D;
+#pragma unroll
+      for (int d = 0; d < D; ++d) in[k][d] = src[d];
+    }
+    if (D == 1) {
+      // 4x4 byte transpose: out word j = pixel j's 4 time steps
+      const uint32_t a = in[0][0], b = in[1][0], c2 = in[2][0], d2 = in[3][0];
+      const uint32_t ab_lo = __byte_perm(a, b, 0x5140), ab_hi = __byte_perm(a, b, 0x7362);   // a0 b0 a1 b1 | a2 b2 a3 b3
+      const uint32_t cd_lo = __byte_perm(c2, d2, 0x5140), cd_hi = __byte_perm(c2, d2, 0x7362);
+      uint4 o;
+      o.x = __byte_perm(ab_lo, cd_lo, 0x5410); o.y = __byte_perm(ab_lo, cd_lo, 0x7632);
+      o.z = __byte_perm(ab_hi, cd_hi, 0x5410); o.w = __byte_perm(ab_hi, cd_hi, 0x7632);
+      out[q] = o;
+    } else {
+      // 4 pixels x (3 colours x 4 steps) = 48 bytes = 3 x uint4
+      uint8_t bytes[MN_STACK][12];
+#pragma unroll
+      for (int k = 0; k < MN_STACK; ++k)
+#pragma unroll
+        for (int i = 0; i < 12; ++i) bytes[k][i] = uint8_t(in[k][i >> 2] >> (8 * (i & 3)));
+      uint32_t w[12];
+#pragma unroll
+      for (int px = 0; px < 4; ++px)
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+          w[px * 3 + d] = uint32_t(bytes[0][px * 3 + d]) | (uint32_t(bytes[1][px * 3 + d]) << 8) |
+                          (uint32_t(bytes[2][px * 3 + d]) << 16) | (uint32_t(bytes[3][px * 3 + d]) << 24);
+      out[3 * q + 0] = make_uint4(w[0], w[1], w[2], w[3]);
+      out[3 * q + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+      out[3 * q + 2] = make_uint4(w[8], w[9], w[10], w[11]);
+    }
+  }
+  if (publish && threadIdx.x == 0) {
+    p.rewards[e] = float(p.reward_acc[e]);
+    p.terminals[e] = p.over[e] ? 1.0f : 0.0f;
+  }
+}
+
+// ----------------------------------------------------------------------------- K4: FiGAR sampling
+struct Philox { uint32_t v[4]; };
+__device__ __forceinline__ Philox philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  Philox o; o.v[0] = c0; o.v[1] = c1; o.v[2] = c2; o.v[3] = c3;
+  return o;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return float(x >> 8) * (1.0f / 16777216.0f); }
+
+// exploration_policy.py:108-116: np.random.multinomial(1, p - epsneg) is an inverse-CDF draw
+__device__ __forceinline__ int draw_multinomial(const float* p, int k, float u) {
+  const float eps = 5.9604645e-08f;   // np.finfo(np.float32).epsneg
+  float cum = 0.f;
+  for (int j = 0; j < k; ++j) {
+    cum = __fadd_rn(cum, __fsub_rn(p[j], eps));
+    if (u < cum) return j;
+  }
+  return k - 1;
+}
+__device__ __forceinline__ int draw_argmax(const float* p, int k) {
+  int best = 0; float bv = p[0];
+  for (int j = 1; j < k; ++j) if (p[j] > bv) { bv = p[j]; best = j; }
+  return best;
+}
+__device__ __forceinline__ int draw_egreedy(const float* p, int k, float u_test, float u_pick, float eps) {
+  if (u_test < eps) { int i = int(u_pick * float(k)); return i < k ? i : k - 1; }
+  return draw_argmax(p, k);
+}
+__global__ void k_sample_figar(const float* __restrict__ pi, const float* __restrict__ rho, int n, int a, int k, int mode,
+                               float eps, uint32_t seed_lo, uint32_t seed_hi, uint32_t step, int32_t* a_idx, int32_t* r_idx,
+                               float* a_hot, float* r_hot) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const Philox x = philox4x32_10(uint32_t(e), step, 0u, 0u, seed_lo, seed_hi);
+  const float* pa = pi + size_t(e) * a;
+  const float* pr = rho + size_t(e) * k;
+  int ia, ir;
+  if (mode == 0) { ia = draw_multinomial(pa, a, u01(x.v[0])); ir = draw_multinomial(pr, k, u01(x.v[1])); }
+  else if (mode == 1) { ia = draw_egreedy(pa, a, u01(x.v[0]), u01(x.v[2]), eps); ir = draw_egreedy(pr, k, u01(x.v[1]), u01(x.v[3]), eps); }
+  else { ia = draw_argmax(pa, a); ir = draw_argmax(pr, k); }
+  if (a_idx) a_idx[e] = ia;
+  if (r_idx) r_idx[e] = ir;
+  if (a_hot) for (int j = 0; j < a; ++j) a_hot[size_t(e) * a + j] = (j == ia) ? 1.f : 0.f;
+  if (r_hot) for (int j = 0; j < k; ++j) r_hot[size_t(e) * k + j] = (j == ir) ? 1.f : 0.f;
+}
+
+// ----------------------------------------------------------------------------- K5: n-step returns
+// paac.py:176,180,226-231 + actor_learner.py:108-114.  The reference runs this recursion in float64
+// and feeds float32; so does this kernel (T sequential steps per env, one thread per env).
+__global__ void k_nstep(const float* __restrict__ rewards, const float* __restrict__ terminals, const float* __restrict__ values,
+                        const float* __restrict__ bootstrap, double gamma, int clip, int t_max, int n, float* __restrict__ y,
+                        float* __restrict__ adv) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  double R = double(bootstrap[e]);
+  for (int t = t_max - 1; t >= 0; --t) {
+    const size_t i = size_t(t) * n + e;
+    double r = double(rewards[i]);
+    if (clip) r = r > 1.0 ? 1.0 : (r < -1.0 ? -1.0 : r);
+    const double mask = double(1.0f - terminals[i]);
+    R = r + gamma * R * mask;
+    y[i] = float(R);
+    adv[i] = float(R - double(values[i]));
+  }
+}
+
+}  // namespace mn
+
+// ============================================================================= host side / C ABI
+using namespace mn;
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return -1; }
+#define CU(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(_e)); } while (0)
+
+struct mn_pool {
+  PoolDev d;
+  int device;
+  int max_rep;
+  size_t round_smem;
+  int round_grid;
+  cudaEvent_t done;
+  bool pending;
+  int64_t launches;
+  std::vector<void*> allocs;
+  uint8_t* pin_ram;
+  std::vector<int> env_game_host;
+  GameDev games_host[MN_MAX_GAMES];
+  Tables* tables_dev;
+  bool palette_ready;
+};
+
+static bool g_const_ready[64] = {false};
+
+static int upload_constants(int device) {
+  if (device >= 0 && device < 64 && g_const_ready[device]) return 0;
+  uint8_t gray[128], rgb[384];
+  host_palette(gray, rgb);
+  uint32_t pal[128];
+  for (int i = 0; i < 128; ++i) pal[i] = gray[i] | (uint32_t(rgb[3 * i]) << 8) | (uint32_t(rgb[3 * i + 1]) << 16) | (uint32_t(rgb[3 * i + 2]) << 24);
+  CU(cudaMemcpyToSymbol(c_pal, pal, sizeof(pal)));
+  if (device >= 0 && device < 64) g_const_ready[device] = true;
+  return 0;
+}
+
+template <typename T>
+static int dev_alloc(mn_pool* h, T** out, size_t count) {
+  void* ptr = nullptr;
+  cudaError_t e = cudaMalloc(&ptr, count * sizeof(T) > 0 ? count * sizeof(T) : 16);
+  if (e != cudaSuccess) return fail(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  e = cudaMemset(ptr, 0, count * sizeof(T));
+  if (e != cudaSuccess) return fail(std::string("cudaMemset: ") + cudaGetErrorString(e));
+  h->allocs.push_back(ptr);
+  *out = static_cast<T*>(ptr);
+  return 0;
+}
+
+extern "C" {
+
+const char* mn_last_error(void) { return g_err.c_str(); }
+
+int mn_palette(uint8_t* gray128_host, uint8_t* rgb128x3_host) { host_palette(gray128_host, rgb128x3_host); return 0; }
+
+int mn_start_noops(uint32_t seed, uint32_t global_env, uint32_t episode) { return int(start_noops(seed, global_env, episode)); }
+
+int mn_destroy(mn_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->done) cudaEventDestroy(h->done);
+  delete h;
+  return 0;
+}
+
+int mn_create(const mn_config* cfg, mn_handle* out) {
+  if (!cfg || !out) return fail("mn_create: null argument");
+  if (cfg->n_games < 1 || cfg->n_games > MN_MAX_GAMES) return fail("mn_create: n_games must be 1..16");
+  if (cfg->nb_choices < 0 || cfg->nb_choices > 32 || (cfg->nb_choices > 0 && !cfg->tab_rep)) return fail("mn_create: nb_choices must be 0..32 (with a tab_rep when > 0)");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) return fail("mn_create: no CUDA device (the product has no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail("mn_create: bad device ordinal");
+  CU(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major < 10) return fail("mn_create: this library is built for sm_100a (B200) only");
+  if (upload_constants(cfg->device)) return -1;
+
+  mn_pool* h = new mn_pool();
+  memset(&h->d, 0, sizeof(h->d));
+  h->device = cfg->device; h->done = nullptr; h->pending = false; h->launches = 0; h->pin_ram = nullptr;
+  PoolDev& d = h->d;
+  int n = 0, max_actions = 0;
+  size_t rom_total = 0, max_rom = 0;
+  for (int g = 0; g < cfg->n_games; ++g) {
+    const mn_game& mg = cfg->games[g];
+    if (!mg.rom || mg.rom_size < 2048 || mg.rom_size > 16384 || mg.n_envs < 1) { delete h; return fail("mn_create: bad game entry (rom 2K..16K, n_envs >= 1)"); }
+    GameDev& G = d.games[g];
+    G.game_id = game_id_from_name(mg.name ? mg.name : "");
+    const GameEntry& ge = game_db(G.game_id);
+    G.cart = detect_cart(mg.rom, size_t(mg.rom_size));
+    G.ctrl = ge.ctrl;
+    G.n_actions = ge.n_actions;
+    for (int i = 0; i < 18; ++i) G.actions[i] = ge.actions[i];
+    G.rom_off = int(rom_total); G.rom_size = mg.rom_size;
+    rom_total += (size_t(mg.rom_size) + 15) & ~size_t(15);
+    if (size_t(mg.rom_size) > max_rom) max_rom = mg.rom_size;
+    G.env0 = n; G.n_envs = mg.n_envs;
+    n += mg.n_envs;
+    if (G.n_actions > max_actions) max_actions = G.n_actions;
+  }
+  d.n_games = cfg->n_games; d.n_envs = n; d.depth = cfg->rgb ? 3 : 1; d.num_actions = max_actions;
+  d.nb_choices = cfg->nb_choices > 0 ? cfg->nb_choices : 1;
+  d.single_life = cfg->single_life_episodes; d.random_start = cfg->random_start; d.seed = cfg->random_seed; d.env_id_offset = cfg->env_id_offset;
+  h->max_rep = 0;
+  for (int i = 0; i < cfg->nb_choices; ++i) {
+    if (cfg->tab_rep[i] < 0 || cfg->tab_rep[i] > 1000) { delete h; return fail("mn_create: tab_rep entries must be 0..1000"); }
+    d.tab_rep[i] = cfg->tab_rep[i];
+    if (cfg->tab_rep[i] > h->max_rep) h->max_rep = cfg->tab_rep[i];
+  }
+  // env slots per warp: spread the pool over about 16 resident warps per SM
+  int slots = cfg->envs_per_warp;
+  if (slots <= 0) {
+    const int target_warps = prop.multiProcessorCount * 16;
+    slots = 1;
+    while (slots < 32 && n > target_warps * slots) slots *= 2;
+  }
+  if (slots != 1 && slots != 2 && slots != 4 && slots != 8 && slots != 16 && slots != 32) { delete h; return fail("mn_create: envs_per_warp must be 1,2,4,8,16 or 32"); }
+  d.slots = slots;
+  int blk = 0;
+  for (int g = 0; g < d.n_games; ++g) {
+    GameDev& G = d.games[g];
+    G.blk0 = blk;
+    G.n_blks = (G.n_envs + MN_WARPS_PER_BLOCK * slots - 1) / (MN_WARPS_PER_BLOCK * slots);
+    blk += G.n_blks;
+  }
+  h->round_grid = blk;
+  h->round_smem = ((max_rom + 15) & ~size_t(15)) + sizeof(Tables) + size_t(MN_WARPS_PER_BLOCK) * slots * (MN_CORE_WORDS * 4 + 128);
+  if (h->round_smem > size_t(prop.sharedMemPerBlockOptin)) { delete h; return fail("mn_create: shared memory budget exceeded"); }
+  CU(cudaFuncSetAttribute(k_round, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->round_smem)));
+
+  const size_t N = size_t(n), D = size_t(d.depth);
+  uint8_t* roms = nullptr;
+  int rc = 0;
+  rc |= dev_alloc(h, &roms, rom_total);
+  rc |= dev_alloc(h, &d.env, N);
+  rc |= dev_alloc(h, &d.ram, N * 128);
+  rc |= dev_alloc(h, &d.frames, N * 2 * MN_FRAME_BYTES);
+  rc |= dev_alloc(h, &d.ring, N * MN_STACK * MN_PLANE * D);
+  rc |= dev_alloc(h, &d.states, N * MN_STACK * MN_PLANE * D);
+  rc |= dev_alloc(h, &d.rewards, N);
+  rc |= dev_alloc(h, &d.terminals, N);
+  rc |= dev_alloc(h, &d.actions, N * size_t(d.num_actions));
+  rc |= dev_alloc(h, &d.repetitions, N * size_t(32));
+  rc |= dev_alloc(h, &d.action_idx, N);
+  rc |= dev_alloc(h, &d.repetition_idx, N);
+  rc |= dev_alloc(h, &d.next_calls, N);
+  rc |= dev_alloc(h, &d.cur_action, N);
+  rc |= dev_alloc(h, &d.rep_left, N);
+  rc |= dev_alloc(h, &d.reward_acc, N);
+  rc |= dev_alloc(h, &d.over, N);
+  rc |= dev_alloc(h, &d.push_info, N);
+  rc |= dev_alloc(h, &d.episode, N);
+  rc |= dev_alloc(h, &d.env_game, N);
+  rc |= dev_alloc(h, &d.lists, 3 * N);
+  rc |= dev_alloc(h, &d.counts, size_t(3 * MN_MAX_GAMES));
+  rc |= dev_alloc(h, &d.error, size_t(1));
+  rc |= dev_alloc(h, &d.total_next, size_t(1));
+  rc |= dev_alloc(h, &h->tables_dev, size_t(1));
+  if (rc) { mn_destroy(h); return -1; }
+  d.roms = roms;
+  d.tables = h->tables_dev;
+  {
+    Tables t;
+    build_tables(&t);
+    CU(cudaMemcpy(h->tables_dev, &t, sizeof(t), cudaMemcpyHostToDevice));
+    std::vector<uint8_t> eg(N);
+    h->env_game_host.resize(N);
+    for (int g = 0; g < d.n_games; ++g) {
+      CU(cudaMemcpy(roms + d.games[g].rom_off, cfg->games[g].rom, size_t(cfg->games[g].rom_size), cudaMemcpyHostToDevice));
+      for (int i = 0; i < d.games[g].n_envs; ++i) { eg[size_t(d.games[g].env0 + i)] = uint8_t(g); h->env_game_host[size_t(d.games[g].env0 + i)] = g; }
+    }
+    CU(cudaMemcpy(d.env_game, eg.data(), N, cudaMemcpyHostToDevice));
+  }
+  memcpy(h->games_host, d.games, sizeof(d.games));
+  CU(cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming));
+  // construct every AtariEmulator (atari_emulator.py:18-31): seed, RAM garbage, loadROM's reset
+  {
+    const int tb = 256, gb = (n + tb - 1) / tb > 1 ? (n + tb - 1) / tb : 1;
+    k_fill_list<<<gb, tb>>>(d, 0);
+    k_round<<<h->round_grid, MN_THREADS, h->round_smem>>>(d, ROUND_POWER_ON, 0, -1);
+    h->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+  }
+  *out = h;
+  return 0;
+}
+
+int mn_get_buffers(mn_handle h, mn_buffers* out) {
+  if (!h || !out) return fail("mn_get_buffers: null argument");
+  const PoolDev& d = h->d;
+  out->n_envs = d.n_envs; out->num_actions = d.num_actions; out->nb_choices = d.nb_choices; out->depth = d.depth;
+  out->states = d.states; out->rewards = d.rewards; out->terminals = d.terminals; out->actions = d.actions;
+  out->repetitions = d.repetitions; out->action_idx = d.action_idx; out->repetition_idx = d.repetition_idx;
+  out->next_calls = d.next_calls; out->frames = d.frames; out->ring = d.ring;
+  return 0;
+}
+
+int mn_set_tab_rep(mn_handle h, const int* tab_rep, int nb_choices) {
+  if (!h || !tab_rep || nb_choices < 1 || nb_choices > 32) return fail("mn_set_tab_rep: nb_choices must be 1..32");
+  for (int i = 0; i < nb_choices; ++i) if (tab_rep[i] < 0 || tab_rep[i] > 1000) return fail("mn_set_tab_rep: entries must be 0..1000");
+  if (h->pending) return fail("mn_set_tab_rep: a macro step is in flight");
+  h->max_rep = 0;
+  for (int i = 0; i < nb_choices; ++i) { h->d.tab_rep[i] = tab_rep[i]; if (tab_rep[i] > h->max_rep) h->max_rep = tab_rep[i]; }
+  h->d.nb_choices = nb_choices;
+  return 0;
+}
+
+int mn_legal_actions(mn_handle h, int env, int32_t* out) {
+  if (!h || env < 0 || env >= h->d.n_envs) return fail("mn_legal_actions: bad environment id");
+  const GameDev& G = h->games_host[h->env_game_host[size_t(env)]];
+  if (out) for (int i = 0; i < G.n_actions; ++i) out[i] = G.actions[i];
+  return G.n_actions;
+}
+
+}  // extern "C"
+
+// ---- launch helpers (host)
+static void launch_push(mn_pool* h, int in, cudaStream_t st) {
+  if (h->d.depth == 1) k_push_frames<1><<<h->d.n_envs, 256, 0, st>>>(h->d, in);
+  else k_push_frames<3><<<h->d.n_envs, 256, 0, st>>>(h->d, in);
+  h->launches++;
+}
+static void launch_round(mn_pool* h, int mode, int in, int out, cudaStream_t st) {
+  k_round<<<h->round_grid, MN_THREADS, h->round_smem, st>>>(h->d, mode, in, out);
+  h->launches++;
+}
+static void launch_emit(mn_pool* h, int lo, int hi, int publish, cudaStream_t st) {
+  if (h->d.depth == 1) k_emit<1><<<hi - lo, 256, 0, st>>>(h->d, lo, hi, publish);
+  else k_emit<3><<<hi - lo, 256, 0, st>>>(h->d, lo, hi, publish);
+  h->launches++;
+}
+// get_initial_state() for the envs on list `which` (atari_emulator.py:102-110)
+static void launch_initial_state(mn_pool* h, int which, cudaStream_t st) {
+  launch_round(h, ROUND_RESET, which, -1, st);
+  for (int i = 0; i < MN_STACK; ++i) {
+    launch_round(h, ROUND_INITIAL, which, (i == MN_STACK - 1) ? -1 : -2, st);
+    launch_push(h, which, st);
+  }
+}
+
+extern "C" {
+
+int mn_reset_all(mn_handle h, void* stream) {
+  if (!h) return fail("mn_reset_all: null handle");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = h->d.n_envs, tb = 256, gb = (n + tb - 1) / tb;
+  k_fill_list<<<gb, tb, 0, st>>>(h->d, 2);
+  h->launches++;
+  launch_initial_state(h, 2, st);
+  launch_emit(h, 0, n, 1, st);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(h->done, st));
+  h->pending = true;
+  return 0;
+}
+
+int mn_step_async(mn_handle h, int use_indices, void* stream) {
+  if (!h) return fail("mn_step_async: null handle");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = h->d.n_envs, tb = 256, gb = (n + tb - 1) / tb;
+  k_begin_step<<<gb, tb, 0, st>>>(h->d, use_indices);
+  h->launches++;
+  int in = 0;
+  for (int r = 0; r <= h->max_rep; ++r) {
+    const int out = in ^ 1;
+    launch_round(h, ROUND_FIGAR, in, out, st);
+    launch_push(h, in, st);
+    if (r < h->max_rep) { k_clear_counts<<<1, 32, 0, st>>>(h->d, in); h->launches++; }
+    in = out;
+  }
+  launch_initial_state(h, 2, st);
+  launch_emit(h, 0, n, 1, st);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(h->done, st));
+  h->pending = true;
+  return 0;
+}
+
+int mn_wait(mn_handle h) {
+  if (!h) return fail("mn_wait: null handle");
+  CU(cudaSetDevice(h->device));
+  if (h->pending) { CU(cudaEventSynchronize(h->done)); h->pending = false; }
+  CU(cudaGetLastError());
+  int err = 0;
+  CU(cudaMemcpy(&err, h->d.error, sizeof(int), cudaMemcpyDeviceToHost));
+  if (err) return fail("episode over right after reset ('This should never happen.', atari_emulator.py:108-109)");
+  return 0;
+}
+
+int mn_step_host(mn_handle h, const float* actions_host, const float* repetitions_host, uint8_t* states_host,
+                 float* rewards_host, float* terminals_host, void* stream) {
+  if (!h) return fail("mn_step_host: null handle");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const PoolDev& d = h->d;
+  const size_t N = size_t(d.n_envs);
+  CU(cudaMemcpyAsync(d.actions, actions_host, N * d.num_actions * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d.repetitions, repetitions_host, N * d.nb_choices * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (mn_step_async(h, 0, stream)) return -1;
+  CU(cudaMemcpyAsync(states_host, d.states, N * MN_STACK * MN_PLANE * d.depth, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(rewards_host, d.rewards, N * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(terminals_host, d.terminals, N * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return mn_wait(h);
+}
+
+int mn_env_reset(mn_handle h, int env, void* stream) {
+  if (!h || env < 0 || env >= h->d.n_envs) return fail("mn_env_reset: bad environment id");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  k_single_list<<<1, 64, 0, st>>>(h->d, 2, env, 0);
+  h->launches++;
+  launch_initial_state(h, 2, st);
+  launch_emit(h, env, env + 1, 1, st);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(st));
+  return mn_wait(h);
+}
+
+int mn_env_next(mn_handle h, int env, int action_index, float* reward, int* terminal, void* stream) {
+  if (!h || env < 0 || env >= h->d.n_envs) return fail("mn_env_next: bad environment id");
+  const GameDev& G = h->games_host[h->env_game_host[size_t(env)]];
+  if (action_index < 0 || action_index >= G.n_actions) return fail("mn_env_next: action index outside the legal action set");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  k_single_list<<<1, 64, 0, st>>>(h->d, 0, env, int(G.actions[action_index]));
+  h->launches++;
+  launch_round(h, ROUND_SINGLE, 0, 1, st);
+  launch_push(h, 0, st);
+  launch_emit(h, env, env + 1, 1, st);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(st));
+  float r = 0.f, t = 0.f;
+  CU(cudaMemcpy(&r, h->d.rewards + env, sizeof(float), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(&t, h->d.terminals + env, sizeof(float), cudaMemcpyDeviceToHost));
+  if (reward) *reward = r;
+  if (terminal) *terminal = (t != 0.f);
+  return 0;
+}
+
+int mn_get_ram(mn_handle h, int env, uint8_t* out) {
+  if (!h || env < 0 || env >= h->d.n_envs) return fail("mn_get_ram: bad environment id");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpy(out, h->d.ram + size_t(env) * 128, 128, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int mn_get_screen(mn_handle h, int env, uint8_t* out) {
+  if (!h || env < 0 || env >= h->d.n_envs) return fail("mn_get_screen: bad environment id");
+  CU(cudaSetDevice(h->device));
+  EnvState s;
+  CU(cudaMemcpy(&s, h->d.env + env, sizeof(s), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(out, h->d.frames + size_t(env) * 2 * MN_FRAME_BYTES + ((s.flags & F_CURFB) ? MN_FRAME_BYTES : 0), MN_FRAME_BYTES,
+                cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int mn_get_cpu_state(mn_handle h, int env, int32_t* out) {
+  if (!h || env < 0 || env >= h->d.n_envs) return fail("mn_get_cpu_state: bad environment id");
+  CU(cudaSetDevice(h->device));
+  EnvState s;
+  CU(cudaMemcpy(&s, h->d.env + env, sizeof(s), cudaMemcpyDeviceToHost));
+  out[0] = s.A; out[1] = s.X; out[2] = s.Y; out[3] = s.SP; out[4] = s.PC; out[5] = int32_t(pack_ps(s)); out[6] = s.cycles;
+  out[7] = (s.cycles * 3 - s.clk_frame_start) / 228; out[8] = s.bank; out[9] = s.timer;
+  return 0;
+}
+
+int mn_get_lives(mn_handle h, int env, int* lives, int* game_over, int* frame_number) {
+  if (!h || env < 0 || env >= h->d.n_envs) return fail("mn_get_lives: bad environment id");
+  CU(cudaSetDevice(h->device));
+  EnvState s;
+  CU(cudaMemcpy(&s, h->d.env + env, sizeof(s), cudaMemcpyDeviceToHost));
+  if (lives) *lives = s.lives;
+  if (game_over) *game_over = (s.flags & F_TERMINAL) ? 1 : 0;
+  if (frame_number) *frame_number = s.frame_number;
+  return 0;
+}
+
+int mn_total_next_calls(mn_handle h, int64_t* out) {
+  if (!h || !out) return fail("mn_total_next_calls: null argument");
+  CU(cudaSetDevice(h->device));
+  unsigned long long v = 0;
+  CU(cudaMemcpy(&v, h->d.total_next, sizeof(v), cudaMemcpyDeviceToHost));
+  *out = int64_t(v);
+  return 0;
+}
+
+int mn_launch_count(mn_handle h, int64_t* out) {
+  if (!h || !out) return fail("mn_launch_count: null argument");
+  *out = h->launches;
+  return 0;
+}
+
+int mn_preprocess(const uint8_t* frames_dev, uint8_t* planes_dev, int n, int rgb, void* stream) {
+  if (n <= 0) return 0;
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  if (upload_constants(dev)) return -1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = n < 148 * 16 ? n : 148 * 16;
+  if (rgb) k_preprocess<3><<<grid, 256, 0, st>>>(frames_dev, planes_dev, n);
+  else k_preprocess<1><<<grid, 256, 0, st>>>(frames_dev, planes_dev, n);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int mn_sample_figar(const float* pi_dev, const float* rho_dev, int n, int a, int k, int mode, float epsilon, uint64_t seed,
+                    uint32_t step, int32_t* action_idx_dev, int32_t* rep_idx_dev, float* action_onehot_dev,
+                    float* rep_onehot_dev, void* stream) {
+  if (n <= 0) return 0;
+  if (a < 1 || k < 1 || mode < 0 || mode > 2) return fail("mn_sample_figar: bad shape or mode");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  k_sample_figar<<<(n + 255) / 256, 256, 0, st>>>(pi_dev, rho_dev, n, a, k, mode, epsilon, uint32_t(seed), uint32_t(seed >> 32),
+                                                   step, action_idx_dev, rep_idx_dev, action_onehot_dev, rep_onehot_dev);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int mn_nstep(const float* rewards_dev, const float* terminals_dev, const float* values_dev, const float* bootstrap_dev,
+             double gamma, int clip, int t, int n, float* y_dev, float* adv_dev, void* stream) {
+  if (n <= 0 || t <= 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  k_nstep<<<(n + 255) / 256, 256, 0, st>>>(rewards_dev, terminals_dev, values_dev, bootstrap_dev, gamma, clip, t, n, y_dev, adv_dev);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

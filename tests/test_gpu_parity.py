@@ -1,0 +1,107 @@
+"""GPU parity: the CUDA environment pool (through the C ABI) against the CPU oracle on the same ROMs,
+seeds and action sequences -- RAM, raw screen, reward, terminal bit-exact; stacked states exact."""
+import numpy as np
+import pytest
+
+import util
+from util import GAMES12, OraclePool, rom_bytes
+
+pytestmark = pytest.mark.gpu
+
+
+def _device_pool(game, n, **kw):
+    import manette_b200 as mb
+    return mb.DevicePool([(game, rom_bytes(game), n)], **kw)
+
+
+@pytest.mark.parametrize("game", GAMES12)
+def test_single_env_next_matches_oracle(game):
+    """AtariEmulator.next() one call at a time: every tap after every call."""
+    n, steps = 3, 40
+    ora = OraclePool(game, n)
+    pool = _device_pool(game, n)
+    try:
+        assert list(pool.legal_actions(0)) == list(ora.emus[0].get_legal_actions())
+        want = ora.initial_states()
+        pool.reset_all()
+        got = pool.states.cpu().numpy()
+        assert np.array_equal(got, want), "initial states differ"
+        rng = np.random.RandomState(7)
+        for t in range(steps):
+            for e in range(n):
+                a = int(rng.randint(ora.num_actions))
+                obs, rew, term = ora.emus[e].next(a)
+                r2, t2 = pool.env_next(e, a)
+                assert (rew, bool(term)) == (r2, t2), (game, t, e)
+                assert np.array_equal(pool.ram(e), ora.emus[e].ale.getRAM()), (game, t, e, "ram")
+                assert np.array_equal(pool.screen(e), ora.emus[e].ale.getScreen()), (game, t, e, "screen")
+                assert np.array_equal(pool.states[e].cpu().numpy(), obs), (game, t, e, "state")
+                cpu = ora.emus[e].ale.getCPU()
+                assert np.array_equal(pool.cpu_state(e)[:7], cpu[:7]), (game, t, e, "cpu")
+                if term:
+                    want0 = ora.emus[e].get_initial_state()
+                    pool.env_reset(e)
+                    assert np.array_equal(pool.states[e].cpu().numpy(), want0)
+    finally:
+        pool.close()
+
+
+@pytest.mark.parametrize("game,rgb,k,max_rep,n,steps", [
+    ("pong", False, 1, 0, 8, 30),
+    ("breakout", False, 11, 10, 16, 25),
+    ("seaquest", True, 11, 10, 8, 12),
+    ("ms_pacman", False, 6, 10, 8, 12),
+])
+def test_macro_step_matches_oracle(game, rgb, k, max_rep, n, steps):
+    """Runners.update_environments(): FiGAR repeat loop with early exit and in-step reset."""
+    ora = OraclePool(game, n, rgb=rgb, nb_choices=k, max_repetition=max_rep)
+    pool = _device_pool(game, n, rgb=rgb, tab_rep=ora.tab_rep)
+    try:
+        import torch
+        assert np.array_equal(ora.initial_states(), (pool.reset_all(), pool.states.cpu().numpy())[1])
+        acts, reps = util.schedule(99, steps, n, ora.num_actions, k)
+        for t in range(steps):
+            want_s, want_r, want_t, want_c = ora.macro_step(acts[t], reps[t])
+            pool.action_idx.copy_(torch.as_tensor(acts[t].astype(np.int32)))
+            pool.repetition_idx.copy_(torch.as_tensor(reps[t].astype(np.int32)))
+            pool.step_async(use_indices=True)
+            pool.wait()
+            assert np.array_equal(pool.rewards.cpu().numpy(), want_r), (game, t)
+            assert np.array_equal(pool.terminals.cpu().numpy(), want_t), (game, t)
+            assert np.array_equal(pool.next_calls.cpu().numpy(), want_c), (game, t)
+            assert np.array_equal(pool.states.cpu().numpy(), want_s), (game, t)
+        for e in range(n):
+            assert np.array_equal(pool.ram(e), ora.emus[e].ale.getRAM())
+            assert np.array_equal(pool.screen(e), ora.emus[e].ale.getScreen())
+    finally:
+        pool.close()
+
+
+@pytest.mark.parametrize("game", ["pong", "breakout", "seaquest", "ms_pacman"])
+def test_golden_fixture(game):
+    """The committed fixtures were produced by the reference's own EmulatorRunner._run / AtariEmulator code
+    (tests/golden/make_golden.py); the device path must reproduce them through one-hot inputs."""
+    import torch
+    d = np.load("%s/figar_%s.npz" % (util.GOLDEN, game))
+    acts, reps = d["actions"], d["repetitions"]
+    m, n = acts.shape
+    rgb = d["final_states"].shape[-1] == 12
+    pool = _device_pool(game, n, rgb=rgb, tab_rep=list(d["tab_rep"]))
+    try:
+        pool.reset_all()
+        st = pool.states.cpu().numpy()
+        assert [util.crc(st[e]) for e in range(n)] == list(d["init_state_crc"])
+        a_n, k_n = int(d["num_actions"]), len(d["tab_rep"])
+        assert (pool.num_actions, pool.nb_choices) == (a_n, k_n)
+        for t in range(m):
+            pool.actions.copy_(torch.as_tensor(np.eye(a_n, dtype=np.float32)[acts[t]]))
+            pool.repetitions.copy_(torch.as_tensor(np.eye(k_n, dtype=np.float32)[reps[t]]))
+            pool.step_async(use_indices=False)
+            pool.wait()
+            assert np.array_equal(pool.rewards.cpu().numpy(), d["rewards"][t]), t
+            assert np.array_equal(pool.terminals.cpu().numpy(), d["terminals"][t]), t
+            st = pool.states.cpu().numpy()
+            assert [util.crc(st[e]) for e in range(n)] == list(d["state_crc"][t]), t
+        assert np.array_equal(st, d["final_states"])
+    finally:
+        pool.close()
