@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- preprocessed env frames/s of the FiGAR10 environment hot path on N B200s.
+
+One "step" = one macro step of every environment (Runners.update_environments + wait_updated):
+each env runs 1 + tab_rep[k] next() calls (4 emulated frames + one 84x84xD plane each) with early exit
+and in-step reset on terminal, then the stacked states / rewards / terminals are published.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  `value` = next() calls of all ranks / max-over-ranks device time with the
+policy's choices already in HBM; `e2e` = the same through Runners with HOST arrays (H2D of the one-hot
+actions/repetitions and D2H of states/rewards/terminals every step inside the timed region).
+`--impl reference` times the CPU restatement of the reference's own worker pool (oracle/host_path.py
+PortRunners over the C++ oracle emulator) on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GAMES12 = ["asterix", "asteroids", "breakout", "enduro", "gopher", "gravitar", "montezuma_revenge", "ms_pacman",
+           "pong", "seaquest", "space_invaders", "yars_revenge"]
+ROMS = os.path.join(ROOT, "atari_roms")
+
+# BASELINE.json configs
+WORKLOADS = {
+    "pong_paac_n32": dict(games=["pong"], n=32, rgb=False, nb_choices=1, max_rep=0),
+    "breakout_figar10_n256": dict(games=["breakout"], n=256, rgb=False, nb_choices=11, max_rep=10),
+    "seaquest_figar10_rgb_n4096": dict(games=["seaquest"], n=4096, rgb=True, nb_choices=11, max_rep=10),
+    "ms_pacman_figar10_n16384": dict(games=["ms_pacman"], n=16384, rgb=False, nb_choices=11, max_rep=10),
+    "mixed12_figar10_n16384": dict(games=GAMES12, n=16384, rgb=False, nb_choices=11, max_rep=10, allreduce=3400000),
+}
+DEFAULT_WORKLOAD = "ms_pacman_figar10_n16384"
+# algorithmic HBM bytes of one next() for the emulation kernel: the two pooled raw frames it
+# must leave in HBM (2 x 33,600) + machine state in and out (2 x (168 + 128)); K3: 2 raw frames read + one plane
+ROUND_BYTES_PER_NEXT = 2 * 33600 + 2 * (168 + 128)
+
+
+def k3_bytes(depth):
+    return 2 * 210 * 160 + 84 * 84 * depth
+
+
+def split_games(games, n):
+    base, extra = divmod(n, len(games))
+    return [(g, base + (1 if i < extra else 0)) for i, g in enumerate(games)]
+
+
+def tab_repetitions(max_repetition, nb_choices):
+    res = [0] * nb_choices
+    res[-1] = max_repetition
+    if nb_choices > 2:
+        for i in range(1, nb_choices - 1):
+            res[i] = int(max_repetition / (nb_choices - 1)) * i
+    return res
+
+
+def rom_bytes(game):
+    with open(os.path.join(ROMS, game + ".bin"), "rb") as f:
+        return f.read()
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu = gpu
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle = the checker, timed)
+def cpu_pool_run(cfg, steps, warmup, budget_s=None, envs_per_core=4):
+    """The reference's worker pool restated on the CPU oracle (oracle/host_path.py PortRunners: W forked workers,
+    emulator_runner.py:19-42 loop, atari_emulator.py preprocessing), W = all host cores.  Returns a dict."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "shims"))
+    import host_path
+    import orc_loader
+    import ref_harness
+    orc_loader.build()
+    cores = os.cpu_count() or 1
+    n = cores * envs_per_core
+    groups = split_games(cfg["games"], n)
+    tab_rep = tab_repetitions(cfg["max_rep"], cfg["nb_choices"])
+    emus, eid = [], 0
+    for g, k in groups:
+        a = ref_harness.Args(g, ROMS, rgb=cfg["rgb"], max_repetition=cfg["max_rep"], nb_choices=cfg["nb_choices"])
+        for _ in range(k):
+            emus.append(host_path.PortAtariEmulator(eid, a))
+            eid += 1
+    num_actions = max(len(e.get_legal_actions()) for e in emus)
+    acts_per_env = np.array([len(e.get_legal_actions()) for e in emus])
+    states = np.stack([e.get_initial_state() for e in emus])
+    variables = [states, np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros((n, num_actions), np.float32),
+                 np.zeros((n, cfg["nb_choices"]), np.float32)]
+    runners = host_path.PortRunners(tab_rep, emus, cores, variables)
+    runners.start()
+    sv = runners.get_shared_variables()
+    rng = np.random.RandomState(1234)
+
+    def one_step():
+        a = (rng.randint(0, 1 << 30, size=n) % acts_per_env)
+        r = rng.randint(0, cfg["nb_choices"], size=n)
+        sv[3][...] = 0
+        sv[3][np.arange(n), a] = 1
+        sv[4][...] = 0
+        sv[4][np.arange(n), r] = 1
+        runners.update_environments()
+        runners.wait_updated()
+        return int(runners.next_counts().sum())
+
+    try:
+        for _ in range(warmup):
+            one_step()
+        t0 = time.perf_counter()
+        frames, done = 0, 0
+        while done < steps:
+            frames += one_step()
+            done += 1
+            if budget_s is not None and time.perf_counter() - t0 > budget_s:
+                break
+        dt = time.perf_counter() - t0
+    finally:
+        runners.stop()
+    return {"value": frames / dt, "frames": frames, "seconds": dt, "steps": done, "cores": cores, "n_envs": n,
+            "sample": "%d envs (%d per core) x %d macro steps of the same game/FiGAR config on %d worker processes"
+                      % (n, envs_per_core, done, cores)}
+
+
+# ----------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=0, help="override environments per GPU")
+    ap.add_argument("--envs-per-warp", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    cfg = dict(WORKLOADS[args.workload])
+    if args.envs:
+        cfg["n"] = args.envs
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": args.workload, "games": cfg["games"], "envs_per_gpu": cfg["n"], "rgb": cfg["rgb"],
+              "nb_choices": cfg["nb_choices"], "max_repetition": cfg["max_rep"], "policy": "uniform random (counter-based)",
+              "frame_unit": "1 preprocessed frame = 1 next() = 4 emulated frames + one 84x84xD plane"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = cpu_pool_run(cfg, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": "preprocessed env frames/sec (FiGAR10)", "value": r["value"],
+                "unit": "frames/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
+                "ms_per_step": 1000.0 * r["seconds"] / max(r["steps"], 1), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
+                                 "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import manette_b200 as mb
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize(dev)
+
+    n = cfg["n"]
+    tab_rep = tab_repetitions(cfg["max_rep"], cfg["nb_choices"])
+    groups = [(g, rom_bytes(g), k) for g, k in split_games(cfg["games"], n)]
+    pool = mb.DevicePool(groups, rgb=cfg["rgb"], tab_rep=tab_rep, device=local_rank, env_id_offset=rank * n,
+                         envs_per_warp=args.envs_per_warp)
+    pool.reset_all()
+    # the random policy's choices, resident in HBM before the timed region
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1000 + rank)
+    n_act = torch.cat([torch.full((k,), len(mb.csrc_info.MINIMAL_ACTIONS[g]), dtype=torch.int64) for g, _, k in groups]).to(dev)
+    total = args.warmup + args.steps
+    acts = (torch.randint(0, 1 << 30, (2 * total, n), device=dev, generator=gen) % n_act).to(torch.int32)
+    reps = torch.randint(0, cfg["nb_choices"], (2 * total, n), device=dev, generator=gen, dtype=torch.int32)
+    grad = torch.zeros(cfg.get("allreduce", 0) or 1, device=dev) if world > 1 and cfg.get("allreduce") else None
+    stream = pool.stream
+
+    def device_step(t):
+        with torch.cuda.stream(stream):
+            pool.action_idx.copy_(acts[t], non_blocking=True)
+            pool.repetition_idx.copy_(reps[t], non_blocking=True)
+            pool.step_async(use_indices=True, stream=stream)
+            if grad is not None and (t + 1) % 5 == 0:      # synchronous-PAAC gradient allreduce every T=5 macro steps
+                dist.all_reduce(grad)
+
+    # ---- device-resident leg
+    for t in range(args.warmup):
+        device_step(t)
+    pool.wait()
+    barrier()
+    f0, l0 = pool.total_next_calls(), pool.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    pool.profile_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for t in range(args.warmup, total):
+        device_step(t)
+    e1.record(stream)
+    pool.wait()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    prof = pool.profile_end()
+    frames = pool.total_next_calls() - f0
+    launches = pool.launch_count() - l0
+    stat = torch.tensor([ms, float(frames), float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stat.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stat.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_max, frames_all, launches_all = float(mx[0]), float(sm[1]), int(sm[2])
+    else:
+        ms_max, frames_all, launches_all = ms, float(frames), int(launches)
+    value = frames_all / (ms_max / 1000.0)
+
+    # ---- end-to-end leg through Runners with host arrays
+    e2e = None
+    if not args.no_e2e:
+        emus = mb.emulators_for_pool(pool)
+        host_states = pool.states.cpu().numpy()
+        variables = [host_states, np.zeros(n, np.float32), np.zeros(n, np.float32),
+                     np.zeros((n, pool.num_actions), np.float32), np.zeros((n, pool.nb_choices), np.float32)]
+        runners = mb.Runners(tab_rep, mb.EmulatorRunner, emus, 1, variables)
+        runners.start()
+        sv = runners.get_shared_variables()
+        h_acts, h_reps = acts[total:].cpu().numpy(), reps[total:].cpu().numpy()
+        ar = np.arange(n)
+
+        def host_step(t):
+            sv[3][...] = 0
+            sv[3][ar, h_acts[t]] = 1
+            sv[4][...] = 0
+            sv[4][ar, h_reps[t]] = 1
+            runners.update_environments()
+            runners.wait_updated()
+            return float(sv[1].sum()) + float(sv[2].sum()) + float(sv[0][0, 0, 0, 0])
+
+        for t in range(args.warmup):
+            host_step(t)
+        barrier()
+        f0 = pool.total_next_calls()
+        t0 = time.perf_counter()
+        for t in range(args.warmup, total):
+            host_step(t)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        barrier()
+        fr = pool.total_next_calls() - f0
+        st2 = torch.tensor([dt, float(fr)], dtype=torch.float64, device=dev)
+        if world > 1:
+            mx2 = st2.clone(); dist.all_reduce(mx2, op=dist.ReduceOp.MAX)
+            sm2 = st2.clone(); dist.all_reduce(sm2, op=dist.ReduceOp.SUM)
+            dt_max, fr_all = float(mx2[0]), float(sm2[1])
+        else:
+            dt_max, fr_all = dt, float(fr)
+        e2e = {"value": fr_all / dt_max, "unit": "frames/s",
+               "h2d_bytes_per_step": int(world * n * (pool.num_actions + pool.nb_choices) * 4),
+               "d2h_bytes_per_step": int(world * n * (84 * 84 * 4 * pool.depth + 8)), "ms_per_step": 1000.0 * dt_max / args.steps,
+               "api": "Runners.update_environments()/wait_updated() with pinned host arrays"}
+        runners.stop()
+
+    # ---- roofline of the dominant kernel (k_round), CUDA events around every launch on its stream
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        with open(peaks_path) as f:
+            peak, peak_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    round_ms, round_launches = prof["round"]
+    push_ms, push_launches = prof["push"]
+    emit_ms, emit_launches = prof["emit"]
+    achieved = frames * ROUND_BYTES_PER_NEXT / (round_ms / 1000.0) / 1e9 if round_ms > 0 else 0.0
+    k3_achieved = (frames * k3_bytes(pool.depth)) / (push_ms / 1000.0) / 1e9 if push_ms > 0 else 0.0
+    roofline = {"kernel": "k_round (6502+TIA emulation, one next() per listed env)", "bound": "hbm", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": round_ms / max(round_launches, 1), "launches": int(round_launches),
+                "share_of_step": round_ms / ms if ms > 0 else None,
+                "note": "emulation is SM integer-issue bound, not HBM bound: the HBM fraction is reported as the contract "
+                        "asks; issue-slot utilisation and warp execution efficiency are in profiles/"}
+    extra = {"k3_push_frames": {"bound": "hbm", "achieved": k3_achieved, "peak": peak, "unit": "GB/s",
+                                "frac": k3_achieved / peak, "ms": push_ms, "launches": int(push_launches),
+                                "share_of_step": push_ms / ms if ms > 0 else None},
+             "k_emit": {"ms": emit_ms, "launches": int(emit_launches), "share_of_step": emit_ms / ms if ms > 0 else None}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_pool_run(cfg, steps=10 ** 9, warmup=1, budget_s=12.0)
+        cpu = {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    if rank == 0:
+        line = {"metric": "preprocessed env frames/sec (FiGAR10)", "value": value, "unit": "frames/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+                "raw_emulated_frames_per_s": 4.0 * value, "macro_steps_per_s": world * n * args.steps / (ms_max / 1000.0),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline, "kernels": extra,
+                "cpu_baseline": cpu, "envs_per_warp": int(args.envs_per_warp)}
+        config["l2"] = "per-step working set (frame buffers %d MB + states/ring) exceeds the 126 MB L2; no flush needed" \
+            % (n * 67200 // (1 << 20))
+        print(json.dumps(line))
+    pool.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

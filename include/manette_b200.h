@@ -108,6 +108,11 @@ int mn_sample_figar(const float* pi_dev, const float* rho_dev, int n, int a, int
 int mn_nstep(const float* rewards_dev, const float* terminals_dev, const float* values_dev, const float* bootstrap_dev,
              double gamma, int clip, int t, int n, float* y_dev, float* adv_dev, void* stream);
 
+/* per-kernel device timing with CUDA events on the launching stream, for bench.py's roofline object.
+ * kinds: 0 = k_round (emulation), 1 = k_push_frames (K3), 2 = k_emit (stack + publish), 3 = other.
+ * mn_profile_end synchronises the device and returns summed milliseconds and launch counts (4 each). */
+int mn_profile_begin(mn_handle h);
+int mn_profile_end(mn_handle h, double* ms_by_kind4, int64_t* launches_by_kind4);
 /* kernels launched since creation (bench.py's gpu_launches) */
 int mn_launch_count(mn_handle h, int64_t* out);
 

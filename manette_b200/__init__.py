@@ -2,7 +2,7 @@
 emulation under PAAC with FiGAR action repetition, fused preprocessing, FiGAR sampling and n-step returns --
 behind the reference's Runners / EmulatorRunner / AtariEmulator interfaces.  See DESIGN.md."""
 from . import _native
-from .atari_emulator import AtariEmulator, release_pools
+from .atari_emulator import AtariEmulator, emulators_for_pool, release_pools
 from .emulator_runner import EmulatorRunner
 from .environment_creator import EnvironmentCreator
 from .exploration_policy import Action, ExplorationPolicy, sample_figar
@@ -13,4 +13,4 @@ from .runners import Runners
 
 __all__ = ["AtariEmulator", "EmulatorRunner", "EnvironmentCreator", "Action", "ExplorationPolicy", "sample_figar",
            "DevicePool", "load_rom", "palette", "start_noops", "tab_repetitions", "preprocess", "nstep_returns", "Runners",
-           "release_pools"]
+           "release_pools", "emulators_for_pool"]

@@ -56,6 +56,8 @@ SYMBOLS = {
     "mn_preprocess": (_I, [_VP, _VP, _I, _I, _VP]),
     "mn_sample_figar": (_I, [_VP, _VP, _I, _I, _I, _I, _F, _U64, _U32, _VP, _VP, _VP, _VP, _VP]),
     "mn_nstep": (_I, [_VP, _VP, _VP, _VP, _D, _I, _I, _I, _VP, _VP, _VP]),
+    "mn_profile_begin": (_I, [_VP]),
+    "mn_profile_end": (_I, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "mn_launch_count": (_I, [_VP, C.POINTER(C.c_int64)]),
 }
 

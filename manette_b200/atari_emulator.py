@@ -56,6 +56,29 @@ def _group_for(args):
     return g
 
 
+def emulators_for_pool(pool):
+    """AtariEmulator handles 0..N-1 over an existing DevicePool (e.g. a mixed-game pool built directly)."""
+    g = _PoolGroup(None, None)
+    g.pool = pool
+    g.fresh = np.zeros(pool.n_envs, bool)
+    g.closed_to_new = True
+    out = []
+    for i in range(pool.n_envs):
+        e = AtariEmulator.__new__(AtariEmulator)
+        e.actor_id = i
+        e.random_start = e.single_life_episodes = None
+        e.call_on_new_frame = False
+        e.global_step = 0
+        e.rgb = pool.rgb
+        e.depth = pool.depth
+        e.screen_width, e.screen_height = 160, 210
+        e._group = g
+        e._legal = None
+        g.members[i] = e
+        out.append(e)
+    return out
+
+
 def release_pools():
     """Frees every device pool created through AtariEmulator objects."""
     for g in list(_GROUPS.values()):

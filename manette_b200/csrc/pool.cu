@@ -486,8 +486,20 @@ struct mn_pool {
   std::vector<int> env_game_host;
   GameDev games_host[MN_MAX_GAMES];
   Tables* tables_dev;
-  bool palette_ready;
+  // optional per-kernel timing (mn_profile_begin / mn_profile_end)
+  bool profiling;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used;
+  std::vector<int> ev_kind;   // kind of the launch bracketed by events (2i, 2i+1)
 };
+enum { PK_ROUND = 0, PK_PUSH = 1, PK_EMIT = 2, PK_OTHER = 3, PK_COUNT = 4 };
+
+static void prof_mark(mn_pool* h, int kind, cudaStream_t st, bool begin) {
+  if (!h->profiling) return;
+  if (h->ev_used == h->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); h->ev_pool.push_back(e); }
+  cudaEventRecord(h->ev_pool[h->ev_used++], st);
+  if (begin) h->ev_kind.push_back(kind);
+}
 
 static bool g_const_ready[64] = {false};
 
@@ -527,6 +539,7 @@ int mn_destroy(mn_handle h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   for (void* p : h->allocs) cudaFree(p);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->done) cudaEventDestroy(h->done);
   delete h;
   return 0;
@@ -549,6 +562,7 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
   mn_pool* h = new mn_pool();
   memset(&h->d, 0, sizeof(h->d));
   h->device = cfg->device; h->done = nullptr; h->pending = false; h->launches = 0; h->pin_ram = nullptr;
+  h->profiling = false; h->ev_used = 0;
   PoolDev& d = h->d;
   int n = 0, max_actions = 0;
   size_t rom_total = 0, max_rom = 0;
@@ -688,17 +702,23 @@ int mn_legal_actions(mn_handle h, int env, int32_t* out) {
 
 // ---- launch helpers (host)
 static void launch_push(mn_pool* h, int in, cudaStream_t st) {
+  prof_mark(h, PK_PUSH, st, true);
   if (h->d.depth == 1) k_push_frames<1><<<h->d.n_envs, 256, 0, st>>>(h->d, in);
   else k_push_frames<3><<<h->d.n_envs, 256, 0, st>>>(h->d, in);
+  prof_mark(h, PK_PUSH, st, false);
   h->launches++;
 }
 static void launch_round(mn_pool* h, int mode, int in, int out, cudaStream_t st) {
+  prof_mark(h, PK_ROUND, st, true);
   k_round<<<h->round_grid, MN_THREADS, h->round_smem, st>>>(h->d, mode, in, out);
+  prof_mark(h, PK_ROUND, st, false);
   h->launches++;
 }
 static void launch_emit(mn_pool* h, int lo, int hi, int publish, cudaStream_t st) {
+  prof_mark(h, PK_EMIT, st, true);
   if (h->d.depth == 1) k_emit<1><<<hi - lo, 256, 0, st>>>(h->d, lo, hi, publish);
   else k_emit<3><<<hi - lo, 256, 0, st>>>(h->d, lo, hi, publish);
+  prof_mark(h, PK_EMIT, st, false);
   h->launches++;
 }
 // get_initial_state() for the envs on list `which` (atari_emulator.py:102-110)
@@ -856,6 +876,27 @@ int mn_total_next_calls(mn_handle h, int64_t* out) {
   unsigned long long v = 0;
   CU(cudaMemcpy(&v, h->d.total_next, sizeof(v), cudaMemcpyDeviceToHost));
   *out = int64_t(v);
+  return 0;
+}
+
+int mn_profile_begin(mn_handle h) {
+  if (!h) return fail("mn_profile_begin: null handle");
+  h->profiling = true; h->ev_used = 0; h->ev_kind.clear();
+  return 0;
+}
+
+int mn_profile_end(mn_handle h, double* ms_by_kind4, int64_t* launches_by_kind4) {
+  if (!h) return fail("mn_profile_end: null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());
+  for (int k = 0; k < PK_COUNT; ++k) { ms_by_kind4[k] = 0.0; launches_by_kind4[k] = 0; }
+  for (size_t i = 0; i < h->ev_kind.size(); ++i) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]));
+    ms_by_kind4[h->ev_kind[i]] += double(ms);
+    launches_by_kind4[h->ev_kind[i]] += 1;
+  }
+  h->profiling = false; h->ev_used = 0; h->ev_kind.clear();
   return 0;
 }
 

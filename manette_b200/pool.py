@@ -173,6 +173,16 @@ class DevicePool(object):
         _native.check(self._L.mn_launch_count(self._h, C.byref(v)), "mn_launch_count")
         return v.value
 
+    def profile_begin(self):
+        _native.check(self._L.mn_profile_begin(self._h), "mn_profile_begin")
+
+    def profile_end(self):
+        """{kind: (summed ms, launches)} for kinds round / push / emit / other."""
+        ms = (C.c_double * 4)()
+        cnt = (C.c_int64 * 4)()
+        _native.check(self._L.mn_profile_end(self._h, ms, cnt), "mn_profile_end")
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(("round", "push", "emit", "other"))}
+
     def close(self):
         if getattr(self, "_h", None):
             self._L.mn_destroy(self._h)

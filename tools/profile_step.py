@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Small fixed workload for ncu / compute-sanitizer: build a pool, decorrelate it with a few random macro
+steps, then run `--steps` FiGAR10 macro steps.  Prints frames/s of the measured steps."""
+import argparse
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import manette_b200 as mb  # noqa: E402
+
+ROMS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "atari_roms")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--game", default="ms_pacman")
+    ap.add_argument("--envs", type=int, default=2048)
+    ap.add_argument("--rgb", action="store_true")
+    ap.add_argument("--decorrelate", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--envs-per-warp", type=int, default=0)
+    ap.add_argument("--max-rep", type=int, default=10)
+    a = ap.parse_args()
+    k = a.max_rep + 1
+    pool = mb.DevicePool([(a.game, mb.load_rom(ROMS, a.game), a.envs)], rgb=a.rgb, tab_rep=list(range(k)),
+                         envs_per_warp=a.envs_per_warp)
+    pool.reset_all()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7)
+    na = len(pool.legal_actions(0))
+
+    def step():
+        pool.action_idx.copy_(torch.randint(0, na, (a.envs,), device="cuda", generator=g, dtype=torch.int32))
+        pool.repetition_idx.copy_(torch.randint(0, k, (a.envs,), device="cuda", generator=g, dtype=torch.int32))
+        torch.cuda.synchronize()
+        pool.step_async(use_indices=True)
+        pool.wait()
+
+    for _ in range(a.decorrelate):
+        step()
+    f0 = pool.total_next_calls()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step()
+    dt = time.perf_counter() - t0
+    fr = pool.total_next_calls() - f0
+    print("game=%s envs=%d steps=%d next_calls=%d seconds=%.3f frames_per_s=%.1f" % (a.game, a.envs, a.steps, fr, dt, fr / dt))
+    pool.close()
+
+
+if __name__ == "__main__":
+    main()
