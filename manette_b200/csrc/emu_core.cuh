@@ -5,10 +5,20 @@
 //
 // Replaces, for the reference, the external `ALEInterface.act/reset_game/game_over/lives`
 // calls made from atari_emulator.py:72-77,94-97,121,128,133 (ALE = Stella 2.x fork).
-// Formulation differs from the CPU oracle on purpose: object graphics are built as 32-pixel
-// words of 160-bit line masks (collisions = word ANDs), the 6502 is decoded from a packed
-// 16-bit descriptor per opcode into {address phase, read phase, operate phase, write phase},
-// and all state is kept in a compact bit-packed record.
+// Formulation differs from the CPU oracle on purpose:
+//  * the 6502 is decoded from a packed 16-bit descriptor per opcode into {address phase, read phase,
+//    operate phase, write phase};
+//  * TIA register writes are NOT rendered when they happen: the CPU side appends (colour clock,
+//    register, value) to a small per-environment FIFO and only keeps the effects the program can
+//    observe (WSYNC/RSYNC stalls, VSYNC frame end, VBLANK input-dump latch).  The picture side drains
+//    the FIFO later -- all lanes of a warp together -- so the long, branchy rendering path is not
+//    entered by one lane at a time while its 31 neighbours wait;
+//  * object graphics are built as 32-pixel words of 160-bit line masks (collisions = word ANDs) and
+//    pixels leave as 4-byte groups chosen with a byte permute from the packed colour registers;
+//  * of the four frames of a next() only the two pooled ones need pixels: the others run with pixel
+//    output off (collision latches still exact).  Frame lengths are tracked so that the rare case in
+//    which a skipped frame would have left visible bytes (a shorter frame rendered over it, or the
+//    ALE terminal freeze) is detected and the unit is re-run with every frame rendered.
 //
 // The file is also compilable by a host C++ compiler (MN_HD expands to nothing): tests/ build
 // it that way ONLY to pre-check the logic against the oracle on machines without a GPU.
@@ -58,7 +68,9 @@ enum : uint32_t {
   F_VDELP0 = 1u << 6, F_VDELP1 = 1u << 7, F_VDELBL = 1u << 8, F_RESMP0 = 1u << 9, F_RESMP1 = 1u << 10,
   F_SUP0 = 1u << 11, F_SUP1 = 1u << 12, F_PFREFL = 1u << 13, F_HMBLANK = 1u << 14, F_DUMP = 1u << 15,
   F_PARTIAL = 1u << 16, F_CURFB = 1u << 17, F_STOP = 1u << 18, F_INPT4 = 1u << 19, F_INPT5 = 1u << 20,
-  F_TIMER_IRQ_READ = 1u << 21, F_TERMINAL = 1u << 22, F_STARTED = 1u << 23 };
+  F_TIMER_IRQ_READ = 1u << 21, F_TERMINAL = 1u << 22, F_STARTED = 1u << 23,
+  F_PIXELS = 1u << 24 /* picture side: the frame being drawn keeps its pixels */,
+  F_ANOMALY = 1u << 25 /* picture side: a pixel-less frame would have been visible -> re-run with pixels */ };
 
 // addressing modes / operation classes of the packed decode descriptor
 enum { AM_IMP = 0, AM_ACC, AM_IMM, AM_ZP, AM_ZPX, AM_ZPY, AM_ABS, AM_ABX, AM_ABY, AM_IZX, AM_IZY, AM_REL, AM_IND };
@@ -92,10 +104,13 @@ struct EnvState {
   // RIOT
   uint8_t timer, tshift, ddra, ddrb;
   int32_t timer_set_cycle, irq_reset_cycle;
-  uint8_t swcha, swchb, pad0, pad1;
+  uint8_t swcha, swchb, vblank_cpu /* last VBLANK value written (program side) */, pad1;
   int32_t analog[4];
-  // TIA
-  int32_t clk_frame_start, clk_last_update, clks_to_eol, vsync_finish_clk, fb_pos, last_hmove_clk, dump_disabled_cycle;
+  // TIA, program side
+  int32_t clk_frame_start, vsync_finish_clk, dump_disabled_cycle;
+  // TIA, picture side (clocks relative to clk_frame_start of the frame being drawn)
+  int32_t clk_last_update, clks_to_eol, fb_pos;
+  uint16_t pend_len[2];   // per frame buffer: longest pixel-less frame since the last frame drawn with pixels
   uint32_t pf;
   uint32_t flags;
   uint16_t collision;
@@ -123,7 +138,15 @@ struct Ctx {
   int ram_stride;       // bytes between consecutive 4-byte RAM words of this lane
   uint8_t* fb;          // this env's two frame buffers (global memory), 2 * MN_FRAME_BYTES
   const Tables* tab;
+  uint32_t* fifo;       // MN_FIFO_CAP pending TIA writes of this env (shared memory)
+  int fifo_n;
+  bool all_pixels;      // draw every frame with pixels (the exact-fallback mode)
 };
+#define MN_FIFO_CAP 16
+#define MN_FIFO_HIGH 12   // a warp drains when one of its envs has this many pending writes
+// FIFO entry: [16:0] colour clock since clk_frame_start, [22:17] register, [30:23] value; bit 31 marks the
+// start of a new frame (bit 0 then says whether that frame keeps its pixels)
+#define MN_FIFO_FRAME 0x80000000u
 
 MN_HD MN_INLINE uint8_t& ram_at(const Ctx& c, int j) { return c.ram[(j >> 2) * c.ram_stride + (j & 3)]; }
 
@@ -203,16 +226,43 @@ MN_HD MN_INLINE uint32_t ball_word(const EnvState& s, int w) {
   return place(pattern, s.pos[OB_BL], w);
 }
 
+// ------------------------------------------------------------------ TIA: picture side
+MN_HD MN_INLINE uint32_t perm4(uint32_t x, uint32_t sel) {   // byte i of the result = byte sel[4i+1:4i] of x
+#ifdef __CUDA_ARCH__
+  return __byte_perm(x, 0u, sel);
+#else
+  uint32_t r = 0;
+  for (int i = 0; i < 4; ++i) r |= ((x >> (8 * ((sel >> (4 * i)) & 3))) & 0xFFu) << (8 * i);
+  return r;
+#endif
+}
+// the 8 bits of b -> bit 0 of 8 consecutive nibbles
+MN_HD MN_INLINE uint32_t nibbles8(uint32_t b) {
+  b = (b | (b << 12)) & 0x000F000Fu; b = (b | (b << 6)) & 0x03030303u; b = (b | (b << 3)) & 0x11111111u;
+  return b;
+}
+// n bytes of `value` at p (any alignment)
+MN_HD MN_INLINE void fill_px(uint8_t* p, int n, uint32_t value) {
+  const uint32_t v4 = value * 0x01010101u;
+  while (n > 0 && (reinterpret_cast<uintptr_t>(p) & 3)) { *p++ = uint8_t(value); --n; }
+  for (; n >= 4; n -= 4, p += 4) *reinterpret_cast<uint32_t*>(p) = v4;
+  while (n > 0) { *p++ = uint8_t(value); --n; }
+}
+
 // render `n` visible pixels of the current line starting at pixel `hpos`
 MN_HD MN_NOINLINE void tia_render(Ctx& c, int n, int hpos) {
   EnvState& s = *c.s;
+  const bool pixels = (s.flags & F_PIXELS) != 0;
   uint8_t* out = c.fb + ((s.flags & F_CURFB) ? MN_FRAME_BYTES : 0) + s.fb_pos;
   s.fb_pos += n;
-  if (s.vblank & 0x02) { for (int i = 0; i < n; ++i) out[i] = 0; return; }
   const uint32_t en = s.enabled;
-  const uint8_t bk = s.col[3];
-  if (en == 0) { for (int i = 0; i < n; ++i) out[i] = bk; return; }
+  if (s.vblank & 0x02) { if (pixels) fill_px(out, n, 0u); return; }
+  if (en == 0 || (!pixels && (en & (en - 1)) == 0)) {   // nothing to draw / a lone object cannot collide
+    if (pixels) fill_px(out, n, s.col[3]);
+    return;
+  }
   const int x0 = hpos, x1 = hpos + n;
+  const uint32_t colours = uint32_t(s.col[0]) | (uint32_t(s.col[1]) << 8) | (uint32_t(s.col[2]) << 16) | (uint32_t(s.col[3]) << 24);
   const bool prio = (s.ctrlpf & 0x04) != 0, score = (s.ctrlpf & 0x02) != 0;
   uint32_t cx = 0;
   for (int w = x0 >> 5; w <= ((x1 - 1) >> 5); ++w) {
@@ -220,12 +270,12 @@ MN_HD MN_NOINLINE void tia_render(Ctx& c, int n, int hpos) {
     const int lo = (x0 > base) ? (x0 - base) : 0;
     const int hi = (x1 < base + 32) ? (x1 - base) : 32;
     const uint32_t span = ((hi == 32) ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
-    uint32_t pf = (en & EN_PF) ? (pf_word(s, w) & span) : 0u;
-    uint32_t bl = (en & EN_BL) ? (ball_word(s, w) & span) : 0u;
-    uint32_t p0 = (en & EN_P0) ? (player_word(s.cur_grp0, s.nusiz0, s.pos[OB_P0], (s.flags & F_SUP0) != 0, w) & span) : 0u;
-    uint32_t m0 = (en & EN_M0) ? (missile_word(s.nusiz0, s.pos[OB_M0], w) & span) : 0u;
-    uint32_t p1 = (en & EN_P1) ? (player_word(s.cur_grp1, s.nusiz1, s.pos[OB_P1], (s.flags & F_SUP1) != 0, w) & span) : 0u;
-    uint32_t m1 = (en & EN_M1) ? (missile_word(s.nusiz1, s.pos[OB_M1], w) & span) : 0u;
+    const uint32_t pf = (en & EN_PF) ? (pf_word(s, w) & span) : 0u;
+    const uint32_t bl = (en & EN_BL) ? (ball_word(s, w) & span) : 0u;
+    const uint32_t p0 = (en & EN_P0) ? (player_word(s.cur_grp0, s.nusiz0, s.pos[OB_P0], (s.flags & F_SUP0) != 0, w) & span) : 0u;
+    const uint32_t m0 = (en & EN_M0) ? (missile_word(s.nusiz0, s.pos[OB_M0], w) & span) : 0u;
+    const uint32_t p1 = (en & EN_P1) ? (player_word(s.cur_grp1, s.nusiz1, s.pos[OB_P1], (s.flags & F_SUP1) != 0, w) & span) : 0u;
+    const uint32_t m1 = (en & EN_M1) ? (missile_word(s.nusiz1, s.pos[OB_M1], w) & span) : 0u;
     // collision latches: any common pixel inside the span
     cx |= (m0 & p1) ? 0x0001u : 0u; cx |= (m0 & p0) ? 0x0002u : 0u;
     cx |= (m1 & p0) ? 0x0004u : 0u; cx |= (m1 & p1) ? 0x0008u : 0u;
@@ -234,34 +284,46 @@ MN_HD MN_NOINLINE void tia_render(Ctx& c, int n, int hpos) {
     cx |= (m0 & pf) ? 0x0100u : 0u; cx |= (m0 & bl) ? 0x0200u : 0u;
     cx |= (m1 & pf) ? 0x0400u : 0u; cx |= (m1 & bl) ? 0x0800u : 0u;
     cx |= (bl & pf) ? 0x1000u : 0u; cx |= (p0 & p1) ? 0x2000u : 0u; cx |= (m0 & m1) ? 0x4000u : 0u;
+    if (!pixels) continue;
     const uint32_t g0 = p0 | m0, g1 = p1 | m1, gf = pf | bl;
     uint8_t* o = out + (base - x0);
-    if ((g0 | g1 | gf) == 0u) { for (int x = lo; x < hi; ++x) o[x] = bk; continue; }
-    for (int x = lo; x < hi; ++x) {
-      const uint32_t bit = 1u << x;
-      uint8_t colr;
-      if (prio) {
-        if (gf & bit) colr = s.col[2];
-        else if (g0 & bit) colr = s.col[0];
-        else if (g1 & bit) colr = s.col[1];
-        else colr = bk;
-      } else {
-        if (g0 & bit) colr = s.col[0];
-        else if (g1 & bit) colr = s.col[1];
-        else if (pf & bit) colr = score ? s.col[(base + x) < 80 ? 0 : 1] : s.col[2];
-        else if (bl & bit) colr = s.col[2];
-        else colr = bk;
+    if ((g0 | g1 | gf) == 0u) { fill_px(o + lo, hi - lo, s.col[3]); continue; }
+    // colour slot of every pixel as two bit planes: 0 = P0, 1 = P1, 2 = PF, 3 = BK
+    uint32_t is0, is1, is2;
+    if (prio) { is2 = gf; is0 = g0 & ~gf; is1 = g1 & ~(gf | g0); }
+    else {
+      is0 = g0; is1 = g1 & ~g0; is2 = gf & ~(g0 | g1);
+      if (score) {   // playfield pixels take the player colour of their half of the line
+        const uint32_t spf = is2 & pf;
+        const uint32_t left = (base + 31 < 80) ? 0xFFFFFFFFu : (base >= 80) ? 0u : 0x0000FFFFu;
+        is0 |= spf & left; is1 |= spf & ~left; is2 &= ~spf;
       }
-      o[x] = colr;
+    }
+    const uint32_t bk = span & ~(is0 | is1 | is2);
+    const uint32_t plane0 = is1 | bk, plane1 = is2 | bk;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {   // 8 pixels per round
+      const uint32_t sp = (span >> (8 * b)) & 0xFFu;
+      if (sp == 0u) continue;
+      const uint32_t sel = nibbles8((plane0 >> (8 * b)) & 0xFFu) | (nibbles8((plane1 >> (8 * b)) & 0xFFu) << 1);
+      const uint32_t lo4 = perm4(colours, sel), hi4 = perm4(colours, sel >> 16);
+      uint8_t* q = o + 8 * b;
+      if (sp == 0xFFu) { reinterpret_cast<uint32_t*>(q)[0] = lo4; reinterpret_cast<uint32_t*>(q)[1] = hi4; }
+      else {
+        if ((sp & 0x0Fu) == 0x0Fu) reinterpret_cast<uint32_t*>(q)[0] = lo4;
+        else { for (int k = 0; k < 4; ++k) if (sp & (1u << k)) q[k] = uint8_t(lo4 >> (8 * k)); }
+        if ((sp & 0xF0u) == 0xF0u) reinterpret_cast<uint32_t*>(q)[1] = hi4;
+        else { for (int k = 0; k < 4; ++k) if (sp & (16u << k)) q[4 + k] = uint8_t(hi4 >> (8 * k)); }
+      }
     }
   }
   s.collision |= uint16_t(cx);
 }
 
-// bring the picture up to colour clock `clock`
+// bring the picture up to colour clock `clock` (relative to the start of the frame)
 MN_HD MN_NOINLINE void tia_advance(Ctx& c, int32_t clock) {
   EnvState& s = *c.s;
-  const int32_t start = s.clk_frame_start + 228 * MN_YSTART;
+  const int32_t start = 228 * MN_YSTART;
   const int32_t stop = start + 228 * MN_SCREEN_H;
   if (clock < start || s.clk_last_update >= stop || s.clk_last_update >= clock) return;
   if (clock > stop) clock = stop;
@@ -279,8 +341,7 @@ MN_HD MN_NOINLINE void tia_advance(Ctx& c, int32_t clock) {
     if ((s.flags & F_HMBLANK) && from_sol < MN_HBLANK + 8) {
       int32_t blanks = (MN_HBLANK + 8) - from_sol;
       const int32_t room = MN_FRAME_BYTES - old_pos; if (blanks > room) blanks = room;
-      uint8_t* p = c.fb + ((s.flags & F_CURFB) ? MN_FRAME_BYTES : 0) + old_pos;
-      for (int i = 0; i < blanks; ++i) p[i] = 0;
+      if (s.flags & F_PIXELS) fill_px(c.fb + ((s.flags & F_CURFB) ? MN_FRAME_BYTES : 0) + old_pos, blanks, 0u);
       if (n + from_sol >= MN_HBLANK + 8) s.flags &= ~F_HMBLANK;
     }
     if (s.clks_to_eol == 228) {   // line finished: playfield mirror latches, first-copy suppression ends
@@ -288,6 +349,7 @@ MN_HD MN_NOINLINE void tia_advance(Ctx& c, int32_t clock) {
     }
   } while (s.clk_last_update < clock);
 }
+
 
 MN_HD MN_INLINE void tia_refresh_grp(EnvState& s) {
   uint32_t g0 = (s.flags & F_VDELP0) ? s.dgrp0 : s.grp0;
@@ -346,11 +408,10 @@ MN_HD MN_INLINE int resp_zone(int nusiz, int oldx, int newx) {
   return res;
 }
 
-MN_HD MN_NOINLINE void tia_poke(Ctx& c, uint32_t addr, uint32_t v) {
+// ---- picture side: apply one queued register write (colour clock `rel` since the start of the frame)
+MN_HD MN_NOINLINE void tia_apply(Ctx& c, int32_t rel, uint32_t addr, uint32_t v) {
   EnvState& s = *c.s;
-  addr &= 0x3F;
-  const int32_t clock = s.cycles * 3;
-  const int32_t hpos = (clock - s.clk_frame_start) % 228;
+  const int32_t hpos = rel % 228;
   int32_t delay;
   // colour clocks before a write shows: VBLANK/REFPx/GRPx/HMM1../VDELxx/RESMP0 1, NUSIZx/RESMx 8,
   // PFx 2..5 depending on the phase within the playfield cell, everything else immediate
@@ -358,29 +419,9 @@ MN_HD MN_NOINLINE void tia_poke(Ctx& c, uint32_t addr, uint32_t v) {
   else if (addr == 0x04 || addr == 0x05 || addr == 0x12 || addr == 0x13) delay = 8;
   else if (addr == 0x01 || addr == 0x0B || addr == 0x0C || addr == 0x1B || addr == 0x1C || (addr >= 0x23 && addr <= 0x28)) delay = 1;
   else delay = 0;
-  tia_advance(c, clock + delay);
-  if (((clock - s.clk_frame_start) / 228) > MN_MAX_SCANLINES) s.flags = (s.flags | F_STOP) & ~F_PARTIAL;
+  tia_advance(c, rel + delay);
   switch (addr) {
-    case 0x00:
-      s.vsync = uint8_t(v);
-      if (v & 0x02) s.vsync_finish_clk = clock + 228;
-      else if (clock >= s.vsync_finish_clk) { s.vsync_finish_clk = MN_NEVER; s.flags = (s.flags | F_STOP) & ~F_PARTIAL; }
-      break;
-    case 0x01:
-      if (!(s.vblank & 0x80) && (v & 0x80)) s.flags |= F_DUMP;
-      if ((s.vblank & 0x80) && !(v & 0x80)) { s.flags &= ~F_DUMP; s.dump_disabled_cycle = s.cycles; }
-      s.vblank = uint8_t(v);
-      break;
-    case 0x02: {
-      int32_t rest = 76 - ((s.cycles - (s.clk_frame_start / 3)) % 76);
-      if (rest < 76) s.cycles += rest;
-      break;
-    }
-    case 0x03: {
-      int32_t rest = 76 - ((s.cycles - (s.clk_frame_start / 3)) % 76);
-      s.cycles += rest - 1;
-      break;
-    }
+    case 0x01: s.vblank = uint8_t(v); break;
     case 0x04: s.nusiz0 = uint8_t(v); s.flags &= ~F_SUP0; break;
     case 0x05: s.nusiz1 = uint8_t(v); s.flags &= ~F_SUP1; break;
     case 0x06: case 0x07: case 0x08: case 0x09: s.col[addr - 0x06] = uint8_t(v & 0xFE); break;
@@ -397,7 +438,7 @@ MN_HD MN_NOINLINE void tia_poke(Ctx& c, uint32_t addr, uint32_t v) {
       const int p = (addr == 0x10) ? OB_P0 : OB_P1;
       const int newx = (hpos < MN_HBLANK) ? 3 : ((hpos - MN_HBLANK + 5) % 160);
       const int zone = resp_zone((p == OB_P0) ? s.nusiz0 : s.nusiz1, s.pos[p], newx);
-      if (zone == 1) tia_advance(c, clock + 11);
+      if (zone == 1) tia_advance(c, rel + 11);
       s.pos[p] = uint8_t(newx);
       set_flag(s, (p == OB_P0) ? F_SUP0 : F_SUP1, zone >= 0);
       break;
@@ -442,7 +483,6 @@ MN_HD MN_NOINLINE void tia_poke(Ctx& c, uint32_t addr, uint32_t v) {
         s.pos[k] = uint8_t(p);
       }
       s.flags &= ~(F_SUP0 | F_SUP1);
-      s.last_hmove_clk = clock;
       break;
     }
     case 0x2B: for (int k = 0; k < 5; ++k) s.hm[k] = 0; break;
@@ -451,12 +491,76 @@ MN_HD MN_NOINLINE void tia_poke(Ctx& c, uint32_t addr, uint32_t v) {
   }
 }
 
+// a frame ends on the picture side: account for what it left in its buffer (see F_ANOMALY)
+MN_HD MN_INLINE void picture_close_frame(EnvState& s) {
+  const int b = (s.flags & F_CURFB) ? 1 : 0;
+  const uint32_t len = uint32_t(s.fb_pos);
+  if (s.flags & F_PIXELS) { if (s.pend_len[b] > len) s.flags |= F_ANOMALY; s.pend_len[b] = 0; }
+  else if (len > s.pend_len[b]) s.pend_len[b] = uint16_t(len);
+}
+// ... and the next one starts (what the emulated TIA's frame start does to the picture)
+MN_HD MN_INLINE void picture_open_frame(EnvState& s, bool pixels) {
+  picture_close_frame(s);
+  s.flags ^= F_CURFB;
+  s.flags = pixels ? (s.flags | F_PIXELS) : (s.flags & ~F_PIXELS);
+  s.clk_last_update = 228 * MN_YSTART;
+  s.clks_to_eol = 228;
+  s.fb_pos = 0;
+}
+
+// run every queued write through the picture
+MN_HD MN_NOINLINE void tia_drain(Ctx& c) {
+  const int n = c.fifo_n;
+  for (int i = 0; i < n; ++i) {
+    const uint32_t e = c.fifo[i];
+    if (e & MN_FIFO_FRAME) picture_open_frame(*c.s, (e & 1u) != 0);
+    else tia_apply(c, int32_t(e & 0x1FFFFu), (e >> 17) & 0x3Fu, (e >> 23) & 0xFFu);
+  }
+  c.fifo_n = 0;
+}
+MN_HD MN_INLINE void fifo_push(Ctx& c, uint32_t e) {
+  if (c.fifo_n >= MN_FIFO_CAP) tia_drain(c);   // safety net; warps drain together well before this (MN_FIFO_HIGH)
+  c.fifo[c.fifo_n++] = e;
+}
+
+// ---- program side: a TIA register write.  Only what the 6502 can observe happens now.
+MN_HD MN_INLINE void tia_poke(Ctx& c, uint32_t addr, uint32_t v) {
+  EnvState& s = *c.s;
+  addr &= 0x3F;
+  const int32_t clock = s.cycles * 3;
+  const int32_t rel = clock - s.clk_frame_start;
+  if ((rel / 228) > MN_MAX_SCANLINES) s.flags = (s.flags | F_STOP) & ~F_PARTIAL;
+  if (addr <= 0x03) {
+    if (addr == 0x00) {
+      s.vsync = uint8_t(v);
+      if (v & 0x02) s.vsync_finish_clk = clock + 228;
+      else if (clock >= s.vsync_finish_clk) { s.vsync_finish_clk = MN_NEVER; s.flags = (s.flags | F_STOP) & ~F_PARTIAL; }
+      return;
+    }
+    if (addr == 0x01) {
+      if (!(s.vblank_cpu & 0x80) && (v & 0x80)) s.flags |= F_DUMP;
+      if ((s.vblank_cpu & 0x80) && !(v & 0x80)) { s.flags &= ~F_DUMP; s.dump_disabled_cycle = s.cycles; }
+      s.vblank_cpu = uint8_t(v);
+    } else {
+      const int32_t rest = 76 - ((s.cycles - (s.clk_frame_start / 3)) % 76);
+      if (addr == 0x02) { if (rest < 76) s.cycles += rest; }
+      else s.cycles += rest - 1;
+      return;
+    }
+  } else if (addr > 0x2C || (addr >= 0x15 && addr <= 0x1A)) return;   // audio, unused
+  // 17 bits of clock: far beyond the last drawn line only the position within the line still matters
+  const int32_t rel17 = (rel < 570 * 228) ? rel : (570 * 228 + rel % 228);
+  fifo_push(c, uint32_t(rel17) | (addr << 17) | ((v & 0xFFu) << 23));
+}
+
 MN_HD MN_NOINLINE uint32_t tia_peek(Ctx& c, uint32_t addr) {
   EnvState& s = *c.s;
-  tia_advance(c, s.cycles * 3);
   const uint32_t noise = s.dbus & 0x3Fu;
   const uint32_t reg = addr & 0x0F;
   if (reg < 8) {
+    // collision latches need the picture up to date
+    tia_drain(c);
+    tia_advance(c, s.cycles * 3 - s.clk_frame_start);
     // latch pairs in read order: CXM0P CXM1P CXP0FB CXP1FB CXM0FB CXM1FB CXBLPF CXPPMM
     const uint32_t hi = (reg == 6) ? 0x1000u : (reg == 7) ? 0x2000u : (1u << (2 * reg));
     const uint32_t lo = (reg == 6) ? 0u : (reg == 7) ? 0x4000u : (2u << (2 * reg));
@@ -479,6 +583,7 @@ MN_HD MN_NOINLINE uint32_t tia_peek(Ctx& c, uint32_t addr) {
   if (reg == 13) return ((s.flags & F_INPT5) ? 0x80u : 0u) | noise;
   return noise;
 }
+
 
 // ------------------------------------------------------------------ RIOT
 MN_HD MN_NOINLINE uint32_t riot_peek(Ctx& c, uint32_t addr) {
@@ -747,25 +852,18 @@ MN_HD MN_INLINE void cpu_step(Ctx& c) {
 }
 
 // ------------------------------------------------------------------ frame
-MN_HD MN_INLINE void frame_begin(EnvState& s) {
-  s.flags ^= F_CURFB;
+// program side of the emulated TIA's frame start: rebase every cycle-stamped quantity, tell the picture
+MN_HD MN_INLINE void frame_begin(Ctx& c, bool pixels) {
+  EnvState& s = *c.s;
   const int32_t clocks = ((s.cycles * 3) - s.clk_frame_start) % 228;
   const int32_t cy = s.cycles;
   s.timer_set_cycle -= cy; s.irq_reset_cycle -= cy; s.dump_disabled_cycle -= cy;
-  s.last_hmove_clk -= cy * 3;
   if (s.vsync_finish_clk != MN_NEVER) s.vsync_finish_clk -= cy * 3;
   s.cycles = 0;
   s.clk_frame_start = -clocks;
-  s.clk_last_update = s.clk_frame_start + 228 * MN_YSTART;
-  s.clks_to_eol = 228;
-  s.fb_pos = 0;
+  fifo_push(c, MN_FIFO_FRAME | (pixels ? 1u : 0u));
 }
-MN_HD MN_INLINE void run_frame(Ctx& c) {
-  EnvState& s = *c.s;
-  if (!(s.flags & F_PARTIAL)) frame_begin(s);
-  s.flags = (s.flags | F_PARTIAL) & ~F_STOP;
-  for (int n = 25000; n > 0 && !(s.flags & F_STOP); --n) cpu_step(c);
-}
+
 
 // ------------------------------------------------------------------ ALE layer
 MN_HD MN_INLINE void rng_advance(uint32_t* r) {
@@ -899,30 +997,23 @@ MN_HD MN_INLINE void latch_inputs(EnvState& s, int action) {
     s.flags |= F_INPT4 | F_INPT5;
   }
 }
-MN_HD MN_INLINE void ale_emulate(Ctx& c, int action, int frames) {
-  EnvState& s = *c.s;
-  if (s.ctrl == CTRL_JOYSTICK) latch_inputs(s, action);
-  for (int f = 0; f < frames; ++f) {
-    if (s.ctrl != CTRL_JOYSTICK) latch_inputs(s, action);
-    run_frame(c);
-    game_observe(c);
-  }
-}
-
 MN_HD MN_INLINE void console_reset(Ctx& c, uint32_t rnd) {
   EnvState& s = *c.s;
   s.cycles = 0;
   // RIOT
   s.timer = uint8_t(25 + (rnd % 75)); s.tshift = 6; s.timer_set_cycle = 0; s.irq_reset_cycle = 0; s.ddra = 0; s.ddrb = 0;
-  // TIA
+  // TIA (the write FIFO is empty here: units always end drained)
   s.clk_frame_start = 0; s.clk_last_update = 0; s.clks_to_eol = 228; s.vsync_finish_clk = MN_NEVER; s.fb_pos = 0;
-  s.last_hmove_clk = 0; s.dump_disabled_cycle = 0; s.pf = 0; s.collision = 0;
+  s.dump_disabled_cycle = 0; s.pf = 0; s.collision = 0; s.pend_len[0] = s.pend_len[1] = 0;
   s.flags &= (F_TERMINAL | F_STARTED | F_INPT4 | F_INPT5);
-  s.vsync = s.vblank = s.nusiz0 = s.nusiz1 = s.ctrlpf = s.enabled = 0;
+  s.vsync = s.vblank = s.vblank_cpu = s.nusiz0 = s.nusiz1 = s.ctrlpf = s.enabled = 0;
   for (int k = 0; k < 4; ++k) s.col[k] = 0;
   s.grp0 = s.grp1 = s.dgrp0 = s.dgrp1 = s.cur_grp0 = s.cur_grp1 = 0;
   for (int k = 0; k < 5; ++k) { s.pos[k] = 0; s.hm[k] = 0; }
-  for (int i = 0; i < 2 * MN_FRAME_BYTES; ++i) c.fb[i] = 0;
+  {
+    uint32_t* p = reinterpret_cast<uint32_t*>(c.fb);
+    for (int i = 0; i < 2 * MN_FRAME_BYTES / 4; ++i) p[i] = 0u;
+  }
   // cartridge
   s.bank = (s.cart == CART_F8) ? 1 : 0; s.slice0 = 4; s.slice1 = 5; s.slice2 = 6;
   // CPU
@@ -931,34 +1022,91 @@ MN_HD MN_INLINE void console_reset(Ctx& c, uint32_t rnd) {
   s.PC = uint16_t(lo | (bus_read(c, 0xFFFD) << 8));
 }
 
-// ALE reset_game(): console reset, 60 NOOP frames, 4 frames of the RESET switch, per-game start actions
-MN_HD MN_INLINE void ale_reset(Ctx& c) {
+// ------------------------------------------------------------------ units of work
+// Everything a kernel launch asks of one environment is a UNIT: a fixed sequence of single-frame jobs,
+// advanced one 6502 instruction per tick so that all lanes of a warp stay in one flat loop.
+//   U_ACTS   `total` x ALE act(action): two RNG draws, frozen (nothing emulated, reward 0) once the episode is
+//            over, else one frame + the per-game RAM scrape.  next() = 4 acts  (atari_emulator.py:90-100)
+//   U_RESET  ALE reset_game(): console reset, 60 NOOP frames, 4 frames of the RESET switch, settings reset,
+//            the game's start actions; then `noops` act(NOOP) calls          (atari_emulator.py:70-77)
+//   U_POWER_ON  ALE construction + loadROM: seed the RNG, fill RIOT RAM with its garbage, then U_RESET with no no-ops
+enum { U_ACTS = 0, U_RESET = 1, U_POWER_ON = 2 };
+struct Unit {
+  int kind, idx, total, action, nstart, budget;
+  int32_t reward;
+  bool in_frame, frozen_last, job_is_act;
+};
+
+MN_HD MN_INLINE void unit_idle(Unit& u) { u.kind = U_ACTS; u.idx = u.total = 0; u.in_frame = false; u.reward = 0; u.frozen_last = false; }
+
+MN_HD MN_INLINE void unit_init(Ctx& c, Unit& u, int kind, int action, int count, uint32_t seed) {
   EnvState& s = *c.s;
+  u.kind = kind; u.idx = 0; u.action = action; u.reward = 0; u.in_frame = false; u.frozen_last = false; u.budget = 0;
+  u.job_is_act = false; u.nstart = 0;
+  c.fifo_n = 0;
+  s.flags &= ~F_ANOMALY;
+  if (kind == U_ACTS) { u.total = count; return; }
+  if (kind == U_POWER_ON) {
+    rng_seed(s.rng, seed);
+    for (int i = 0; i < 128; ++i) ram_at(c, i) = uint8_t(rng_next(s.rng));
+    s.flags = 0; s.frame_number = 0; s.ring_head = 0; s.pend_len[0] = s.pend_len[1] = 0;
+  }
   s.episode_frame_number = 0;
   s.left_paddle = s.right_paddle = MN_PADDLE_DEFAULT;
   console_reset(c, rng_next(s.rng));
-  ale_emulate(c, 0, 60);
-  ale_emulate(c, 40, 4);
-  s.score = 0; s.reward = 0; s.flags &= ~(F_TERMINAL | F_STARTED); s.lives = game_start_lives(s.game);
-  const int ns = game_start_actions(s.game);
-  for (int i = 0; i < ns; ++i) ale_emulate(c, 1, 1);
+  u.nstart = game_start_actions(s.game);
+  u.total = 64 + u.nstart + count;
 }
-// ALE act(): one frame; frozen (reward 0, nothing emulated) once the episode is over
-MN_HD MN_INLINE int32_t ale_act(Ctx& c, int action) {
+MN_HD MN_INLINE bool unit_has_work(const Unit& u) { return u.in_frame || u.idx < u.total; }
+
+MN_HD MN_INLINE void unit_job_done(Ctx& c, Unit& u) {
   EnvState& s = *c.s;
-  rng_advance(s.rng); rng_advance(s.rng);
-  if (s.flags & F_TERMINAL) return 0;
-  ale_emulate(c, action, 1);
-  s.frame_number++; s.episode_frame_number++;
-  return s.reward;
+  u.in_frame = false;
+  game_observe(c);
+  if (u.job_is_act) { s.frame_number++; s.episode_frame_number++; u.reward += s.reward; }
+  if (u.kind != U_ACTS && u.idx == 64) {   // RomSettings::reset() after the RESET-switch frames
+    s.score = 0; s.reward = 0; s.flags &= ~(F_TERMINAL | F_STARTED); s.lives = game_start_lives(s.game);
+  }
+  // AtariEmulator reads ale.lives() right after loadROM / reset_game (atari_emulator.py:31,73)
+  if (u.kind != U_ACTS && u.idx == 64 + u.nstart) s.host_lives = s.lives;
 }
-// first-time construction: ALE seeds its RNG, fills RIOT RAM with garbage, then resets once (loadROM)
-MN_HD MN_INLINE void ale_power_on(Ctx& c, uint32_t seed) {
+
+// one tick: start the next job, or run one instruction of the frame in progress
+MN_HD MN_INLINE void unit_tick(Ctx& c, Unit& u) {
   EnvState& s = *c.s;
-  rng_seed(s.rng, seed);
-  for (int i = 0; i < 128; ++i) ram_at(c, i) = uint8_t(rng_next(s.rng));
-  s.flags = 0; s.frame_number = 0; s.ring_head = 0;
-  ale_reset(c);
+  if (!u.in_frame) {
+    int action;
+    if (u.kind == U_ACTS) { action = u.action; u.job_is_act = true; }
+    else if (u.idx < 60) { action = 0; u.job_is_act = false; }
+    else if (u.idx < 64) { action = 40; u.job_is_act = false; }
+    else if (u.idx < 64 + u.nstart) { action = 1; u.job_is_act = false; }
+    else { action = 0; u.job_is_act = true; }
+    const bool pixels = c.all_pixels || (u.idx >= u.total - 2);
+    u.idx++;
+    if (u.job_is_act) {
+      rng_advance(s.rng); rng_advance(s.rng);
+      if (u.kind == U_ACTS && u.idx == u.total) u.frozen_last = (s.flags & F_TERMINAL) != 0;
+      if (s.flags & F_TERMINAL) return;   // act() of a finished episode: nothing is emulated
+    }
+    latch_inputs(s, action);
+    if (!(s.flags & F_PARTIAL)) frame_begin(c, pixels);
+    s.flags = (s.flags | F_PARTIAL) & ~F_STOP;
+    u.budget = 25000;
+    u.in_frame = true;
+    return;
+  }
+  cpu_step(c);
+  if ((s.flags & F_STOP) || --u.budget == 0) unit_job_done(c, u);
+}
+
+// after the unit's last tick: flush the picture and report whether the pixel-less frames were harmless
+MN_HD MN_INLINE bool unit_finish(Ctx& c) {
+  EnvState& s = *c.s;
+  tia_drain(c);
+  picture_close_frame(s);
+  const bool bad = (s.flags & F_ANOMALY) || s.pend_len[0] != 0 || s.pend_len[1] != 0;
+  s.flags &= ~F_ANOMALY;
+  return bad;
 }
 
 }  // namespace mn

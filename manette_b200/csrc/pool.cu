@@ -84,7 +84,7 @@ struct GameDev {
 struct PoolDev {             // kernel argument block (by value)
   GameDev games[MN_MAX_GAMES];
   int32_t n_games, n_envs, slots /* env slots per warp */, depth, num_actions, nb_choices;
-  int32_t single_life, random_start, seed, env_id_offset;
+  int32_t single_life, random_start, seed, env_id_offset, draw_all_frames;
   int32_t tab_rep[32];
   const uint8_t* roms;
   EnvState* env;
@@ -106,6 +106,7 @@ struct PoolDev {             // kernel argument block (by value)
   int32_t* counts;           // 3 x MN_MAX_GAMES
   int32_t* error;            // sticky: 1 = episode over right after reset (atari_emulator.py:108-109)
   unsigned long long* total_next;
+  unsigned long long* redo_count;   // units re-run with every frame drawn (exact fallback of the pixel-less frames)
   const Tables* tables;
 };
 
@@ -164,7 +165,8 @@ __global__ void k_single_list(PoolDev p, int which, int env, int ale_action) {
 }
 
 // One round of emulation for the envs on list `in`.  Dynamic shared memory:
-//   [rom | tables | core slots (8 warps x slots x 43 words) | ram (8 warps x slots x 128 B, word-interleaved)]
+//   [rom | tables | core slots (8 warps x slots x 43 words) | ram (8 warps x slots x 128 B, word-interleaved)
+//    | TIA write FIFOs (8 warps x slots x 17 words)]
 __global__ void __launch_bounds__(MN_THREADS, 2) k_round(PoolDev p, int mode, int in, int out) {
   extern __shared__ __align__(16) uint8_t smem[];
   // ---- which game does this block serve
@@ -176,10 +178,12 @@ __global__ void __launch_bounds__(MN_THREADS, 2) k_round(PoolDev p, int mode, in
   const int lo = int((long long)count * j / G.n_blks), hi = int((long long)count * (j + 1) / G.n_blks);
   if (hi <= lo) return;   // whole block idle (uniform)
   const int rom_bytes = (G.rom_size + 15) & ~15;
+  const int nslots = MN_WARPS_PER_BLOCK * p.slots;
   uint8_t* s_rom = smem;
   Tables* s_tab = reinterpret_cast<Tables*>(smem + rom_bytes);
   uint32_t* s_core = reinterpret_cast<uint32_t*>(smem + rom_bytes + sizeof(Tables));
-  uint8_t* s_ram = reinterpret_cast<uint8_t*>(s_core + MN_WARPS_PER_BLOCK * p.slots * MN_CORE_WORDS);
+  uint8_t* s_ram = reinterpret_cast<uint8_t*>(s_core + nslots * MN_CORE_WORDS);
+  uint32_t* s_fifo = reinterpret_cast<uint32_t*>(s_ram + nslots * 128);
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.roms + G.rom_off);
     uint4* dst = reinterpret_cast<uint4*>(s_rom);
@@ -193,47 +197,72 @@ __global__ void __launch_bounds__(MN_THREADS, 2) k_round(PoolDev p, int mode, in
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m = hi - lo;
   const int wlo = lo + m * warp / MN_WARPS_PER_BLOCK, whi = lo + m * (warp + 1) / MN_WARPS_PER_BLOCK;
-  if (lane >= whi - wlo) return;
+  const bool active = lane < whi - wlo;
+  const unsigned wmask = __ballot_sync(0xFFFFFFFFu, active);   // the lanes that vote in the loops below
+  if (!active) return;
   const int e = p.lists[size_t(in) * p.n_envs + G.env0 + wlo + lane];
   const int slot = warp * p.slots + lane;
   EnvState* s = reinterpret_cast<EnvState*>(s_core + slot * MN_CORE_WORDS);
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.env + e);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(s);
-#pragma unroll 6
-    for (int i = 0; i < int(sizeof(EnvState) / 4); ++i) dst[i] = src[i];
-  }
   Ctx c;
   c.s = s; c.rom = s_rom; c.tab = s_tab;
   c.ram = s_ram + warp * p.slots * 128 + lane * 4;
   c.ram_stride = p.slots * 4;
   c.fb = p.frames + size_t(e) * (2 * MN_FRAME_BYTES);
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.ram + size_t(e) * 128);
-    for (int i = 0; i < 32; ++i) *reinterpret_cast<uint32_t*>(c.ram + i * c.ram_stride) = src[i];
-  }
-  const bool single_life = p.single_life != 0;
+  c.fifo = s_fifo + slot * (MN_FIFO_CAP + 1);
+  c.fifo_n = 0;
+  // what this launch asks of the env
+  int kind = U_ACTS, action = 0, ucount = MN_ACTION_REPEAT;
+  uint32_t seed = 0;
   if (mode == ROUND_POWER_ON) {
-    s->game = uint8_t(G.game_id); s->cart = uint8_t(G.cart); s->ctrl = uint8_t(G.ctrl);
-    s->host_lives = 0;
     // atari_emulator.py:20: ALE seed = random_seed * (actor_id + 1); loadROM resets once
-    ale_power_on(c, uint32_t(p.seed) * uint32_t(p.env_id_offset + e + 1));
-    s->host_lives = s->lives;
+    kind = U_POWER_ON; ucount = 0; seed = uint32_t(p.seed) * uint32_t(p.env_id_offset + e + 1);
     p.episode[e] = 0;
   } else if (mode == ROUND_RESET) {
     const uint32_t ep = p.episode[e];
-    const int noops = p.random_start ? int(start_noops(uint32_t(p.seed), uint32_t(p.env_id_offset + e), ep)) : 0;
+    kind = U_RESET;
+    ucount = p.random_start ? int(start_noops(uint32_t(p.seed), uint32_t(p.env_id_offset + e), ep)) : 0;
     p.episode[e] = ep + 1;
-    env_new_game(c, noops);
-  } else {
-    const int action = (mode == ROUND_INITIAL) ? int(G.actions[0]) : p.cur_action[e];
-    const NextOut o = env_next(c, action, single_life);
+  } else action = (mode == ROUND_INITIAL) ? int(G.actions[0]) : p.cur_action[e];
+
+  // First pass: only the pooled frames keep their pixels.  If that turns out to have been visible
+  // (unit_finish), the env is reloaded and the unit re-run with every frame drawn.
+  Unit res;
+  bool bad = false;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const bool mine = (attempt == 0) || bad;
+    Unit u;
+    unit_idle(u);
+    if (mine) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(p.env + e);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(s);
+#pragma unroll 6
+      for (int i = 0; i < int(sizeof(EnvState) / 4); ++i) dst[i] = src[i];
+      const uint32_t* rsrc = reinterpret_cast<const uint32_t*>(p.ram + size_t(e) * 128);
+      for (int i = 0; i < 32; ++i) *reinterpret_cast<uint32_t*>(c.ram + i * c.ram_stride) = rsrc[i];
+      if (mode == ROUND_POWER_ON) { s->game = uint8_t(G.game_id); s->cart = uint8_t(G.cart); s->ctrl = uint8_t(G.ctrl); s->host_lives = 0; }
+      c.all_pixels = (attempt == 1) || (p.draw_all_frames != 0);
+      unit_init(c, u, kind, action, ucount, seed);
+    }
+    for (;;) {
+      const bool work = unit_has_work(u);
+      if (!__any_sync(wmask, work)) break;
+      if (work) unit_tick(c, u);
+      if (__any_sync(wmask, c.fifo_n >= MN_FIFO_HIGH)) tia_drain(c);
+    }
+    if (mine) { bad = unit_finish(c); res = u; }
+    if (!__any_sync(wmask, bad)) break;
+    if (attempt == 0 && bad) atomicAdd(p.redo_count, 1ull);
+  }
+
+  const bool single_life = p.single_life != 0;
+  if (mode != ROUND_POWER_ON && mode != ROUND_RESET) {
+    const NextOut o = env_next_result(*s, res, single_life);
     const int head = s->ring_head;
     s->ring_head = uint8_t((head + 1) & (MN_STACK - 1));
     const int pool_mode = o.pool_single ? ((s->flags & F_CURFB) ? 2 : 1) : 0;
     p.push_info[e] = uint8_t(head | (pool_mode << 2));
     if (mode == ROUND_INITIAL) {
-      if (out < 0 && o.terminal) atomicExch(p.error, 1);   // last of the four start frames: 'This should never happen.'
+      if (out == -1 && o.terminal) atomicExch(p.error, 1);   // last of the four start frames: 'This should never happen.'
     } else {
       p.reward_acc[e] += o.reward;
       p.next_calls[e] += 1;
@@ -586,6 +615,7 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
   d.n_games = cfg->n_games; d.n_envs = n; d.depth = cfg->rgb ? 3 : 1; d.num_actions = max_actions;
   d.nb_choices = cfg->nb_choices > 0 ? cfg->nb_choices : 1;
   d.single_life = cfg->single_life_episodes; d.random_start = cfg->random_start; d.seed = cfg->random_seed; d.env_id_offset = cfg->env_id_offset;
+  d.draw_all_frames = cfg->draw_all_frames;
   h->max_rep = 0;
   for (int i = 0; i < cfg->nb_choices; ++i) {
     if (cfg->tab_rep[i] < 0 || cfg->tab_rep[i] > 1000) { delete h; return fail("mn_create: tab_rep entries must be 0..1000"); }
@@ -609,7 +639,8 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
     blk += G.n_blks;
   }
   h->round_grid = blk;
-  h->round_smem = ((max_rom + 15) & ~size_t(15)) + sizeof(Tables) + size_t(MN_WARPS_PER_BLOCK) * slots * (MN_CORE_WORDS * 4 + 128);
+  h->round_smem = ((max_rom + 15) & ~size_t(15)) + sizeof(Tables) +
+                  size_t(MN_WARPS_PER_BLOCK) * slots * (MN_CORE_WORDS * 4 + 128 + (MN_FIFO_CAP + 1) * 4);
   if (h->round_smem > size_t(prop.sharedMemPerBlockOptin)) { delete h; return fail("mn_create: shared memory budget exceeded"); }
   CU(cudaFuncSetAttribute(k_round, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->round_smem)));
 
@@ -640,6 +671,7 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
   rc |= dev_alloc(h, &d.counts, size_t(3 * MN_MAX_GAMES));
   rc |= dev_alloc(h, &d.error, size_t(1));
   rc |= dev_alloc(h, &d.total_next, size_t(1));
+  rc |= dev_alloc(h, &d.redo_count, size_t(1));
   rc |= dev_alloc(h, &h->tables_dev, size_t(1));
   if (rc) { mn_destroy(h); return -1; }
   d.roms = roms;
@@ -897,6 +929,15 @@ int mn_profile_end(mn_handle h, double* ms_by_kind4, int64_t* launches_by_kind4)
     launches_by_kind4[h->ev_kind[i]] += 1;
   }
   h->profiling = false; h->ev_used = 0; h->ev_kind.clear();
+  return 0;
+}
+
+int mn_redo_count(mn_handle h, int64_t* out) {
+  if (!h || !out) return fail("mn_redo_count: null argument");
+  CU(cudaSetDevice(h->device));
+  unsigned long long v = 0;
+  CU(cudaMemcpy(&v, h->d.redo_count, sizeof(v), cudaMemcpyDeviceToHost));
+  *out = int64_t(v);
   return 0;
 }
 

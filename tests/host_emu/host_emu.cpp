@@ -3,7 +3,7 @@
 // Never loaded by the product package.
 #include <vector>
 #include <cstring>
-#include "../../manette_b200/csrc/emu_core.cuh"
+#include "../../manette_b200/csrc/atari_env.cuh"
 #include "../../manette_b200/csrc/decode_tables.h"
 #include "../../manette_b200/csrc/game_db.h"
 
@@ -11,10 +11,36 @@ using namespace mn;
 
 struct HostEnv {
   EnvState s; Ctx c; Tables tab; std::vector<uint8_t> rom; std::vector<uint8_t> fb; uint8_t ram[128];
+  uint32_t fifo[MN_FIFO_CAP];
+  int drain_at;        // drain when this many writes are pending (tests sweep it)
+  int redo_count;      // units that had to be re-run with every frame drawn
+  Unit last;
 };
 
+// the flat loop of k_round for a single environment, with the exact fallback
+static void run_unit(HostEnv* e, int kind, int action, int count, uint32_t seed, bool all_pixels) {
+  EnvState snap = e->s;
+  uint8_t ram_snap[128];
+  memcpy(ram_snap, e->ram, 128);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    e->c.all_pixels = all_pixels || attempt == 1;
+    Unit u;
+    unit_init(e->c, u, kind, action, count, seed);
+    while (unit_has_work(u)) {
+      unit_tick(e->c, u);
+      if (e->c.fifo_n >= e->drain_at) tia_drain(e->c);
+    }
+    const bool bad = unit_finish(e->c);
+    e->last = u;
+    if (!bad) break;
+    e->redo_count++;
+    e->s = snap;
+    memcpy(e->ram, ram_snap, 128);
+  }
+}
+
 extern "C" {
-void* he_create(const uint8_t* rom, int n, const char* game, uint32_t seed) {
+void* he_create(const uint8_t* rom, int n, const char* game, uint32_t seed, int skip_frames) {
   HostEnv* e = new HostEnv();
   memset(&e->s, 0, sizeof(e->s));
   build_tables(&e->tab);
@@ -23,12 +49,24 @@ void* he_create(const uint8_t* rom, int n, const char* game, uint32_t seed) {
   int g = game_id_from_name(game);
   e->s.game = (uint8_t)g; e->s.cart = (uint8_t)detect_cart(rom, n); e->s.ctrl = (uint8_t)game_db(g).ctrl;
   e->c.s = &e->s; e->c.rom = e->rom.data(); e->c.ram = e->ram; e->c.ram_stride = 4; e->c.fb = e->fb.data(); e->c.tab = &e->tab;
-  ale_power_on(e->c, seed);
+  e->c.fifo = e->fifo; e->c.fifo_n = 0;
+  e->drain_at = MN_FIFO_HIGH; e->redo_count = 0;
+  run_unit(e, U_POWER_ON, 0, 0, seed, !skip_frames);
   return e;
 }
 void he_destroy(void* h) { delete (HostEnv*)h; }
-int he_act(void* h, int a) { return ale_act(((HostEnv*)h)->c, a); }
-void he_reset_game(void* h) { ale_reset(((HostEnv*)h)->c); }
+void he_set_drain_at(void* h, int n) { ((HostEnv*)h)->drain_at = n < 1 ? 1 : (n > MN_FIFO_CAP ? MN_FIFO_CAP : n); }
+int he_redo_count(void* h) { return ((HostEnv*)h)->redo_count; }
+// ALE act(): one frame, every frame drawn
+int he_act(void* h, int a) { HostEnv* e = (HostEnv*)h; run_unit(e, U_ACTS, a, 1, 0, true); return e->last.reward; }
+// AtariEmulator.__action_repeat: 4 acts; with skip_frames only the two pooled frames keep their pixels
+int he_next(void* h, int a, int skip_frames, int* pool_single) {
+  HostEnv* e = (HostEnv*)h;
+  run_unit(e, U_ACTS, a, 4, 0, !skip_frames);
+  if (pool_single) *pool_single = e->last.frozen_last ? 1 : 0;
+  return e->last.reward;
+}
+void he_reset_game(void* h, int noops, int skip_frames) { run_unit((HostEnv*)h, U_RESET, 0, noops, 0, !skip_frames); }
 int he_game_over(void* h) { return (((HostEnv*)h)->s.flags & F_TERMINAL) ? 1 : 0; }
 int he_lives(void* h) { return ((HostEnv*)h)->s.lives; }
 void he_get_ram(void* h, uint8_t* out) { memcpy(out, ((HostEnv*)h)->ram, 128); }
@@ -36,6 +74,7 @@ void he_get_screen(void* h, uint8_t* out) {
   HostEnv* e = (HostEnv*)h;
   memcpy(out, e->fb.data() + ((e->s.flags & F_CURFB) ? MN_FRAME_BYTES : 0), MN_FRAME_BYTES);
 }
+void he_get_both_screens(void* h, uint8_t* out) { memcpy(out, ((HostEnv*)h)->fb.data(), 2 * MN_FRAME_BYTES); }
 void he_get_cpu(void* h, int32_t* out) {
   EnvState& s = ((HostEnv*)h)->s;
   out[0] = s.A; out[1] = s.X; out[2] = s.Y; out[3] = s.SP; out[4] = s.PC; out[5] = (int32_t)pack_ps(s); out[6] = s.cycles;

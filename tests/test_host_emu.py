@@ -1,0 +1,119 @@
+"""CPU pre-check of the DEVICE emulator core: manette_b200/csrc/emu_core.cuh compiled with the host compiler
+(tests/host_emu) against the oracle, so the kernels' logic is diffed on machines without a GPU.
+(The GPU parity tests proper are in test_gpu_parity.py.)"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import util
+from util import GAMES12, rom_bytes
+
+import orc_loader
+
+HE_DIR = os.path.join(util.ROOT, "tests", "host_emu")
+
+
+@pytest.fixture(scope="module")
+def libs():
+    so = os.path.join(HE_DIR, "libhost_emu.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so,
+                           os.path.join(HE_DIR, "host_emu.cpp")])
+    H = C.CDLL(so)
+    H.he_create.restype = C.c_void_p
+    H.he_create.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_uint32, C.c_int]
+    H.he_destroy.argtypes = [C.c_void_p]
+    H.he_set_drain_at.argtypes = [C.c_void_p, C.c_int]
+    H.he_redo_count.argtypes = [C.c_void_p]
+    H.he_act.argtypes = [C.c_void_p, C.c_int]
+    H.he_next.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    H.he_reset_game.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    for f in ("he_game_over", "he_lives"):
+        getattr(H, f).argtypes = [C.c_void_p]
+    for f in ("he_get_ram", "he_get_screen", "he_get_both_screens", "he_get_cpu"):
+        getattr(H, f).argtypes = [C.c_void_p, C.c_void_p]
+    return orc_loader.lib(), H
+
+
+def _taps(L, H, o, h):
+    ro, rh = np.zeros(128, np.uint8), np.zeros(128, np.uint8)
+    so, sh = np.zeros(33600, np.uint8), np.zeros(33600, np.uint8)
+    co, ch = np.zeros(10, np.int32), np.zeros(10, np.int32)
+    L.orc_get_ram(o, ro.ctypes.data); H.he_get_ram(h, rh.ctypes.data)
+    L.orc_get_screen(o, so.ctypes.data); H.he_get_screen(h, sh.ctypes.data)
+    L.orc_get_cpu(o, co.ctypes.data); H.he_get_cpu(h, ch.ctypes.data)
+    return (ro, so, co), (rh, sh, ch)
+
+
+@pytest.mark.parametrize("game", GAMES12)
+def test_every_frame_matches_oracle(libs, game):
+    """act() by act(): RAM, raw screen, CPU registers, reward, game over -- every frame drawn."""
+    L, H = libs
+    rom = rom_bytes(game)
+    o = L.orc_create(rom, len(rom), game.encode(), 6)
+    h = H.he_create(rom, len(rom), game.encode(), 6, 0)
+    n = L.orc_num_actions(o)
+    acts = np.zeros(18, np.int32)
+    L.orc_minimal_actions(o, acts.ctypes.data)
+    rng = np.random.RandomState(1)
+    for drain_at, frames in ((12, 500), (1, 120), (16, 120)):
+        H.he_set_drain_at(h, drain_at)
+        for i in range(frames):
+            a = int(acts[rng.randint(n)])
+            assert L.orc_act(o, a) == H.he_act(h, a), (game, i)
+            (ro, so, co), (rh, sh, ch) = _taps(L, H, o, h)
+            assert np.array_equal(ro, rh), (game, i, "ram")
+            assert np.array_equal(so, sh), (game, i, "screen", int((so != sh).sum()))
+            assert np.array_equal(co, ch), (game, i, "cpu")
+            assert L.orc_game_over(o) == H.he_game_over(h)
+            if L.orc_game_over(o):
+                L.orc_reset_game(o); H.he_reset_game(h, 0, 0)
+    L.orc_destroy(o); H.he_destroy(h)
+
+
+@pytest.mark.parametrize("game", GAMES12)
+def test_next_with_pixel_less_frames_matches_oracle(libs, game):
+    """next() by next() with only the two pooled frames drawn (the product's mode): both frame buffers,
+    RAM, reward, terminal must still be exact, including across resets with start no-ops."""
+    L, H = libs
+    rom = rom_bytes(game)
+    o = L.orc_create(rom, len(rom), game.encode(), 9)
+    h = H.he_create(rom, len(rom), game.encode(), 9, 1)
+    n = L.orc_num_actions(o)
+    acts = np.zeros(18, np.int32)
+    L.orc_minimal_actions(o, acts.ctypes.data)
+    rng = np.random.RandomState(2)
+    both = np.zeros((2, 33600), np.uint8)
+    prev = np.zeros(33600, np.uint8)
+    cur = np.zeros(33600, np.uint8)
+    for i in range(220):
+        a = int(acts[rng.randint(n)])
+        want_r, grabs = 0, []
+        for f in range(4):
+            want_r += L.orc_act(o, a)
+            if f >= 2:
+                g = np.zeros(33600, np.uint8)
+                L.orc_get_screen(o, g.ctypes.data)
+                grabs.append(g)
+        single = C.c_int()
+        got_r = H.he_next(h, a, 1, C.byref(single))
+        assert want_r == got_r, (game, i)
+        (ro, so, co), (rh, sh, ch) = _taps(L, H, o, h)
+        assert np.array_equal(ro, rh) and np.array_equal(co, ch), (game, i)
+        assert np.array_equal(so, sh), (game, i, "current screen")
+        H.he_get_both_screens(h, both.ctypes.data)
+        want_max = np.maximum(grabs[0], grabs[1])
+        got_max = sh if single.value else np.maximum(both[0], both[1])
+        assert np.array_equal(want_max, got_max), (game, i, "pooled frames")
+        assert L.orc_game_over(o) == H.he_game_over(h)
+        if L.orc_game_over(o) or i % 70 == 69:
+            noops = int(rng.randint(0, 31))
+            L.orc_reset_game(o)
+            for _ in range(noops):
+                L.orc_act(o, 0)
+            H.he_reset_game(h, noops, 1)
+            (ro, so, co), (rh, sh, ch) = _taps(L, H, o, h)
+            assert np.array_equal(ro, rh) and np.array_equal(so, sh) and np.array_equal(co, ch), (game, i, "reset")
+    L.orc_destroy(o); H.he_destroy(h)
