@@ -81,6 +81,56 @@ static const MnemonicInfo kMnemonics[] = {
 
 static const char* const kModeNames[] = {"imp", "acc", "imm", "zp", "zpx", "zpy", "abs", "abx", "aby", "izx", "izy", "rel", "ind"};
 
+// Control word of cpu_step's table-driven datapath for one opcode: which register / constant feeds each
+// ALU input, the function, which flags and registers take the result.  Opcodes it cannot express (stack,
+// flow, flag ops, BIT, undocumented read-modify-write combinations) are left to cpu_special().
+inline uint32_t datapath_control(int op, int mode) {
+  uint32_t len = (mode <= AM_ACC) ? 1u : (mode == AM_ABS || mode == AM_ABX || mode == AM_ABY || mode == AM_IND) ? 3u : 2u;
+  uint32_t isel = (mode == AM_ZPX || mode == AM_ABX) ? 1u : (mode == AM_ZPY || mode == AM_ABY) ? 2u : 0u;
+  uint32_t k = ((len - 1) << K_LEN) | (isel << K_ISEL);
+  const uint32_t G = K_GENERIC;
+  auto mk = [&](uint32_t asel, uint32_t bsel, uint32_t csel, uint32_t fn, uint32_t flags) {
+    return k | G | (asel << K_ASEL) | (bsel << K_BSEL) | (csel << K_CSEL) | (fn << K_FN) | flags;
+  };
+  const uint32_t shift_src = (mode == AM_ACC) ? AS_A : AS_M, shift_dst = (mode == AM_ACC) ? K_DA : 0u;
+  switch (op) {
+    case O_NOP: return mk(AS_ZERO, BS_ZERO, 0, FN_ADD, 0);
+    case O_LDA: return mk(AS_M, BS_ZERO, 0, FN_ADD, K_NZ | K_DA);
+    case O_LDX: return mk(AS_M, BS_ZERO, 0, FN_ADD, K_NZ | K_DX);
+    case O_LDY: return mk(AS_M, BS_ZERO, 0, FN_ADD, K_NZ | K_DY);
+    case O_LAX: return mk(AS_M, BS_ZERO, 0, FN_ADD, K_NZ | K_DA | K_DX);
+    case O_STA: return mk(AS_A, BS_ZERO, 0, FN_ADD, 0);
+    case O_STX: return mk(AS_X, BS_ZERO, 0, FN_ADD, 0);
+    case O_STY: return mk(AS_Y, BS_ZERO, 0, FN_ADD, 0);
+    case O_SAX: return mk(AS_AX, BS_ZERO, 0, FN_ADD, 0);
+    case O_ORA: return mk(AS_A, BS_M, 0, FN_OR, K_NZ | K_DA);
+    case O_AND: return mk(AS_A, BS_M, 0, FN_AND, K_NZ | K_DA);
+    case O_EOR: return mk(AS_A, BS_M, 0, FN_EOR, K_NZ | K_DA);
+    case O_ADC: return mk(AS_A, BS_M, 2, FN_ADD, K_NZ | K_C | K_V | K_DA | K_DECIMAL);
+    case O_SBC: return mk(AS_A, BS_M, 2, FN_ADD, K_NZ | K_C | K_V | K_DA | K_DECIMAL | K_BINV);
+    case O_CMP: return mk(AS_A, BS_M, 1, FN_ADD, K_NZ | K_C | K_BINV);
+    case O_CPX: return mk(AS_X, BS_M, 1, FN_ADD, K_NZ | K_C | K_BINV);
+    case O_CPY: return mk(AS_Y, BS_M, 1, FN_ADD, K_NZ | K_C | K_BINV);
+    case O_INC: return mk(AS_M, BS_ONE, 0, FN_ADD, K_NZ);
+    case O_DEC: return mk(AS_M, BS_FF, 0, FN_ADD, K_NZ);
+    case O_INX: return mk(AS_X, BS_ONE, 0, FN_ADD, K_NZ | K_DX);
+    case O_INY: return mk(AS_Y, BS_ONE, 0, FN_ADD, K_NZ | K_DY);
+    case O_DEX: return mk(AS_X, BS_FF, 0, FN_ADD, K_NZ | K_DX);
+    case O_DEY: return mk(AS_Y, BS_FF, 0, FN_ADD, K_NZ | K_DY);
+    case O_TAX: return mk(AS_A, BS_ZERO, 0, FN_ADD, K_NZ | K_DX);
+    case O_TAY: return mk(AS_A, BS_ZERO, 0, FN_ADD, K_NZ | K_DY);
+    case O_TXA: return mk(AS_X, BS_ZERO, 0, FN_ADD, K_NZ | K_DA);
+    case O_TYA: return mk(AS_Y, BS_ZERO, 0, FN_ADD, K_NZ | K_DA);
+    case O_TSX: return mk(AS_SP, BS_ZERO, 0, FN_ADD, K_NZ | K_DX);
+    case O_TXS: return mk(AS_X, BS_ZERO, 0, FN_ADD, K_DSP);
+    case O_ASL: return mk(shift_src, BS_ZERO, 0, FN_ASL, K_NZ | K_C | shift_dst);
+    case O_LSR: return mk(shift_src, BS_ZERO, 0, FN_LSR, K_NZ | K_C | shift_dst);
+    case O_ROL: return mk(shift_src, BS_ZERO, 0, FN_ROL, K_NZ | K_C | shift_dst);
+    case O_ROR: return mk(shift_src, BS_ZERO, 0, FN_ROR, K_NZ | K_C | shift_dst);
+    default: return k;
+  }
+}
+
 inline void build_tables(Tables* t) {
   memset(t, 0, sizeof(*t));
   for (int opc = 0; opc < 256; ++opc) {
@@ -99,6 +149,7 @@ inline void build_tables(Tables* t) {
     if (mi->op == O_NOP && mode == AM_IMP) cls = OC_NONE;   // only the multi-byte NOPs touch memory
     t->desc[opc] = MN_DESC(mode, cls, mi->op, cyc & 7);
     t->aux[opc] = (uint8_t)mi->aux;
+    t->ctl[opc] = datapath_control(mi->op, mode);
   }
 }
 // cycles 8 does not fit 3 bits: the read-modify-write undocumented (zp,X)/(zp),Y forms take 8.

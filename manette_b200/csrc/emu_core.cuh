@@ -87,6 +87,7 @@ enum {  // operations
 #define MN_DESC(mode, cls, op, cyc) uint16_t((mode) | ((cls) << 4) | ((op) << 6) | ((cyc) << 12))
 
 struct Tables {          // read-only, staged in shared memory by the kernels
+  uint32_t ctl[256];     // control word of the table-driven datapath (K_* fields, see cpu_step)
   uint16_t desc[256];
   uint8_t aux[256];      // branch: [7:6]=flag selector (0 N,1 V,2 C,3 Z) [0]=wanted value ; flag op: [7:1]=bit index in P [0]=set
 };
@@ -629,227 +630,270 @@ MN_HD MN_INLINE void cart_touch(EnvState& s, uint32_t a) {   // a = addr & 0xFFF
     }
   }
 }
-MN_HD MN_INLINE uint32_t bus_read(Ctx& c, uint32_t addr) {
+
+// The 6502 and what it needs on every instruction, register resident while a frame runs.
+struct Cpu {
+  uint32_t A, X, Y, SP, PC;
+  uint32_t P;        // C(0x01) I(0x04) D(0x08) B(0x10) V(0x40); N/Z live in nz
+  uint32_t nz;       // Z <=> (nz & 0xFF) == 0 ; N <=> nz & 0x180
+  uint32_t dbus;     // last value on the data bus (the undriven bits of TIA reads)
+  uint32_t segmap;   // cartridge window: byte k = 1K ROM page visible at $1000 + k * $400
+  int32_t cycles;
+  bool banked, stop;
+};
+// the read-mostly pointers of the fast paths, passed by value so they stay in registers
+struct Mem { const uint8_t* rom; uint8_t* ram; uint32_t ram_stride; const Tables* tab; };
+MN_HD MN_INLINE Mem mem_of(const Ctx& c) { Mem m; m.rom = c.rom; m.ram = c.ram; m.ram_stride = uint32_t(c.ram_stride); m.tab = c.tab; return m; }
+MN_HD MN_INLINE uint32_t make_segmap(const EnvState& s) {
+  if (s.cart == CART_2K) return 0x01000100u;
+  if (s.cart == CART_4K) return 0x03020100u;
+  if (s.cart == CART_E0) return uint32_t(s.slice0) | (uint32_t(s.slice1) << 8) | (uint32_t(s.slice2) << 16) | (7u << 24);
+  const uint32_t b = uint32_t(s.bank) * 4u;   // F8 / F6: one 4K bank
+  return b | ((b + 1) << 8) | ((b + 2) << 16) | ((b + 3) << 24);
+}
+MN_HD MN_INLINE void cpu_load(const EnvState& s, Cpu& r) {
+  r.A = s.A; r.X = s.X; r.Y = s.Y; r.SP = s.SP; r.PC = s.PC; r.P = s.P; r.nz = s.nz; r.dbus = s.dbus;
+  r.cycles = s.cycles; r.segmap = make_segmap(s); r.banked = s.cart > CART_4K; r.stop = (s.flags & F_STOP) != 0;
+}
+MN_HD MN_INLINE void cpu_store(EnvState& s, const Cpu& r) {
+  s.A = uint8_t(r.A); s.X = uint8_t(r.X); s.Y = uint8_t(r.Y); s.SP = uint8_t(r.SP); s.PC = uint16_t(r.PC);
+  s.P = uint8_t(r.P); s.nz = uint16_t(r.nz); s.dbus = uint8_t(r.dbus); s.cycles = r.cycles;
+}
+
+// ROM and RIOT RAM both sit in shared memory: one byte load from a selected address serves either
+MN_HD MN_INLINE uint8_t* fast_ptr(const Mem& mm, uint32_t segmap, uint32_t addr) {
+  const uint32_t a = addr & 0xFFFu;
+  const uint32_t ri = (((segmap >> ((a >> 10) << 3)) & 0xFFu) << 10) | (a & 0x3FFu);
+  const uint32_t j = addr & 0x7Fu;
+  const uint32_t mi = (j >> 2) * mm.ram_stride + (j & 3u);
+  return (addr & 0x1000u) ? const_cast<uint8_t*>(mm.rom + ri) : (mm.ram + mi);
+}
+// the uncommon reads: bank-switch hot spots (the switch happens before the read), TIA, RIOT
+MN_HD MN_NOINLINE uint32_t rd_slow(Ctx& c, uint32_t addr, int32_t cycles, uint32_t dbus) {
   EnvState& s = *c.s;
+  if (addr & 0x1000u) { cart_touch(s, addr & 0xFFFu); return *fast_ptr(mem_of(c), make_segmap(s), addr); }
+  s.cycles = cycles; s.dbus = uint8_t(dbus);
+  return (addr & 0x80u) ? riot_peek(c, addr) : tia_peek(c, addr);
+}
+MN_HD MN_INLINE uint32_t rd(Ctx& c, const Mem& mm, Cpu& r, uint32_t addr) {
+  const bool rom = (addr & 0x1000u) != 0;
+  const bool fast = rom ? !(r.banked && (addr & 0xFFFu) >= 0xFE0u) : ((addr & 0x0280u) == 0x0080u);
   uint32_t v;
-  if (addr & 0x1000) {
-    const uint32_t a = addr & 0x0FFF;
-    if (s.cart <= CART_4K) v = c.rom[(s.cart == CART_2K) ? (a & 0x7FF) : a];
-    else {
-      if (a >= 0xFE0) cart_touch(s, a);
-      if (s.cart == CART_E0) {
-        const uint32_t seg = a >> 10;
-        const uint32_t sl = (seg == 0) ? s.slice0 : (seg == 1) ? s.slice1 : (seg == 2) ? s.slice2 : 7u;
-        v = c.rom[(sl << 10) + (a & 0x3FF)];
-      } else v = c.rom[(uint32_t(s.bank) << 12) + a];
-    }
-  } else if (addr & 0x80) {
-    if (addr & 0x200) v = riot_peek(c, addr); else v = ram_at(c, addr & 0x7F);
-  } else v = tia_peek(c, addr);
-  s.dbus = uint8_t(v);
+  if (fast) v = *fast_ptr(mm, r.segmap, addr);
+  else { v = rd_slow(c, addr, r.cycles, r.dbus); if (rom) r.segmap = make_segmap(*c.s); }
+  r.dbus = v;
   return v;
 }
-MN_HD MN_INLINE void bus_write(Ctx& c, uint32_t addr, uint32_t v) {
+// the writes that do not land in RIOT RAM; returns the CPU cycle count (WSYNC / RSYNC stall the 6502)
+MN_HD MN_NOINLINE int32_t wr_slow(Ctx& c, uint32_t addr, uint32_t v, int32_t cycles) {
   EnvState& s = *c.s;
-  v &= 0xFF;
-  if (addr & 0x1000) { if (s.cart > CART_4K) cart_touch(s, addr & 0x0FFF); }
-  else if (addr & 0x80) { if (addr & 0x200) riot_poke(c, addr, v); else ram_at(c, addr & 0x7F) = uint8_t(v); }
-  else tia_poke(c, addr, v);
-  s.dbus = uint8_t(v);
+  if (addr & 0x1000u) { if (s.cart > CART_4K) cart_touch(s, addr & 0xFFFu); return cycles; }
+  s.cycles = cycles;
+  if (addr & 0x80u) riot_poke(c, addr, v); else tia_poke(c, addr, v);
+  return s.cycles;
+}
+MN_HD MN_INLINE void wr(Ctx& c, const Mem& mm, Cpu& r, uint32_t addr, uint32_t v) {
+  v &= 0xFFu;
+  if ((addr & 0x1280u) == 0x0080u) *fast_ptr(mm, r.segmap, addr) = uint8_t(v);
+  else {
+    r.cycles = wr_slow(c, addr, v, r.cycles);
+    if (addr & 0x1000u) r.segmap = make_segmap(*c.s);
+    else r.stop = (c.s->flags & F_STOP) != 0;
+  }
+  r.dbus = v;
 }
 
 // ------------------------------------------------------------------ 6502
-MN_HD MN_INLINE uint32_t pack_ps(const EnvState& s) {
-  return 0x20u | (s.P & 0x5Du) | ((s.nz & 0x180) ? 0x80u : 0u) | ((s.nz & 0xFF) ? 0u : 0x02u);
+MN_HD MN_INLINE uint32_t pack_ps(uint32_t P, uint32_t nz) {
+  return 0x20u | (P & 0x5Du) | ((nz & 0x180u) ? 0x80u : 0u) | ((nz & 0xFFu) ? 0u : 0x02u);
 }
+MN_HD MN_INLINE uint32_t pack_ps(const EnvState& s) { return pack_ps(s.P, s.nz); }
+MN_HD MN_INLINE void unpack_ps(Cpu& r, uint32_t p) { r.P = p & 0x5Du; r.nz = ((p & 0x80u) << 1) | ((p & 0x02u) ? 0u : 1u); }
 MN_HD MN_INLINE void unpack_ps(EnvState& s, uint32_t p) {
   s.P = uint8_t(p & 0x5D);
   s.nz = uint16_t(((p & 0x80) << 1) | ((p & 0x02) ? 0 : 1));
 }
 MN_HD MN_INLINE uint32_t bcd_bin(uint32_t v) { return (v >> 4) * 10 + (v & 15); }
-MN_HD MN_INLINE void op_adc(EnvState& s, uint32_t m) {
-  const uint32_t a = s.A, cin = s.P & 1;
-  if (!(s.P & 0x08)) {
+MN_HD MN_INLINE void op_adc(Cpu& r, uint32_t m) {
+  const uint32_t a = r.A, cin = r.P & 1;
+  if (!(r.P & 0x08)) {
     const uint32_t sum = a + m + cin;
     const bool v = ((~(a ^ m)) & (a ^ sum) & 0x80) != 0;
-    s.A = uint8_t(sum); s.nz = uint8_t(sum);
-    s.P = uint8_t((s.P & ~0x41) | (sum > 0xFF ? 1 : 0) | (v ? 0x40 : 0));
+    r.A = sum & 0xFF; r.nz = r.A;
+    r.P = (r.P & ~0x41u) | (sum > 0xFF ? 1u : 0u) | (v ? 0x40u : 0u);
   } else {
     const uint32_t sum = bcd_bin(a) + bcd_bin(m) + cin;
     const uint32_t low = sum & 0xFF;
-    const uint32_t r = (((low % 100) / 10) << 4) | (low % 10);
-    const bool v = ((a ^ r) & 0x80) && ((r ^ m) & 0x80);
-    s.A = uint8_t(r); s.nz = uint8_t(r);
-    s.P = uint8_t((s.P & ~0x41) | (sum > 99 ? 1 : 0) | (v ? 0x40 : 0));
+    const uint32_t res = (((low % 100) / 10) << 4) | (low % 10);
+    const bool v = ((a ^ res) & 0x80) && ((res ^ m) & 0x80);
+    r.A = res & 0xFF; r.nz = r.A;
+    r.P = (r.P & ~0x41u) | (sum > 99 ? 1u : 0u) | (v ? 0x40u : 0u);
   }
 }
-MN_HD MN_INLINE void op_sbc(EnvState& s, uint32_t m) {
-  const uint32_t a = s.A, cin = s.P & 1;
-  if (!(s.P & 0x08)) {
+MN_HD MN_INLINE void op_sbc(Cpu& r, uint32_t m) {
+  const uint32_t a = r.A, cin = r.P & 1;
+  if (!(r.P & 0x08)) {
     const uint32_t nm = (~m) & 0xFF;
     const uint32_t sum = a + nm + cin;
     const bool v = ((~(a ^ nm)) & (a ^ sum) & 0x80) != 0;
-    s.A = uint8_t(sum); s.nz = uint8_t(sum);
-    s.P = uint8_t((s.P & ~0x41) | (sum > 0xFF ? 1 : 0) | (v ? 0x40 : 0));
+    r.A = sum & 0xFF; r.nz = r.A;
+    r.P = (r.P & ~0x41u) | (sum > 0xFF ? 1u : 0u) | (v ? 0x40u : 0u);
   } else {
     int32_t diff = int32_t(bcd_bin(a)) - int32_t(bcd_bin(m)) - int32_t(1 - cin);
     if (diff < 0) diff += 100;
-    const uint32_t r = ((uint32_t(diff % 100) / 10) << 4) | uint32_t(diff % 10);
+    const uint32_t res = ((uint32_t(diff % 100) / 10) << 4) | uint32_t(diff % 10);
     const bool carry = a >= (m + (1 - cin));
-    const bool v = ((a ^ r) & 0x80) && ((r ^ m) & 0x80);
-    s.A = uint8_t(r); s.nz = uint8_t(r);
-    s.P = uint8_t((s.P & ~0x41) | (carry ? 1 : 0) | (v ? 0x40 : 0));
+    const bool v = ((a ^ res) & 0x80) && ((res ^ m) & 0x80);
+    r.A = res & 0xFF; r.nz = r.A;
+    r.P = (r.P & ~0x41u) | (carry ? 1u : 0u) | (v ? 0x40u : 0u);
   }
 }
-MN_HD MN_INLINE void op_cmp(EnvState& s, uint32_t r, uint32_t m) {
-  const uint32_t d = (r - m) & 0x1FF;
-  s.nz = uint8_t(d);
-  s.P = uint8_t((s.P & ~1) | ((d & 0x100) ? 0 : 1));
+MN_HD MN_INLINE void op_cmp(Cpu& r, uint32_t reg, uint32_t m) {
+  const uint32_t d = (reg - m) & 0x1FF;
+  r.nz = d & 0xFF;
+  r.P = (r.P & ~1u) | ((d & 0x100) ? 0u : 1u);
 }
-MN_HD MN_INLINE void stk_push(Ctx& c, uint32_t v) { bus_write(c, 0x0100u | c.s->SP, v); c.s->SP--; }
-MN_HD MN_INLINE uint32_t stk_pull(Ctx& c) { c.s->SP++; return bus_read(c, 0x0100u | c.s->SP); }
+MN_HD MN_INLINE void stk_push(Ctx& c, const Mem& mm, Cpu& r, uint32_t v) { wr(c, mm, r, 0x0100u | r.SP, v); r.SP = (r.SP - 1) & 0xFFu; }
+MN_HD MN_INLINE uint32_t stk_pull(Ctx& c, const Mem& mm, Cpu& r) { r.SP = (r.SP + 1) & 0xFFu; return rd(c, mm, r, 0x0100u | r.SP); }
 
-// one instruction
-MN_HD MN_INLINE void cpu_step(Ctx& c) {
-  EnvState& s = *c.s;
-  const uint32_t ir = bus_read(c, s.PC); s.PC++;
-  const uint32_t d = c.tab->desc[ir];
-  const uint32_t mode = d & 15, cls = (d >> 4) & 3, op = (d >> 6) & 63;
-  { const uint32_t cy = (d >> 12) & 7; s.cycles += int32_t(cy ? cy : 8u); }   // 0 encodes the 8-cycle forms
-  // ---- address phase
-  uint32_t ea = 0, b1 = 0;
-  if (mode >= AM_IMM) {
-    b1 = bus_read(c, s.PC);   // every mode from IMM on has at least one operand byte
-    uint32_t base;
-    switch (mode) {
-      case AM_IMM: case AM_REL: ea = s.PC; s.PC++; break;
-      case AM_ZP: ea = b1; s.PC++; break;
-      case AM_ZPX: ea = (b1 + s.X) & 0xFF; s.PC++; break;
-      case AM_ZPY: ea = (b1 + s.Y) & 0xFF; s.PC++; break;
-      case AM_ABS: case AM_ABX: case AM_ABY: case AM_IND: {
-        const uint32_t b2 = bus_read(c, uint16_t(s.PC + 1)); s.PC += 2;
-        base = b1 | (b2 << 8);
-        if (mode == AM_ABS) ea = base;
-        else if (mode == AM_IND) {
-          const uint32_t hi_addr = ((base & 0xFF) == 0xFF) ? (base & 0xFF00) : ((base + 1) & 0xFFFF);
-          const uint32_t tl = bus_read(c, base);
-          ea = tl | (bus_read(c, hi_addr) << 8);
-        } else {
-          ea = (base + ((mode == AM_ABX) ? s.X : s.Y)) & 0xFFFF;
-          if (cls == OC_READ && ((base ^ ea) & 0xFF00)) s.cycles += 1;
-        }
-        break;
-      }
-      case AM_IZX: {
-        s.PC++;
-        const uint32_t p = (b1 + s.X) & 0xFF;
-        const uint32_t lo = bus_read(c, p);
-        ea = lo | (bus_read(c, (p + 1) & 0xFF) << 8);
-        break;
-      }
-      default: {   // AM_IZY
-        s.PC++;
-        const uint32_t lo = bus_read(c, b1);
-        base = lo | (bus_read(c, (b1 + 1) & 0xFF) << 8);
-        ea = (base + s.Y) & 0xFFFF;
-        if (cls == OC_READ && ((base ^ ea) & 0xFF00)) s.cycles += 1;
-        break;
-      }
-    }
-  }
-  // ---- read phase
-  uint32_t m = 0;
-  if (cls == OC_READ) m = (mode == AM_IMM) ? b1 : bus_read(c, ea);
-  else if (cls == OC_RMW) m = (mode == AM_ACC) ? s.A : bus_read(c, ea);
-  // ---- operate phase
+// The opcodes outside the table-driven datapath (stack / flow / flag ops, BIT, decimal ADC/SBC, undocumented).
+// Returns the value of the write phase for the write / read-modify-write classes.
+MN_HD MN_INLINE uint32_t cpu_special(Ctx& c, const Mem& mm, Cpu& r, uint32_t ir, uint32_t op, uint32_t m, uint32_t ea, uint32_t b1) {
   uint32_t w = 0;
   switch (op) {
-    case O_NOP: break;
-    case O_ORA: s.A |= uint8_t(m); s.nz = s.A; break;
-    case O_AND: s.A &= uint8_t(m); s.nz = s.A; break;
-    case O_EOR: s.A ^= uint8_t(m); s.nz = s.A; break;
-    case O_ADC: op_adc(s, m); break;
-    case O_SBC: op_sbc(s, m); break;
-    case O_CMP: op_cmp(s, s.A, m); break;
-    case O_CPX: op_cmp(s, s.X, m); break;
-    case O_CPY: op_cmp(s, s.Y, m); break;
-    case O_BIT: s.nz = uint16_t(((m & 0x80) << 1) | ((s.A & m) ? 1 : 0)); s.P = uint8_t((s.P & ~0x40) | (m & 0x40)); break;
-    case O_LDA: s.A = uint8_t(m); s.nz = s.A; break;
-    case O_LDX: s.X = uint8_t(m); s.nz = s.X; break;
-    case O_LDY: s.Y = uint8_t(m); s.nz = s.Y; break;
-    case O_LAX: s.A = s.X = uint8_t(m); s.nz = s.A; break;
-    case O_LXA: s.A = s.X = uint8_t((s.A | 0xEE) & m); s.nz = s.A; break;
-    case O_ANC: s.A &= uint8_t(m); s.nz = s.A; s.P = uint8_t((s.P & ~1) | (s.A >> 7)); break;
-    case O_ALR: s.A &= uint8_t(m); s.P = uint8_t((s.P & ~1) | (s.A & 1)); s.A >>= 1; s.nz = s.A; break;
+    case O_ADC: op_adc(r, m); break;
+    case O_SBC: op_sbc(r, m); break;
+    case O_BIT: r.nz = ((m & 0x80) << 1) | ((r.A & m) ? 1u : 0u); r.P = (r.P & ~0x40u) | (m & 0x40); break;
+    case O_LXA: r.A = r.X = (r.A | 0xEE) & m; r.nz = r.A; break;
+    case O_ANC: r.A &= m; r.nz = r.A; r.P = (r.P & ~1u) | (r.A >> 7); break;
+    case O_ALR: r.A &= m; r.P = (r.P & ~1u) | (r.A & 1); r.A >>= 1; r.nz = r.A; break;
     case O_ARR: {
-      uint32_t a = s.A & m; a = ((a >> 1) & 0x7F) | ((s.P & 1) << 7);
-      s.A = uint8_t(a); s.nz = s.A;
-      s.P = uint8_t((s.P & ~0x41) | ((a >> 6) & 1) | ((((a >> 6) ^ (a >> 5)) & 1) ? 0x40 : 0));
+      uint32_t a = r.A & m; a = ((a >> 1) & 0x7F) | ((r.P & 1) << 7);
+      r.A = a; r.nz = a;
+      r.P = (r.P & ~0x41u) | ((a >> 6) & 1) | ((((a >> 6) ^ (a >> 5)) & 1) ? 0x40u : 0u);
       break;
     }
-    case O_XAA: s.A = uint8_t(s.X & m); s.nz = s.A; break;
-    case O_AXS: { const uint32_t dd = ((s.X & s.A) - m) & 0x1FF; s.X = uint8_t(dd); s.nz = s.X; s.P = uint8_t((s.P & ~1) | ((dd & 0x100) ? 0 : 1)); break; }
-    case O_LAS: s.A = s.X = s.SP = uint8_t(m & s.SP); s.nz = s.A; break;
-    case O_STA: w = s.A; break;
-    case O_STX: w = s.X; break;
-    case O_STY: w = s.Y; break;
-    case O_SAX: w = s.A & s.X; break;
-    case O_AHX: w = s.A & s.X & (((ea >> 8) + 1) & 0xFF); break;
-    case O_SHY: w = s.Y & (((ea >> 8) + 1) & 0xFF); break;
-    case O_SHX: w = s.X & (((ea >> 8) + 1) & 0xFF); break;
-    case O_TAS: s.SP = s.A & s.X; w = s.SP & (((ea >> 8) + 1) & 0xFF); break;
-    case O_ASL: case O_SLO: s.P = uint8_t((s.P & ~1) | (m >> 7)); w = (m << 1) & 0xFF; if (op == O_ASL) s.nz = uint8_t(w); else { s.A |= uint8_t(w); s.nz = s.A; } break;
-    case O_LSR: case O_SRE: s.P = uint8_t((s.P & ~1) | (m & 1)); w = m >> 1; if (op == O_LSR) s.nz = uint8_t(w); else { s.A ^= uint8_t(w); s.nz = s.A; } break;
-    case O_ROL: case O_RLA: { const uint32_t cin = s.P & 1; s.P = uint8_t((s.P & ~1) | (m >> 7)); w = ((m << 1) | cin) & 0xFF; if (op == O_ROL) s.nz = uint8_t(w); else { s.A &= uint8_t(w); s.nz = s.A; } break; }
-    case O_ROR: case O_RRA: { const uint32_t cin = s.P & 1; s.P = uint8_t((s.P & ~1) | (m & 1)); w = (m >> 1) | (cin << 7); if (op == O_ROR) s.nz = uint8_t(w); else op_adc(s, w); break; }
-    case O_INC: w = (m + 1) & 0xFF; s.nz = uint8_t(w); break;
-    case O_DEC: w = (m - 1) & 0xFF; s.nz = uint8_t(w); break;
-    case O_DCP: w = (m - 1) & 0xFF; op_cmp(s, s.A, w); break;
-    case O_ISC: w = (m + 1) & 0xFF; op_sbc(s, w); break;
-    case O_BRANCH: {
-      const uint32_t ax = c.tab->aux[ir];
-      const uint32_t sel = ax >> 6;
-      const bool flag = (sel == 0) ? ((s.nz & 0x180) != 0) : (sel == 1) ? ((s.P & 0x40) != 0) : (sel == 2) ? ((s.P & 1) != 0) : ((s.nz & 0xFF) == 0);
-      const int32_t off = int8_t(b1);
-      if (flag == ((ax & 1) != 0)) {
-        const uint32_t target = (s.PC + off) & 0xFFFF;
-        s.cycles += ((s.PC ^ target) & 0xFF00) ? 2 : 1;
-        s.PC = uint16_t(target);
-      }
-      break;
-    }
-    case O_JMP: s.PC = uint16_t(ea); break;
-    case O_JSR: { const uint32_t ret = (s.PC - 1) & 0xFFFF; stk_push(c, ret >> 8); stk_push(c, ret & 0xFF); s.PC = uint16_t(ea); break; }
-    case O_RTS: { const uint32_t lo = stk_pull(c); const uint32_t hi = stk_pull(c); s.PC = uint16_t((lo | (hi << 8)) + 1); break; }
-    case O_RTI: { unpack_ps(s, stk_pull(c)); const uint32_t lo = stk_pull(c); const uint32_t hi = stk_pull(c); s.PC = uint16_t(lo | (hi << 8)); break; }
+    case O_XAA: r.A = r.X & m; r.nz = r.A; break;
+    case O_AXS: { const uint32_t dd = ((r.X & r.A) - m) & 0x1FF; r.X = dd & 0xFF; r.nz = r.X; r.P = (r.P & ~1u) | ((dd & 0x100) ? 0u : 1u); break; }
+    case O_LAS: r.A = r.X = r.SP = m & r.SP; r.nz = r.A; break;
+    case O_AHX: w = r.A & r.X & (((ea >> 8) + 1) & 0xFF); break;
+    case O_SHY: w = r.Y & (((ea >> 8) + 1) & 0xFF); break;
+    case O_SHX: w = r.X & (((ea >> 8) + 1) & 0xFF); break;
+    case O_TAS: r.SP = r.A & r.X; w = r.SP & (((ea >> 8) + 1) & 0xFF); break;
+    case O_SLO: r.P = (r.P & ~1u) | (m >> 7); w = (m << 1) & 0xFF; r.A |= w; r.nz = r.A; break;
+    case O_SRE: r.P = (r.P & ~1u) | (m & 1); w = m >> 1; r.A ^= w; r.nz = r.A; break;
+    case O_RLA: { const uint32_t cin = r.P & 1; r.P = (r.P & ~1u) | (m >> 7); w = ((m << 1) | cin) & 0xFF; r.A &= w; r.nz = r.A; break; }
+    case O_RRA: { const uint32_t cin = r.P & 1; r.P = (r.P & ~1u) | (m & 1); w = (m >> 1) | (cin << 7); op_adc(r, w); break; }
+    case O_DCP: w = (m - 1) & 0xFF; op_cmp(r, r.A, w); break;
+    case O_ISC: w = (m + 1) & 0xFF; op_sbc(r, w); break;
+    case O_JMP: r.PC = ea; break;
+    case O_JSR: { const uint32_t ret = (r.PC - 1) & 0xFFFF; stk_push(c, mm, r, ret >> 8); stk_push(c, mm, r, ret & 0xFF); r.PC = ea; break; }
+    case O_RTS: { const uint32_t lo = stk_pull(c, mm, r); const uint32_t hi = stk_pull(c, mm, r); r.PC = ((lo | (hi << 8)) + 1) & 0xFFFF; break; }
+    case O_RTI: { unpack_ps(r, stk_pull(c, mm, r)); const uint32_t lo = stk_pull(c, mm, r); const uint32_t hi = stk_pull(c, mm, r); r.PC = lo | (hi << 8); break; }
     case O_BRK: {
-      bus_read(c, s.PC); s.PC++; s.P |= 0x10;
-      stk_push(c, s.PC >> 8); stk_push(c, s.PC & 0xFF); stk_push(c, pack_ps(s));
-      s.P |= 0x04;
-      const uint32_t lo = bus_read(c, 0xFFFE); s.PC = uint16_t(lo | (bus_read(c, 0xFFFF) << 8));
+      rd(c, mm, r, r.PC); r.PC = (r.PC + 1) & 0xFFFF; r.P |= 0x10;
+      stk_push(c, mm, r, r.PC >> 8); stk_push(c, mm, r, r.PC & 0xFF); stk_push(c, mm, r, pack_ps(r.P, r.nz));
+      r.P |= 0x04;
+      const uint32_t lo = rd(c, mm, r, 0xFFFE); r.PC = lo | (rd(c, mm, r, 0xFFFF) << 8);
       break;
     }
-    case O_PHA: stk_push(c, s.A); break;
-    case O_PHP: stk_push(c, pack_ps(s) | 0x10); break;
-    case O_PLA: s.A = uint8_t(stk_pull(c)); s.nz = s.A; break;
-    case O_PLP: unpack_ps(s, stk_pull(c)); break;
-    case O_TAX: s.X = s.A; s.nz = s.X; break;
-    case O_TAY: s.Y = s.A; s.nz = s.Y; break;
-    case O_TXA: s.A = s.X; s.nz = s.A; break;
-    case O_TYA: s.A = s.Y; s.nz = s.A; break;
-    case O_TSX: s.X = s.SP; s.nz = s.X; break;
-    case O_TXS: s.SP = s.X; break;
-    case O_INX: s.X++; s.nz = s.X; break;
-    case O_INY: s.Y++; s.nz = s.Y; break;
-    case O_DEX: s.X--; s.nz = s.X; break;
-    case O_DEY: s.Y--; s.nz = s.Y; break;
-    case O_FLAG: { const uint32_t ax = c.tab->aux[ir]; const uint8_t mask = uint8_t(1u << (ax >> 1)); s.P = (ax & 1) ? (s.P | mask) : (s.P & ~mask); break; }
-    default: break;   // O_KIL
+    case O_PHA: stk_push(c, mm, r, r.A); break;
+    case O_PHP: stk_push(c, mm, r, pack_ps(r.P, r.nz) | 0x10); break;
+    case O_PLA: r.A = stk_pull(c, mm, r); r.nz = r.A; break;
+    case O_PLP: unpack_ps(r, stk_pull(c, mm, r)); break;
+    case O_FLAG: { const uint32_t ax = mm.tab->aux[ir]; const uint32_t mask = 1u << (ax >> 1); r.P = (ax & 1) ? (r.P | mask) : (r.P & ~mask); break; }
+    default: break;   // O_KIL, O_NOP
   }
-  // ---- write phase
-  if (cls == OC_WRITE) bus_write(c, ea, w);
-  else if (cls == OC_RMW) { if (mode == AM_ACC) { s.A = uint8_t(w); } else bus_write(c, ea, w); }
+  (void)b1;
+  return w;
 }
+
+// control word of the table-driven datapath (Tables::ctl), see decode_tables.h
+enum : uint32_t {
+  K_ASEL = 0, K_BSEL = 3, K_BINV = 1u << 5, K_CSEL = 6, K_FN = 8, K_NZ = 1u << 11, K_C = 1u << 12, K_V = 1u << 13,
+  K_DA = 1u << 14, K_DX = 1u << 15, K_DY = 1u << 16, K_DSP = 1u << 17, K_GENERIC = 1u << 18, K_DECIMAL = 1u << 19,
+  K_ISEL = 20, K_LEN = 22 };
+enum { FN_ADD = 0, FN_OR, FN_AND, FN_EOR, FN_ASL, FN_LSR, FN_ROL, FN_ROR };
+enum { AS_A = 0, AS_X, AS_Y, AS_SP, AS_M, AS_AX, AS_ZERO };
+enum { BS_M = 0, BS_ONE, BS_FF, BS_ZERO };
+
+// one instruction
+MN_HD MN_INLINE void cpu_step(Ctx& c, const Mem& mm, Cpu& r) {
+  const uint32_t pc = r.PC;
+  // ---- fetch: code almost always runs from cartridge ROM away from the bank-switch hot spots
+  const bool fast_code = (pc & 0x1000u) && ((pc & 0xFFFu) < 0xFDEu);
+  uint32_t ir, b1 = 0, b2 = 0;
+  if (fast_code) { ir = *fast_ptr(mm, r.segmap, pc); b1 = *fast_ptr(mm, r.segmap, pc + 1); b2 = *fast_ptr(mm, r.segmap, pc + 2); }
+  else ir = rd(c, mm, r, pc);
+  const uint32_t d = mm.tab->desc[ir];
+  const uint32_t k = mm.tab->ctl[ir];
+  const uint32_t mode = d & 15, cls = (d >> 4) & 3, op = (d >> 6) & 63;
+  const uint32_t len = ((k >> K_LEN) & 3u) + 1u;
+  if (!fast_code) { if (len >= 2) b1 = rd(c, mm, r, (pc + 1) & 0xFFFFu); if (len == 3) b2 = rd(c, mm, r, (pc + 2) & 0xFFFFu); }
+  else r.dbus = (len == 1) ? ir : (len == 2) ? b1 : b2;
+  r.PC = (pc + len) & 0xFFFFu;
+  { const uint32_t cy = (d >> 12) & 7; r.cycles += int32_t(cy ? cy : 8u); }   // 0 encodes the 8-cycle forms
+  // ---- address phase
+  uint32_t ea = 0, m = b1;
+  if (mode >= AM_ZP && mode != AM_REL) {
+    uint32_t base;
+    if (mode >= AM_IZX) {   // (zp,X)  (zp),Y  (abs)
+      uint32_t p0, p1;
+      if (mode == AM_IND) { p0 = b1 | (b2 << 8); p1 = ((p0 & 0xFF) == 0xFF) ? (p0 & 0xFF00u) : ((p0 + 1) & 0xFFFFu); }
+      else { p0 = (mode == AM_IZX) ? ((b1 + r.X) & 0xFFu) : b1; p1 = (p0 + 1) & 0xFFu; }
+      const uint32_t lo = rd(c, mm, r, p0);
+      base = lo | (rd(c, mm, r, p1) << 8);
+      ea = (mode == AM_IZY) ? ((base + r.Y) & 0xFFFFu) : base;
+    } else {
+      const uint32_t isel = (k >> K_ISEL) & 3u;
+      const uint32_t idx = (isel == 1) ? r.X : (isel == 2) ? r.Y : 0u;
+      const bool wide = mode >= AM_ABS;
+      base = wide ? (b1 | (b2 << 8)) : b1;
+      ea = (base + idx) & (wide ? 0xFFFFu : 0xFFu);
+    }
+    if (cls == OC_READ && ((base ^ ea) & 0xFF00u)) r.cycles += 1;
+    // ---- read phase
+    if (cls == OC_READ || cls == OC_RMW) m = rd(c, mm, r, ea);
+  }
+  // ---- operate phase
+  uint32_t w;
+  if ((k & K_GENERIC) && !((k & K_DECIMAL) && (r.P & 0x08u))) {
+    const uint32_t asel = k & 7u, bsel = (k >> K_BSEL) & 3u, csel = (k >> K_CSEL) & 3u, fn = (k >> K_FN) & 7u;
+    const uint32_t a = (asel == AS_A) ? r.A : (asel == AS_X) ? r.X : (asel == AS_Y) ? r.Y : (asel == AS_SP) ? r.SP :
+                       (asel == AS_M) ? m : (asel == AS_AX) ? (r.A & r.X) : 0u;
+    uint32_t b = (bsel == BS_M) ? m : (bsel == BS_ONE) ? 1u : (bsel == BS_FF) ? 0xFFu : 0u;
+    if (k & K_BINV) b ^= 0xFFu;
+    const uint32_t carry = r.P & 1u;
+    const uint32_t cin = (csel == 2) ? carry : csel;
+    const uint32_t sum = a + b + cin;
+    const uint32_t rot = (fn >= FN_ROL) ? carry : 0u;
+    const uint32_t left = ((a << 1) | rot) & 0xFFu, right = (a >> 1) | (rot << 7);
+    const uint32_t res = (fn == FN_ADD) ? (sum & 0xFFu) : (fn == FN_OR) ? (a | b) : (fn == FN_AND) ? (a & b) :
+                         (fn == FN_EOR) ? (a ^ b) : (fn == FN_ASL || fn == FN_ROL) ? left : right;
+    const uint32_t cout = (fn == FN_ADD) ? (sum >> 8) : (fn == FN_ASL || fn == FN_ROL) ? (a >> 7) : (a & 1u);
+    if (k & K_NZ) r.nz = res;
+    if (k & K_C) r.P = (r.P & ~1u) | cout;
+    if (k & K_V) r.P = (r.P & ~0x40u) | (((~(a ^ b)) & (a ^ sum) & 0x80u) >> 1);
+    if (k & K_DA) r.A = res;
+    if (k & K_DX) r.X = res;
+    if (k & K_DY) r.Y = res;
+    if (k & K_DSP) r.SP = res;
+    w = res;
+  } else if (op == O_BRANCH) {
+    const uint32_t ax = mm.tab->aux[ir];
+    const uint32_t sel = ax >> 6;
+    const bool flag = (sel == 0) ? ((r.nz & 0x180u) != 0) : (sel == 1) ? ((r.P & 0x40u) != 0) : (sel == 2) ? ((r.P & 1u) != 0) : ((r.nz & 0xFFu) == 0);
+    if (flag == ((ax & 1u) != 0)) {
+      const uint32_t target = (r.PC + uint32_t(int32_t(int8_t(b1)))) & 0xFFFFu;
+      r.cycles += ((r.PC ^ target) & 0xFF00u) ? 2 : 1;
+      r.PC = target;
+    }
+    w = 0;
+  } else w = cpu_special(c, mm, r, ir, op, m, ea, b1);
+  // ---- write phase
+  if (cls == OC_WRITE || (cls == OC_RMW && mode != AM_ACC)) wr(c, mm, r, ea, w);
+}
+
 
 // ------------------------------------------------------------------ frame
 // program side of the emulated TIA's frame start: rebase every cycle-stamped quantity, tell the picture
@@ -1018,8 +1062,14 @@ MN_HD MN_INLINE void console_reset(Ctx& c, uint32_t rnd) {
   s.bank = (s.cart == CART_F8) ? 1 : 0; s.slice0 = 4; s.slice1 = 5; s.slice2 = 6;
   // CPU
   s.A = s.X = s.Y = 0; s.SP = 0xFF; unpack_ps(s, 0x20);
-  const uint32_t lo = bus_read(c, 0xFFFC);
-  s.PC = uint16_t(lo | (bus_read(c, 0xFFFD) << 8));
+  {   // reset vector (a hot-spot free cartridge read)
+    Cpu r;
+    cpu_load(s, r);
+    const Mem mm = mem_of(c);
+    const uint32_t lo = rd(c, mm, r, 0xFFFC);
+    s.PC = uint16_t(lo | (rd(c, mm, r, 0xFFFD) << 8));
+    s.dbus = uint8_t(r.dbus);
+  }
 }
 
 // ------------------------------------------------------------------ units of work
@@ -1036,6 +1086,8 @@ struct Unit {
   int32_t reward;
   bool in_frame, frozen_last, job_is_act;
 };
+// the part of a running unit the flat loop keeps in registers
+struct Hot { Cpu cpu; int budget; bool in_frame, more; };
 
 MN_HD MN_INLINE void unit_idle(Unit& u) { u.kind = U_ACTS; u.idx = u.total = 0; u.in_frame = false; u.reward = 0; u.frozen_last = false; }
 
@@ -1057,9 +1109,8 @@ MN_HD MN_INLINE void unit_init(Ctx& c, Unit& u, int kind, int action, int count,
   u.nstart = game_start_actions(s.game);
   u.total = 64 + u.nstart + count;
 }
-MN_HD MN_INLINE bool unit_has_work(const Unit& u) { return u.in_frame || u.idx < u.total; }
 
-MN_HD MN_INLINE void unit_job_done(Ctx& c, Unit& u) {
+MN_HD MN_NOINLINE void unit_job_done(Ctx& c, Unit& u) {
   EnvState& s = *c.s;
   u.in_frame = false;
   game_observe(c);
@@ -1071,10 +1122,10 @@ MN_HD MN_INLINE void unit_job_done(Ctx& c, Unit& u) {
   if (u.kind != U_ACTS && u.idx == 64 + u.nstart) s.host_lives = s.lives;
 }
 
-// one tick: start the next job, or run one instruction of the frame in progress
-MN_HD MN_INLINE void unit_tick(Ctx& c, Unit& u) {
+// start the next job of the unit
+MN_HD MN_NOINLINE void unit_job_begin(Ctx& c, Unit& u) {
   EnvState& s = *c.s;
-  if (!u.in_frame) {
+  {
     int action;
     if (u.kind == U_ACTS) { action = u.action; u.job_is_act = true; }
     else if (u.idx < 60) { action = 0; u.job_is_act = false; }
@@ -1091,12 +1142,21 @@ MN_HD MN_INLINE void unit_tick(Ctx& c, Unit& u) {
     latch_inputs(s, action);
     if (!(s.flags & F_PARTIAL)) frame_begin(c, pixels);
     s.flags = (s.flags | F_PARTIAL) & ~F_STOP;
-    u.budget = 25000;
     u.in_frame = true;
+  }
+}
+MN_HD MN_INLINE void hot_init(const Unit& u, Hot& h) { h.in_frame = false; h.more = u.idx < u.total; h.budget = 0; h.cpu.stop = false; }
+MN_HD MN_INLINE bool hot_has_work(const Hot& h) { return h.in_frame || h.more; }
+// one tick: start the next job, or run one instruction of the frame in progress
+MN_HD MN_INLINE void unit_tick(Ctx& c, const Mem& mm, Unit& u, Hot& h) {
+  if (!h.in_frame) {
+    unit_job_begin(c, u);
+    h.in_frame = u.in_frame; h.more = u.idx < u.total;
+    if (h.in_frame) { cpu_load(*c.s, h.cpu); h.cpu.stop = false; h.budget = 25000; }
     return;
   }
-  cpu_step(c);
-  if ((s.flags & F_STOP) || --u.budget == 0) unit_job_done(c, u);
+  cpu_step(c, mm, h.cpu);
+  if (h.cpu.stop || --h.budget == 0) { cpu_store(*c.s, h.cpu); unit_job_done(c, u); h.in_frame = false; }
 }
 
 // after the unit's last tick: flush the picture and report whether the pixel-less frames were harmless

@@ -243,10 +243,13 @@ __global__ void __launch_bounds__(MN_THREADS, 2) k_round(PoolDev p, int mode, in
       c.all_pixels = (attempt == 1) || (p.draw_all_frames != 0);
       unit_init(c, u, kind, action, ucount, seed);
     }
+    Hot hot;
+    hot_init(u, hot);
+    const Mem mm = mem_of(c);
     for (;;) {
-      const bool work = unit_has_work(u);
+      const bool work = hot_has_work(hot);
       if (!__any_sync(wmask, work)) break;
-      if (work) unit_tick(c, u);
+      if (work) unit_tick(c, mm, u, hot);
       if (__any_sync(wmask, c.fifo_n >= MN_FIFO_HIGH)) tia_drain(c);
     }
     if (mine) { bad = unit_finish(c); res = u; }

@@ -26,8 +26,11 @@ static void run_unit(HostEnv* e, int kind, int action, int count, uint32_t seed,
     e->c.all_pixels = all_pixels || attempt == 1;
     Unit u;
     unit_init(e->c, u, kind, action, count, seed);
-    while (unit_has_work(u)) {
-      unit_tick(e->c, u);
+    Hot hot;
+    hot_init(u, hot);
+    const Mem mm = mem_of(e->c);
+    while (hot_has_work(hot)) {
+      unit_tick(e->c, mm, u, hot);
       if (e->c.fifo_n >= e->drain_at) tia_drain(e->c);
     }
     const bool bad = unit_finish(e->c);
