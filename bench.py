@@ -185,6 +185,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=0, help="override environments per GPU")
     ap.add_argument("--envs-per-warp", type=int, default=0)
+    ap.add_argument("--decorrelate", type=int, default=24,
+                    help="untimed random-policy macro steps before the warm-up so the envs are spread over game states")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -197,6 +199,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": args.workload, "games": cfg["games"], "envs_per_gpu": cfg["n"], "rgb": cfg["rgb"],
               "nb_choices": cfg["nb_choices"], "max_repetition": cfg["max_rep"], "policy": "uniform random (counter-based)",
+              "decorrelate_steps": args.decorrelate,
               "frame_unit": "1 preprocessed frame = 1 next() = 4 emulated frames + one 84x84xD plane"}
 
     if args.impl == "reference":
@@ -253,11 +256,17 @@ def main():
                 dist.all_reduce(grad)
 
     # ---- device-resident leg
+    for t in range(args.decorrelate):   # spread the envs over game states (they all start identical)
+        with torch.cuda.stream(stream):
+            pool.action_idx.copy_((torch.randint(0, 1 << 30, (n,), device=dev, generator=gen) % n_act).to(torch.int32))
+            pool.repetition_idx.copy_(torch.randint(0, cfg["nb_choices"], (n,), device=dev, generator=gen, dtype=torch.int32))
+            pool.step_async(use_indices=True, stream=stream)
+        pool.wait()
     for t in range(args.warmup):
         device_step(t)
     pool.wait()
     barrier()
-    f0, l0 = pool.total_next_calls(), pool.launch_count()
+    f0, l0, i0 = pool.total_next_calls(), pool.launch_count(), pool.total_instructions()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -274,6 +283,7 @@ def main():
     prof = pool.profile_end()
     frames = pool.total_next_calls() - f0
     launches = pool.launch_count() - l0
+    ins_timed = pool.total_instructions() - i0
     stat = torch.tensor([ms, float(frames), float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         mx = stat.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -363,7 +373,9 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
                 "raw_emulated_frames_per_s": 4.0 * value, "macro_steps_per_s": world * n * args.steps / (ms_max / 1000.0),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline, "kernels": extra,
-                "cpu_baseline": cpu, "envs_per_warp": int(args.envs_per_warp)}
+                "cpu_baseline": cpu, "envs_per_warp": int(args.envs_per_warp),
+                "reset_memo": dict(zip(("restored", "emulated", "stored"), pool.memo_stats())), "exact_reruns": pool.redo_count(),
+                "emulated_6502_instr_per_s": world * ins_timed / (ms_max / 1000.0)}
         config["l2"] = "per-step working set (frame buffers %d MB + states/ring) exceeds the 126 MB L2; no flush needed" \
             % (n * 67200 // (1 << 20))
         print(json.dumps(line))

@@ -44,6 +44,7 @@ typedef struct {
   const int* tab_rep;        /* ExplorationPolicy.get_tab_repetitions() (exploration_policy.py:56-62) */
   int envs_per_warp;         /* tuning: 1,2,4,8,16,32 lanes of a warp that own an environment (0 = default) */
   int draw_all_frames;       /* debug: draw the pixels of all four frames of a next(), not only the two pooled ones */
+  int no_reset_memo;         /* debug: emulate every get_initial_state() instead of restoring memoised ones */
 } mn_config;
 
 /* device-resident arrays (the reference's five shared variables, paac.py:97-102, + index forms) */
@@ -91,6 +92,8 @@ int mn_get_screen(mn_handle h, int env, uint8_t* out33600_host);            /* c
 int mn_get_cpu_state(mn_handle h, int env, int32_t* out10_host);            /* A X Y SP PC PS cycles scanlines bank timer */
 int mn_get_lives(mn_handle h, int env, int* lives, int* game_over, int* frame_number);
 int mn_total_next_calls(mn_handle h, int64_t* out);                         /* since creation */
+int mn_memo_stats(mn_handle h, int64_t* out3);          /* get_initial_state() calls restored from the memo, emulated, stored */
+int mn_total_instructions(mn_handle h, int64_t* out);   /* emulated 6502 instructions since creation */
 int mn_redo_count(mn_handle h, int64_t* out);   /* units re-run with every frame drawn (exact fallback), since creation */
 int mn_palette(uint8_t* gray128_host, uint8_t* rgb128x3_host);
 /* start no-ops of episode `episode` of global environment `global_env` when random_start is on.  The

@@ -21,7 +21,7 @@ class MnConfig(C.Structure):
     _fields_ = [("device", C.c_int), ("n_games", C.c_int), ("games", C.POINTER(MnGame)), ("rgb", C.c_int),
                 ("single_life_episodes", C.c_int), ("random_start", C.c_int), ("random_seed", C.c_int),
                 ("env_id_offset", C.c_int), ("nb_choices", C.c_int), ("tab_rep", C.POINTER(C.c_int)),
-                ("envs_per_warp", C.c_int), ("draw_all_frames", C.c_int)]
+                ("envs_per_warp", C.c_int), ("draw_all_frames", C.c_int), ("no_reset_memo", C.c_int)]
 
 
 class MnBuffers(C.Structure):
@@ -51,6 +51,8 @@ SYMBOLS = {
     "mn_get_cpu_state": (_I, [_VP, _I, _VP]),
     "mn_get_lives": (_I, [_VP, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "mn_total_next_calls": (_I, [_VP, C.POINTER(C.c_int64)]),
+    "mn_memo_stats": (_I, [_VP, C.POINTER(C.c_int64)]),
+    "mn_total_instructions": (_I, [_VP, C.POINTER(C.c_int64)]),
     "mn_redo_count": (_I, [_VP, C.POINTER(C.c_int64)]),
     "mn_palette": (_I, [_VP, _VP]),
     "mn_start_noops": (_I, [_U32, _U32, _U32]),

@@ -142,6 +142,7 @@ struct Ctx {
   uint32_t* fifo;       // MN_FIFO_CAP pending TIA writes of this env (shared memory)
   int fifo_n;
   bool all_pixels;      // draw every frame with pixels (the exact-fallback mode)
+  uint64_t obs_lo, obs_hi;   // RAM bytes the last game_observe() looked at (reset memoisation probe)
 };
 #define MN_FIFO_CAP 16
 #define MN_FIFO_HIGH 12   // a warp drains when one of its envs has this many pending writes
@@ -640,6 +641,10 @@ struct Cpu {
   uint32_t segmap;   // cartridge window: byte k = 1K ROM page visible at $1000 + k * $400
   int32_t cycles;
   bool banked, stop;
+  // RAM-dependence probe (TRACK instantiations only): which RIOT RAM bytes the program has written since
+  // the console reset, and whether it ever read one before writing it
+  uint64_t def_lo, def_hi, dep_lo, dep_hi;   // dep: the bytes read before written
+  bool tainted;
 };
 // the read-mostly pointers of the fast paths, passed by value so they stay in registers
 struct Mem { const uint8_t* rom; uint8_t* ram; uint32_t ram_stride; const Tables* tab; };
@@ -654,6 +659,7 @@ MN_HD MN_INLINE uint32_t make_segmap(const EnvState& s) {
 MN_HD MN_INLINE void cpu_load(const EnvState& s, Cpu& r) {
   r.A = s.A; r.X = s.X; r.Y = s.Y; r.SP = s.SP; r.PC = s.PC; r.P = s.P; r.nz = s.nz; r.dbus = s.dbus;
   r.cycles = s.cycles; r.segmap = make_segmap(s); r.banked = s.cart > CART_4K; r.stop = (s.flags & F_STOP) != 0;
+  r.def_lo = r.def_hi = r.dep_lo = r.dep_hi = 0; r.tainted = false;
 }
 MN_HD MN_INLINE void cpu_store(EnvState& s, const Cpu& r) {
   s.A = uint8_t(r.A); s.X = uint8_t(r.X); s.Y = uint8_t(r.Y); s.SP = uint8_t(r.SP); s.PC = uint16_t(r.PC);
@@ -675,10 +681,12 @@ MN_HD MN_NOINLINE uint32_t rd_slow(Ctx& c, uint32_t addr, int32_t cycles, uint32
   s.cycles = cycles; s.dbus = uint8_t(dbus);
   return (addr & 0x80u) ? riot_peek(c, addr) : tia_peek(c, addr);
 }
+template <bool TRACK>
 MN_HD MN_INLINE uint32_t rd(Ctx& c, const Mem& mm, Cpu& r, uint32_t addr) {
   const bool rom = (addr & 0x1000u) != 0;
   const bool fast = rom ? !(r.banked && (addr & 0xFFFu) >= 0xFE0u) : ((addr & 0x0280u) == 0x0080u);
   uint32_t v;
+  if (TRACK && !rom && fast) { const uint32_t j = addr & 0x7Fu; if (!((((j & 64u) ? r.def_hi : r.def_lo) >> (j & 63u)) & 1ull)) { r.tainted = true; if (j & 64u) r.dep_hi |= 1ull << (j & 63u); else r.dep_lo |= 1ull << (j & 63u); } }
   if (fast) v = *fast_ptr(mm, r.segmap, addr);
   else { v = rd_slow(c, addr, r.cycles, r.dbus); if (rom) r.segmap = make_segmap(*c.s); }
   r.dbus = v;
@@ -692,9 +700,13 @@ MN_HD MN_NOINLINE int32_t wr_slow(Ctx& c, uint32_t addr, uint32_t v, int32_t cyc
   if (addr & 0x80u) riot_poke(c, addr, v); else tia_poke(c, addr, v);
   return s.cycles;
 }
+template <bool TRACK>
 MN_HD MN_INLINE void wr(Ctx& c, const Mem& mm, Cpu& r, uint32_t addr, uint32_t v) {
   v &= 0xFFu;
-  if ((addr & 0x1280u) == 0x0080u) *fast_ptr(mm, r.segmap, addr) = uint8_t(v);
+  if ((addr & 0x1280u) == 0x0080u) {
+    *fast_ptr(mm, r.segmap, addr) = uint8_t(v);
+    if (TRACK) { const uint32_t j = addr & 0x7Fu; if (j & 64u) r.def_hi |= 1ull << (j & 63u); else r.def_lo |= 1ull << (j & 63u); }
+  }
   else {
     r.cycles = wr_slow(c, addr, v, r.cycles);
     if (addr & 0x1000u) r.segmap = make_segmap(*c.s);
@@ -753,11 +765,14 @@ MN_HD MN_INLINE void op_cmp(Cpu& r, uint32_t reg, uint32_t m) {
   r.nz = d & 0xFF;
   r.P = (r.P & ~1u) | ((d & 0x100) ? 0u : 1u);
 }
-MN_HD MN_INLINE void stk_push(Ctx& c, const Mem& mm, Cpu& r, uint32_t v) { wr(c, mm, r, 0x0100u | r.SP, v); r.SP = (r.SP - 1) & 0xFFu; }
-MN_HD MN_INLINE uint32_t stk_pull(Ctx& c, const Mem& mm, Cpu& r) { r.SP = (r.SP + 1) & 0xFFu; return rd(c, mm, r, 0x0100u | r.SP); }
+template <bool TRACK>
+MN_HD MN_INLINE void stk_push(Ctx& c, const Mem& mm, Cpu& r, uint32_t v) { wr<TRACK>(c, mm, r, 0x0100u | r.SP, v); r.SP = (r.SP - 1) & 0xFFu; }
+template <bool TRACK>
+MN_HD MN_INLINE uint32_t stk_pull(Ctx& c, const Mem& mm, Cpu& r) { r.SP = (r.SP + 1) & 0xFFu; return rd<TRACK>(c, mm, r, 0x0100u | r.SP); }
 
 // The opcodes outside the table-driven datapath (stack / flow / flag ops, BIT, decimal ADC/SBC, undocumented).
 // Returns the value of the write phase for the write / read-modify-write classes.
+template <bool TRACK>
 MN_HD MN_INLINE uint32_t cpu_special(Ctx& c, const Mem& mm, Cpu& r, uint32_t ir, uint32_t op, uint32_t m, uint32_t ea, uint32_t b1) {
   uint32_t w = 0;
   switch (op) {
@@ -787,20 +802,20 @@ MN_HD MN_INLINE uint32_t cpu_special(Ctx& c, const Mem& mm, Cpu& r, uint32_t ir,
     case O_DCP: w = (m - 1) & 0xFF; op_cmp(r, r.A, w); break;
     case O_ISC: w = (m + 1) & 0xFF; op_sbc(r, w); break;
     case O_JMP: r.PC = ea; break;
-    case O_JSR: { const uint32_t ret = (r.PC - 1) & 0xFFFF; stk_push(c, mm, r, ret >> 8); stk_push(c, mm, r, ret & 0xFF); r.PC = ea; break; }
-    case O_RTS: { const uint32_t lo = stk_pull(c, mm, r); const uint32_t hi = stk_pull(c, mm, r); r.PC = ((lo | (hi << 8)) + 1) & 0xFFFF; break; }
-    case O_RTI: { unpack_ps(r, stk_pull(c, mm, r)); const uint32_t lo = stk_pull(c, mm, r); const uint32_t hi = stk_pull(c, mm, r); r.PC = lo | (hi << 8); break; }
+    case O_JSR: { const uint32_t ret = (r.PC - 1) & 0xFFFF; stk_push<TRACK>(c, mm, r, ret >> 8); stk_push<TRACK>(c, mm, r, ret & 0xFF); r.PC = ea; break; }
+    case O_RTS: { const uint32_t lo = stk_pull<TRACK>(c, mm, r); const uint32_t hi = stk_pull<TRACK>(c, mm, r); r.PC = ((lo | (hi << 8)) + 1) & 0xFFFF; break; }
+    case O_RTI: { unpack_ps(r, stk_pull<TRACK>(c, mm, r)); const uint32_t lo = stk_pull<TRACK>(c, mm, r); const uint32_t hi = stk_pull<TRACK>(c, mm, r); r.PC = lo | (hi << 8); break; }
     case O_BRK: {
-      rd(c, mm, r, r.PC); r.PC = (r.PC + 1) & 0xFFFF; r.P |= 0x10;
-      stk_push(c, mm, r, r.PC >> 8); stk_push(c, mm, r, r.PC & 0xFF); stk_push(c, mm, r, pack_ps(r.P, r.nz));
+      rd<TRACK>(c, mm, r, r.PC); r.PC = (r.PC + 1) & 0xFFFF; r.P |= 0x10;
+      stk_push<TRACK>(c, mm, r, r.PC >> 8); stk_push<TRACK>(c, mm, r, r.PC & 0xFF); stk_push<TRACK>(c, mm, r, pack_ps(r.P, r.nz));
       r.P |= 0x04;
-      const uint32_t lo = rd(c, mm, r, 0xFFFE); r.PC = lo | (rd(c, mm, r, 0xFFFF) << 8);
+      const uint32_t lo = rd<TRACK>(c, mm, r, 0xFFFE); r.PC = lo | (rd<TRACK>(c, mm, r, 0xFFFF) << 8);
       break;
     }
-    case O_PHA: stk_push(c, mm, r, r.A); break;
-    case O_PHP: stk_push(c, mm, r, pack_ps(r.P, r.nz) | 0x10); break;
-    case O_PLA: r.A = stk_pull(c, mm, r); r.nz = r.A; break;
-    case O_PLP: unpack_ps(r, stk_pull(c, mm, r)); break;
+    case O_PHA: stk_push<TRACK>(c, mm, r, r.A); break;
+    case O_PHP: stk_push<TRACK>(c, mm, r, pack_ps(r.P, r.nz) | 0x10); break;
+    case O_PLA: r.A = stk_pull<TRACK>(c, mm, r); r.nz = r.A; break;
+    case O_PLP: unpack_ps(r, stk_pull<TRACK>(c, mm, r)); break;
     case O_FLAG: { const uint32_t ax = mm.tab->aux[ir]; const uint32_t mask = 1u << (ax >> 1); r.P = (ax & 1) ? (r.P | mask) : (r.P & ~mask); break; }
     default: break;   // O_KIL, O_NOP
   }
@@ -818,18 +833,19 @@ enum { AS_A = 0, AS_X, AS_Y, AS_SP, AS_M, AS_AX, AS_ZERO };
 enum { BS_M = 0, BS_ONE, BS_FF, BS_ZERO };
 
 // one instruction
+template <bool TRACK>
 MN_HD MN_INLINE void cpu_step(Ctx& c, const Mem& mm, Cpu& r) {
   const uint32_t pc = r.PC;
   // ---- fetch: code almost always runs from cartridge ROM away from the bank-switch hot spots
   const bool fast_code = (pc & 0x1000u) && ((pc & 0xFFFu) < 0xFDEu);
   uint32_t ir, b1 = 0, b2 = 0;
   if (fast_code) { ir = *fast_ptr(mm, r.segmap, pc); b1 = *fast_ptr(mm, r.segmap, pc + 1); b2 = *fast_ptr(mm, r.segmap, pc + 2); }
-  else ir = rd(c, mm, r, pc);
+  else ir = rd<TRACK>(c, mm, r, pc);
   const uint32_t d = mm.tab->desc[ir];
   const uint32_t k = mm.tab->ctl[ir];
   const uint32_t mode = d & 15, cls = (d >> 4) & 3, op = (d >> 6) & 63;
   const uint32_t len = ((k >> K_LEN) & 3u) + 1u;
-  if (!fast_code) { if (len >= 2) b1 = rd(c, mm, r, (pc + 1) & 0xFFFFu); if (len == 3) b2 = rd(c, mm, r, (pc + 2) & 0xFFFFu); }
+  if (!fast_code) { if (len >= 2) b1 = rd<TRACK>(c, mm, r, (pc + 1) & 0xFFFFu); if (len == 3) b2 = rd<TRACK>(c, mm, r, (pc + 2) & 0xFFFFu); }
   else r.dbus = (len == 1) ? ir : (len == 2) ? b1 : b2;
   r.PC = (pc + len) & 0xFFFFu;
   { const uint32_t cy = (d >> 12) & 7; r.cycles += int32_t(cy ? cy : 8u); }   // 0 encodes the 8-cycle forms
@@ -841,8 +857,8 @@ MN_HD MN_INLINE void cpu_step(Ctx& c, const Mem& mm, Cpu& r) {
       uint32_t p0, p1;
       if (mode == AM_IND) { p0 = b1 | (b2 << 8); p1 = ((p0 & 0xFF) == 0xFF) ? (p0 & 0xFF00u) : ((p0 + 1) & 0xFFFFu); }
       else { p0 = (mode == AM_IZX) ? ((b1 + r.X) & 0xFFu) : b1; p1 = (p0 + 1) & 0xFFu; }
-      const uint32_t lo = rd(c, mm, r, p0);
-      base = lo | (rd(c, mm, r, p1) << 8);
+      const uint32_t lo = rd<TRACK>(c, mm, r, p0);
+      base = lo | (rd<TRACK>(c, mm, r, p1) << 8);
       ea = (mode == AM_IZY) ? ((base + r.Y) & 0xFFFFu) : base;
     } else {
       const uint32_t isel = (k >> K_ISEL) & 3u;
@@ -853,7 +869,7 @@ MN_HD MN_INLINE void cpu_step(Ctx& c, const Mem& mm, Cpu& r) {
     }
     if (cls == OC_READ && ((base ^ ea) & 0xFF00u)) r.cycles += 1;
     // ---- read phase
-    if (cls == OC_READ || cls == OC_RMW) m = rd(c, mm, r, ea);
+    if (cls == OC_READ || cls == OC_RMW) m = rd<TRACK>(c, mm, r, ea);
   }
   // ---- operate phase
   uint32_t w;
@@ -889,9 +905,9 @@ MN_HD MN_INLINE void cpu_step(Ctx& c, const Mem& mm, Cpu& r) {
       r.PC = target;
     }
     w = 0;
-  } else w = cpu_special(c, mm, r, ir, op, m, ea, b1);
+  } else w = cpu_special<TRACK>(c, mm, r, ir, op, m, ea, b1);
   // ---- write phase
-  if (cls == OC_WRITE || (cls == OC_RMW && mode != AM_ACC)) wr(c, mm, r, ea, w);
+  if (cls == OC_WRITE || (cls == OC_RMW && mode != AM_ACC)) wr<TRACK>(c, mm, r, ea, w);
 }
 
 
@@ -933,14 +949,20 @@ MN_HD MN_INLINE void rng_seed(uint32_t* r, uint32_t seed) {
   for (int i = 0; i < 8; ++i) rng_advance(r);
 }
 
-MN_HD MN_INLINE int32_t ram_bcd(const Ctx& c, int off) { const uint32_t b = ram_at(c, off & 0x7F); return int32_t((b >> 4) * 10 + (b & 15)); }
+MN_HD MN_INLINE uint32_t ram_seen(Ctx& c, int off) {
+  const uint32_t j = uint32_t(off) & 0x7Fu;
+  if (j & 64u) c.obs_hi |= 1ull << (j & 63u); else c.obs_lo |= 1ull << (j & 63u);
+  return ram_at(c, int(j));
+}
+MN_HD MN_INLINE int32_t ram_bcd(Ctx& c, int off) { const uint32_t b = ram_seen(c, off); return int32_t((b >> 4) * 10 + (b & 15)); }
 
 // per-game reward / terminal / lives from RAM after every frame
 MN_HD MN_NOINLINE void game_observe(Ctx& c) {
   EnvState& s = *c.s;
   int32_t sc = s.score;
   bool term = false;
-#define RB(o) int32_t(ram_at(c, (o) & 0x7F))
+#define RB(o) int32_t(ram_seen(c, (o)))
+  c.obs_lo = c.obs_hi = 0;
   switch (s.game) {
     case G_PONG: { const int32_t x = RB(13), y = RB(14); sc = y - x; term = (x == 21 || y == 21); break; }
     case G_BREAKOUT: {
@@ -1066,8 +1088,8 @@ MN_HD MN_INLINE void console_reset(Ctx& c, uint32_t rnd) {
     Cpu r;
     cpu_load(s, r);
     const Mem mm = mem_of(c);
-    const uint32_t lo = rd(c, mm, r, 0xFFFC);
-    s.PC = uint16_t(lo | (rd(c, mm, r, 0xFFFD) << 8));
+    const uint32_t lo = rd<false>(c, mm, r, 0xFFFC);
+    s.PC = uint16_t(lo | (rd<false>(c, mm, r, 0xFFFD) << 8));
     s.dbus = uint8_t(r.dbus);
   }
 }
@@ -1087,10 +1109,16 @@ struct Unit {
   bool in_frame, frozen_last, job_is_act;
 };
 // the part of a running unit the flat loop keeps in registers
-struct Hot { Cpu cpu; int budget; bool in_frame, more; };
+struct Hot {
+  Cpu cpu; int budget; bool in_frame, more;
+  uint32_t instr;                 // 6502 instructions executed
+  uint64_t def_lo, def_hi, dep_lo, dep_hi;   // RAM-dependence probe, carried from frame to frame (see Cpu)
+  bool tainted, obs_bad;          // obs_bad: the RAM scrape looked at a byte the program had not written yet
+};
 
 MN_HD MN_INLINE void unit_idle(Unit& u) { u.kind = U_ACTS; u.idx = u.total = 0; u.in_frame = false; u.reward = 0; u.frozen_last = false; }
 
+// `seed`: U_POWER_ON: the ALE seed; U_RESET: the RNG draw (already taken) that seeds the RIOT timer
 MN_HD MN_INLINE void unit_init(Ctx& c, Unit& u, int kind, int action, int count, uint32_t seed) {
   EnvState& s = *c.s;
   u.kind = kind; u.idx = 0; u.action = action; u.reward = 0; u.in_frame = false; u.frozen_last = false; u.budget = 0;
@@ -1105,7 +1133,7 @@ MN_HD MN_INLINE void unit_init(Ctx& c, Unit& u, int kind, int action, int count,
   }
   s.episode_frame_number = 0;
   s.left_paddle = s.right_paddle = MN_PADDLE_DEFAULT;
-  console_reset(c, rng_next(s.rng));
+  console_reset(c, (kind == U_POWER_ON) ? rng_next(s.rng) : seed);
   u.nstart = game_start_actions(s.game);
   u.total = 64 + u.nstart + count;
 }
@@ -1145,18 +1173,35 @@ MN_HD MN_NOINLINE void unit_job_begin(Ctx& c, Unit& u) {
     u.in_frame = true;
   }
 }
-MN_HD MN_INLINE void hot_init(const Unit& u, Hot& h) { h.in_frame = false; h.more = u.idx < u.total; h.budget = 0; h.cpu.stop = false; }
+MN_HD MN_INLINE void hot_init(const Unit& u, Hot& h) {
+  h.in_frame = false; h.more = u.idx < u.total; h.budget = 0; h.cpu.stop = false; h.instr = 0;
+  h.def_lo = h.def_hi = h.dep_lo = h.dep_hi = 0; h.tainted = false; h.obs_bad = false;
+}
 MN_HD MN_INLINE bool hot_has_work(const Hot& h) { return h.in_frame || h.more; }
 // one tick: start the next job, or run one instruction of the frame in progress
+template <bool TRACK>
 MN_HD MN_INLINE void unit_tick(Ctx& c, const Mem& mm, Unit& u, Hot& h) {
   if (!h.in_frame) {
     unit_job_begin(c, u);
     h.in_frame = u.in_frame; h.more = u.idx < u.total;
-    if (h.in_frame) { cpu_load(*c.s, h.cpu); h.cpu.stop = false; h.budget = 25000; }
+    if (h.in_frame) {
+      cpu_load(*c.s, h.cpu); h.cpu.stop = false; h.budget = 25000;
+      if (TRACK) { h.cpu.def_lo = h.def_lo; h.cpu.def_hi = h.def_hi; h.cpu.dep_lo = h.dep_lo; h.cpu.dep_hi = h.dep_hi; h.cpu.tainted = h.tainted; }
+    }
     return;
   }
-  cpu_step(c, mm, h.cpu);
-  if (h.cpu.stop || --h.budget == 0) { cpu_store(*c.s, h.cpu); unit_job_done(c, u); h.in_frame = false; }
+  cpu_step<TRACK>(c, mm, h.cpu);
+  if (h.cpu.stop || --h.budget == 0) {
+    h.instr += uint32_t(25000 - h.budget);
+    cpu_store(*c.s, h.cpu);
+    if (TRACK) {
+      h.def_lo = h.cpu.def_lo; h.def_hi = h.cpu.def_hi; h.dep_lo = h.cpu.dep_lo; h.dep_hi = h.cpu.dep_hi; h.tainted = h.cpu.tainted;
+    }
+    unit_job_done(c, u);
+    h.in_frame = false;
+    // scrapes after RomSettings::reset() (job 64 on) shape the episode: they must only see written bytes
+    if (TRACK && (u.kind == U_ACTS || u.idx > 64) && ((c.obs_lo & ~h.def_lo) | (c.obs_hi & ~h.def_hi))) h.obs_bad = true;
+  }
 }
 
 // after the unit's last tick: flush the picture and report whether the pixel-less frames were harmless

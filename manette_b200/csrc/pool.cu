@@ -106,11 +106,42 @@ struct PoolDev {             // kernel argument block (by value)
   int32_t* counts;           // 3 x MN_MAX_GAMES
   int32_t* error;            // sticky: 1 = episode over right after reset (atari_emulator.py:108-109)
   unsigned long long* total_next;
+  // reset memoisation (see k_reset_prepare)
+  uint8_t* memo;             // n_games x 75 timer seeds x MN_MEMO_SLOTS entries of memo_entry_bytes
+  int32_t memo_entry_bytes, memo_enabled;
+  uint32_t* reset_rnd;       // (N,) the RNG draw that seeds the RIOT timer of the reset in flight
+  uint8_t* pre_ram;          // (N,128) RIOT RAM as it was before the reset in flight (memo key of a miss)
+  int32_t* memo_hit;         // (N,) entry index the reset in flight is restored from
+  int32_t* memo_busy;        // per (game, timer seed) bucket: one insertion at a time
+  unsigned long long* track; // (N,5) def_lo def_hi dep_lo dep_hi flags : RAM-dependence probe of the reset in flight
+  unsigned long long* memo_stats;   // hits, misses, inserts
+  unsigned long long* total_instr;  // emulated 6502 instructions
   unsigned long long* redo_count;   // units re-run with every frame drawn (exact fallback of the pixel-less frames)
   const Tables* tables;
 };
 
 enum { ROUND_FIGAR = 0, ROUND_RESET = 1, ROUND_INITIAL = 2, ROUND_POWER_ON = 3, ROUND_SINGLE = 4 };
+
+// ---- reset memoisation
+// get_initial_state() = reset_game (64+ frames) + 16 NOOP frames is a pure function of (a) the RNG draw that
+// seeds the RIOT timer, 25 + draw % 75, and (b) the RIOT RAM bytes the program READS BEFORE IT WRITES them
+// after the console reset -- for 11 of the 12 README games there are none.  The first reset with a given key
+// is emulated with a probe (k_round<true>) that records exactly that read-before-write set and which bytes got
+// written; its result is stored.  Later resets whose RAM agrees on the entry's read-before-write bytes are
+// bit-identical by determinism and are restored by copy (bytes the segment never wrote keep their own value).
+#define MN_MEMO_SLOTS 8
+#define MN_TIMER_SEEDS 75
+struct MemoHdr {
+  int32_t state;             // 0 empty, 1 being written, 2 valid
+  int32_t n_acts;            // ALE act() calls inside the segment (2 RNG advances and one frame count each)
+  unsigned long long dep_lo, dep_hi, def_lo, def_hi;
+  uint8_t dep_val[128];      // RAM before the reset (only the dep bytes matter)
+  uint8_t ram[128];          // RAM after the segment (only the def bytes matter)
+  EnvState env;              // after the segment; RNG / frame counter / ring head are the env's own on restore
+  uint32_t ring_head;
+  uint32_t pad;
+};
+__host__ __device__ inline size_t memo_hdr_bytes() { return (sizeof(MemoHdr) + 15) & ~size_t(15); }
 
 // ----------------------------------------------------------------------------- kernels
 __global__ void k_begin_step(PoolDev p, int use_indices) {
@@ -167,6 +198,7 @@ __global__ void k_single_list(PoolDev p, int which, int env, int ale_action) {
 // One round of emulation for the envs on list `in`.  Dynamic shared memory:
 //   [rom | tables | core slots (8 warps x slots x 43 words) | ram (8 warps x slots x 128 B, word-interleaved)
 //    | TIA write FIFOs (8 warps x slots x 17 words)]
+template <bool TRACK>
 __global__ void __launch_bounds__(MN_THREADS, 2) k_round(PoolDev p, int mode, int in, int out) {
   extern __shared__ __align__(16) uint8_t smem[];
   // ---- which game does this block serve
@@ -221,6 +253,7 @@ __global__ void __launch_bounds__(MN_THREADS, 2) k_round(PoolDev p, int mode, in
     const uint32_t ep = p.episode[e];
     kind = U_RESET;
     ucount = p.random_start ? int(start_noops(uint32_t(p.seed), uint32_t(p.env_id_offset + e), ep)) : 0;
+    seed = p.reset_rnd[e];   // drawn by k_reset_prepare
     p.episode[e] = ep + 1;
   } else action = (mode == ROUND_INITIAL) ? int(G.actions[0]) : p.cur_action[e];
 
@@ -245,14 +278,28 @@ __global__ void __launch_bounds__(MN_THREADS, 2) k_round(PoolDev p, int mode, in
     }
     Hot hot;
     hot_init(u, hot);
+    if (TRACK && mine && mode == ROUND_INITIAL) {   // the probe continues from the reset round
+      const unsigned long long* t = p.track + size_t(e) * 5;
+      hot.def_lo = t[0]; hot.def_hi = t[1]; hot.dep_lo = t[2]; hot.dep_hi = t[3];
+      hot.tainted = (t[4] & 1ull) != 0; hot.obs_bad = (t[4] & 2ull) != 0;
+    }
     const Mem mm = mem_of(c);
     for (;;) {
       const bool work = hot_has_work(hot);
       if (!__any_sync(wmask, work)) break;
-      if (work) unit_tick(c, mm, u, hot);
+      if (work) unit_tick<TRACK>(c, mm, u, hot);
       if (__any_sync(wmask, c.fifo_n >= MN_FIFO_HIGH)) tia_drain(c);
     }
-    if (mine) { bad = unit_finish(c); res = u; }
+    if (mine) {
+      bad = unit_finish(c); res = u; atomicAdd(p.total_instr, (unsigned long long)hot.instr);
+      // an env whose game ended inside this macro step is reset before anyone can look at its frames
+      if (mode == ROUND_FIGAR && (s->flags & F_TERMINAL)) bad = false;
+      if (TRACK) {
+        unsigned long long* t = p.track + size_t(e) * 5;
+        t[0] = hot.def_lo; t[1] = hot.def_hi; t[2] = hot.dep_lo; t[3] = hot.dep_hi;
+        t[4] = (hot.tainted ? 1ull : 0ull) | (hot.obs_bad ? 2ull : 0ull);
+      }
+    }
     if (!__any_sync(wmask, bad)) break;
     if (attempt == 0 && bad) atomicAdd(p.redo_count, 1ull);
   }
@@ -299,6 +346,150 @@ __global__ void __launch_bounds__(MN_THREADS, 2) k_round(PoolDev p, int mode, in
 
 __global__ void k_clear_counts(PoolDev p, int which) {
   if (threadIdx.x < MN_MAX_GAMES) p.counts[which * MN_MAX_GAMES + threadIdx.x] = 0;
+}
+
+// Every env on the reset list draws the RNG value that seeds its RIOT timer (ALE's System::reset) and looks for
+// a memo entry it may be restored from: hits go to list 0, misses (to be emulated with the probe) to list 1.
+__global__ void k_reset_prepare(PoolDev p) {
+  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= p.n_envs) return;
+  int gi = 0;
+  while (gi + 1 < p.n_games && pos >= p.games[gi + 1].env0) ++gi;
+  if (pos - p.games[gi].env0 >= p.counts[2 * MN_MAX_GAMES + gi]) return;
+  const int e = p.lists[size_t(2) * p.n_envs + pos];
+  const uint32_t rnd = rng_next(p.env[e].rng);
+  p.reset_rnd[e] = rnd;
+  int hit = -1;
+  const unsigned long long* ram8 = reinterpret_cast<const unsigned long long*>(p.ram + size_t(e) * 128);
+  if (p.memo_enabled) {
+    const size_t bucket = (size_t(gi) * MN_TIMER_SEEDS + rnd % MN_TIMER_SEEDS) * MN_MEMO_SLOTS;
+    for (int sl = 0; sl < MN_MEMO_SLOTS && hit < 0; ++sl) {
+      const MemoHdr* m = reinterpret_cast<const MemoHdr*>(p.memo + (bucket + sl) * size_t(p.memo_entry_bytes));
+      if (*reinterpret_cast<const volatile int32_t*>(&m->state) != 2) continue;
+      bool same = true;
+      if (m->dep_lo | m->dep_hi) {
+        const unsigned long long* want = reinterpret_cast<const unsigned long long*>(m->dep_val);
+        for (int w = 0; w < 16 && same; ++w) {
+          const unsigned long long bits = ((w < 8) ? m->dep_lo : m->dep_hi) >> ((w & 7) * 8);
+          unsigned long long mask = 0;   // one 0xFF per dependent byte of this 8-byte word
+          for (int b = 0; b < 8; ++b) if ((bits >> b) & 1ull) mask |= 0xFFull << (8 * b);
+          same = ((ram8[w] ^ want[w]) & mask) == 0ull;
+        }
+      }
+      if (same) hit = int(bucket + sl);
+    }
+  }
+  p.memo_hit[e] = hit;
+  const int which = (hit >= 0) ? 0 : 1;
+  const int k = atomicAdd(&p.counts[which * MN_MAX_GAMES + gi], 1);
+  p.lists[size_t(which) * p.n_envs + p.games[gi].env0 + k] = e;
+  atomicAdd(p.memo_stats + which, 1ull);
+  if (hit < 0) {
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.pre_ram + size_t(e) * 128);
+    for (int w = 0; w < 16; ++w) dst[w] = ram8[w];
+  }
+}
+
+// restores the envs on list 0 from their memo entries: machine, RAM, both frame buffers, the four ring planes
+template <int D>
+__global__ void __launch_bounds__(256) k_reset_restore(PoolDev p) {
+  const int pos = blockIdx.x;
+  int gi = 0;
+  while (gi + 1 < p.n_games && pos >= p.games[gi + 1].env0) ++gi;
+  if (pos - p.games[gi].env0 >= p.counts[0 * MN_MAX_GAMES + gi]) return;
+  const int e = p.lists[size_t(0) * p.n_envs + pos];
+  const uint8_t* entry = p.memo + size_t(p.memo_hit[e]) * size_t(p.memo_entry_bytes);
+  const MemoHdr* m = reinterpret_cast<const MemoHdr*>(entry);
+  const uint4* src = reinterpret_cast<const uint4*>(entry + memo_hdr_bytes());
+  uint4* fb = reinterpret_cast<uint4*>(p.frames + size_t(e) * (2 * MN_FRAME_BYTES));
+  for (int i = threadIdx.x; i < 2 * MN_FRAME_BYTES / 16; i += blockDim.x) fb[i] = src[i];
+  src += 2 * MN_FRAME_BYTES / 16;
+  const int head = p.env[e].ring_head;   // unchanged by four pushes
+  for (int k = 0; k < MN_STACK; ++k) {   // memo plane k = k-th oldest
+    uint4* dst = reinterpret_cast<uint4*>(p.ring + (size_t(e) * MN_STACK + ((head + k) & 3)) * (MN_PLANE * D));
+    for (int i = threadIdx.x; i < MN_PLANE * D / 16; i += blockDim.x) dst[i] = src[size_t(k) * (MN_PLANE * D / 16) + i];
+  }
+  if (threadIdx.x < 128) {
+    const int j = threadIdx.x;
+    const bool def = (((j & 64) ? m->def_hi : m->def_lo) >> (j & 63)) & 1ull;
+    if (def) p.ram[size_t(e) * 128 + j] = m->ram[j];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    EnvState own = p.env[e];
+    EnvState s = m->env;
+    for (int i = 0; i < 4; ++i) s.rng[i] = own.rng[i];
+    for (int i = 0; i < 2 * m->n_acts; ++i) rng_advance(s.rng);
+    s.frame_number = own.frame_number + m->n_acts;
+    s.ring_head = own.ring_head;
+    p.env[e] = s;
+    p.episode[e] += 1;
+  }
+}
+
+// after the probe emulated the misses (list 1): store what it found
+template <int D>
+__global__ void __launch_bounds__(256) k_memo_insert(PoolDev p) {
+  __shared__ int s_slot;
+  const int pos = blockIdx.x;
+  int gi = 0;
+  while (gi + 1 < p.n_games && pos >= p.games[gi + 1].env0) ++gi;
+  if (pos - p.games[gi].env0 >= p.counts[1 * MN_MAX_GAMES + gi]) return;
+  const int e = p.lists[size_t(1) * p.n_envs + pos];
+  const unsigned long long* t = p.track + size_t(e) * 5;
+  const int bucket_id = gi * MN_TIMER_SEEDS + int(p.reset_rnd[e] % MN_TIMER_SEEDS);
+  if (threadIdx.x == 0) {
+    int slot = -1;
+    // the RAM scrape must only have seen written bytes; one insertion per bucket at a time
+    if (!(t[4] & 2ull) && atomicCAS(&p.memo_busy[bucket_id], 0, 1) == 0) {
+      const size_t bucket = size_t(bucket_id) * MN_MEMO_SLOTS;
+      const uint8_t* pre = p.pre_ram + size_t(e) * 128;
+      bool known = false;
+      for (int sl = 0; sl < MN_MEMO_SLOTS && !known; ++sl) {   // stored since k_reset_prepare looked?
+        const MemoHdr* m = reinterpret_cast<const MemoHdr*>(p.memo + (bucket + sl) * size_t(p.memo_entry_bytes));
+        if (*reinterpret_cast<const volatile int32_t*>(&m->state) != 2) continue;
+        bool same = true;
+        for (int j = 0; j < 128 && same; ++j)
+          if ((((j & 64) ? m->dep_hi : m->dep_lo) >> (j & 63)) & 1ull) same = (m->dep_val[j] == pre[j]);
+        known = same;
+      }
+      for (int sl = 0; sl < MN_MEMO_SLOTS && !known && slot < 0; ++sl) {
+        MemoHdr* m = reinterpret_cast<MemoHdr*>(p.memo + (bucket + sl) * size_t(p.memo_entry_bytes));
+        if (atomicCAS(&m->state, 0, 1) == 0) slot = int(bucket + sl);
+      }
+      if (slot < 0) atomicExch(&p.memo_busy[bucket_id], 0);
+    }
+    s_slot = slot;
+  }
+  __syncthreads();
+  if (s_slot < 0) return;
+  uint8_t* entry = p.memo + size_t(s_slot) * size_t(p.memo_entry_bytes);
+  MemoHdr* m = reinterpret_cast<MemoHdr*>(entry);
+  uint4* dst = reinterpret_cast<uint4*>(entry + memo_hdr_bytes());
+  const uint4* fb = reinterpret_cast<const uint4*>(p.frames + size_t(e) * (2 * MN_FRAME_BYTES));
+  for (int i = threadIdx.x; i < 2 * MN_FRAME_BYTES / 16; i += blockDim.x) dst[i] = fb[i];
+  dst += 2 * MN_FRAME_BYTES / 16;
+  const int head = p.env[e].ring_head;
+  for (int k = 0; k < MN_STACK; ++k) {
+    const uint4* src = reinterpret_cast<const uint4*>(p.ring + (size_t(e) * MN_STACK + ((head + k) & 3)) * (MN_PLANE * D));
+    for (int i = threadIdx.x; i < MN_PLANE * D / 16; i += blockDim.x) dst[size_t(k) * (MN_PLANE * D / 16) + i] = src[i];
+  }
+  if (threadIdx.x < 128) { m->dep_val[threadIdx.x] = p.pre_ram[size_t(e) * 128 + threadIdx.x]; m->ram[threadIdx.x] = p.ram[size_t(e) * 128 + threadIdx.x]; }
+  if (threadIdx.x == 0) {
+    m->def_lo = t[0]; m->def_hi = t[1]; m->dep_lo = t[2]; m->dep_hi = t[3];
+    m->env = p.env[e];
+    m->n_acts = MN_STACK * MN_ACTION_REPEAT;
+    m->ring_head = uint32_t(head);
+    atomicAdd(p.memo_stats + 2, 1ull);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    *reinterpret_cast<volatile int32_t*>(&m->state) = 2;
+    __threadfence();
+    atomicExch(&p.memo_busy[bucket_id], 0);
+  }
 }
 
 // K3 core: one output word = 4 horizontally adjacent pixels of one channel-interleaved plane row.
@@ -645,7 +836,8 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
   h->round_smem = ((max_rom + 15) & ~size_t(15)) + sizeof(Tables) +
                   size_t(MN_WARPS_PER_BLOCK) * slots * (MN_CORE_WORDS * 4 + 128 + (MN_FIFO_CAP + 1) * 4);
   if (h->round_smem > size_t(prop.sharedMemPerBlockOptin)) { delete h; return fail("mn_create: shared memory budget exceeded"); }
-  CU(cudaFuncSetAttribute(k_round, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->round_smem)));
+  CU(cudaFuncSetAttribute(k_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->round_smem)));
+  CU(cudaFuncSetAttribute(k_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->round_smem)));
 
   const size_t N = size_t(n), D = size_t(d.depth);
   uint8_t* roms = nullptr;
@@ -675,6 +867,16 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
   rc |= dev_alloc(h, &d.error, size_t(1));
   rc |= dev_alloc(h, &d.total_next, size_t(1));
   rc |= dev_alloc(h, &d.redo_count, size_t(1));
+  rc |= dev_alloc(h, &d.total_instr, size_t(1));
+  d.memo_enabled = (cfg->random_start == 0 && cfg->no_reset_memo == 0) ? 1 : 0;
+  d.memo_entry_bytes = int32_t(memo_hdr_bytes() + 2 * MN_FRAME_BYTES + size_t(MN_STACK) * MN_PLANE * D);
+  rc |= dev_alloc(h, &d.memo, d.memo_enabled ? size_t(d.n_games) * MN_TIMER_SEEDS * MN_MEMO_SLOTS * size_t(d.memo_entry_bytes) : size_t(16));
+  rc |= dev_alloc(h, &d.reset_rnd, N);
+  rc |= dev_alloc(h, &d.pre_ram, N * 128);
+  rc |= dev_alloc(h, &d.memo_hit, N);
+  rc |= dev_alloc(h, &d.memo_busy, size_t(d.n_games) * MN_TIMER_SEEDS);
+  rc |= dev_alloc(h, &d.track, N * 5);
+  rc |= dev_alloc(h, &d.memo_stats, size_t(4));
   rc |= dev_alloc(h, &h->tables_dev, size_t(1));
   if (rc) { mn_destroy(h); return -1; }
   d.roms = roms;
@@ -697,7 +899,7 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
   {
     const int tb = 256, gb = (n + tb - 1) / tb > 1 ? (n + tb - 1) / tb : 1;
     k_fill_list<<<gb, tb>>>(d, 0);
-    k_round<<<h->round_grid, MN_THREADS, h->round_smem>>>(d, ROUND_POWER_ON, 0, -1);
+    k_round<false><<<h->round_grid, MN_THREADS, h->round_smem>>>(d, ROUND_POWER_ON, 0, -1);
     h->launches += 2;
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
@@ -743,9 +945,10 @@ static void launch_push(mn_pool* h, int in, cudaStream_t st) {
   prof_mark(h, PK_PUSH, st, false);
   h->launches++;
 }
-static void launch_round(mn_pool* h, int mode, int in, int out, cudaStream_t st) {
+static void launch_round(mn_pool* h, int mode, int in, int out, cudaStream_t st, bool track = false) {
   prof_mark(h, PK_ROUND, st, true);
-  k_round<<<h->round_grid, MN_THREADS, h->round_smem, st>>>(h->d, mode, in, out);
+  if (track) k_round<true><<<h->round_grid, MN_THREADS, h->round_smem, st>>>(h->d, mode, in, out);
+  else k_round<false><<<h->round_grid, MN_THREADS, h->round_smem, st>>>(h->d, mode, in, out);
   prof_mark(h, PK_ROUND, st, false);
   h->launches++;
 }
@@ -756,12 +959,31 @@ static void launch_emit(mn_pool* h, int lo, int hi, int publish, cudaStream_t st
   prof_mark(h, PK_EMIT, st, false);
   h->launches++;
 }
-// get_initial_state() for the envs on list `which` (atari_emulator.py:102-110)
-static void launch_initial_state(mn_pool* h, int which, cudaStream_t st) {
-  launch_round(h, ROUND_RESET, which, -1, st);
+// get_initial_state() for the envs on the reset list (list 2) (atari_emulator.py:102-110): memo hits are restored
+// by copy, misses are emulated with the RAM-dependence probe and then stored
+static void launch_initial_state(mn_pool* h, cudaStream_t st) {
+  const int n = h->d.n_envs;
+  prof_mark(h, PK_OTHER, st, true);
+  k_clear_counts<<<1, 32, 0, st>>>(h->d, 0);
+  k_clear_counts<<<1, 32, 0, st>>>(h->d, 1);
+  k_reset_prepare<<<(n + 255) / 256, 256, 0, st>>>(h->d);
+  if (h->d.memo_enabled) {
+    if (h->d.depth == 1) k_reset_restore<1><<<n, 256, 0, st>>>(h->d); else k_reset_restore<3><<<n, 256, 0, st>>>(h->d);
+    h->launches++;
+  }
+  prof_mark(h, PK_OTHER, st, false);
+  h->launches += 3;
+  const bool track = h->d.memo_enabled != 0;
+  launch_round(h, ROUND_RESET, 1, -1, st, track);
   for (int i = 0; i < MN_STACK; ++i) {
-    launch_round(h, ROUND_INITIAL, which, (i == MN_STACK - 1) ? -1 : -2, st);
-    launch_push(h, which, st);
+    launch_round(h, ROUND_INITIAL, 1, (i == MN_STACK - 1) ? -1 : -2, st, track);
+    launch_push(h, 1, st);
+  }
+  if (h->d.memo_enabled) {
+    prof_mark(h, PK_OTHER, st, true);
+    if (h->d.depth == 1) k_memo_insert<1><<<n, 256, 0, st>>>(h->d); else k_memo_insert<3><<<n, 256, 0, st>>>(h->d);
+    prof_mark(h, PK_OTHER, st, false);
+    h->launches++;
   }
 }
 
@@ -774,7 +996,7 @@ int mn_reset_all(mn_handle h, void* stream) {
   const int n = h->d.n_envs, tb = 256, gb = (n + tb - 1) / tb;
   k_fill_list<<<gb, tb, 0, st>>>(h->d, 2);
   h->launches++;
-  launch_initial_state(h, 2, st);
+  launch_initial_state(h, st);
   launch_emit(h, 0, n, 1, st);
   CU(cudaGetLastError());
   CU(cudaEventRecord(h->done, st));
@@ -797,7 +1019,7 @@ int mn_step_async(mn_handle h, int use_indices, void* stream) {
     if (r < h->max_rep) { k_clear_counts<<<1, 32, 0, st>>>(h->d, in); h->launches++; }
     in = out;
   }
-  launch_initial_state(h, 2, st);
+  launch_initial_state(h, st);
   launch_emit(h, 0, n, 1, st);
   CU(cudaGetLastError());
   CU(cudaEventRecord(h->done, st));
@@ -839,7 +1061,7 @@ int mn_env_reset(mn_handle h, int env, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   k_single_list<<<1, 64, 0, st>>>(h->d, 2, env, 0);
   h->launches++;
-  launch_initial_state(h, 2, st);
+  launch_initial_state(h, st);
   launch_emit(h, env, env + 1, 1, st);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(st));
@@ -940,6 +1162,24 @@ int mn_redo_count(mn_handle h, int64_t* out) {
   CU(cudaSetDevice(h->device));
   unsigned long long v = 0;
   CU(cudaMemcpy(&v, h->d.redo_count, sizeof(v), cudaMemcpyDeviceToHost));
+  *out = int64_t(v);
+  return 0;
+}
+
+int mn_memo_stats(mn_handle h, int64_t* out3) {
+  if (!h || !out3) return fail("mn_memo_stats: null argument");
+  CU(cudaSetDevice(h->device));
+  unsigned long long v[4] = {0, 0, 0, 0};
+  CU(cudaMemcpy(v, h->d.memo_stats, sizeof(v), cudaMemcpyDeviceToHost));
+  out3[0] = int64_t(v[0]); out3[1] = int64_t(v[1]); out3[2] = int64_t(v[2]);
+  return 0;
+}
+
+int mn_total_instructions(mn_handle h, int64_t* out) {
+  if (!h || !out) return fail("mn_total_instructions: null argument");
+  CU(cudaSetDevice(h->device));
+  unsigned long long v = 0;
+  CU(cudaMemcpy(&v, h->d.total_instr, sizeof(v), cudaMemcpyDeviceToHost));
   *out = int64_t(v);
   return 0;
 }

@@ -43,7 +43,7 @@ class DevicePool(object):
     """games: list of (name, rom_bytes, n_envs) groups laid out back to back (env ids 0..N-1)."""
 
     def __init__(self, games, rgb=False, single_life_episodes=False, random_start=False, random_seed=3,
-                 env_id_offset=0, tab_rep=None, device=None, envs_per_warp=0, draw_all_frames=False):
+                 env_id_offset=0, tab_rep=None, device=None, envs_per_warp=0, draw_all_frames=False, reset_memo=True):
         if not torch.cuda.is_available():
             raise _native.NativeError("manette_b200 needs a CUDA device (there is no CPU fallback)")
         self._L = _native.load()
@@ -64,7 +64,7 @@ class DevicePool(object):
         cfg = _native.MnConfig(device=self.device.index, n_games=len(self._games), games=arr, rgb=int(bool(rgb)),
                                single_life_episodes=int(bool(single_life_episodes)), random_start=int(bool(random_start)),
                                random_seed=int(random_seed), env_id_offset=int(env_id_offset), nb_choices=len(tab),
-                               tab_rep=ctab, envs_per_warp=int(envs_per_warp), draw_all_frames=int(bool(draw_all_frames)))
+                               tab_rep=ctab, envs_per_warp=int(envs_per_warp), draw_all_frames=int(bool(draw_all_frames)), no_reset_memo=int(not reset_memo))
         h = C.c_void_p()
         _native.check(self._L.mn_create(C.byref(cfg), C.byref(h)), "mn_create")
         self._h = h
@@ -166,6 +166,17 @@ class DevicePool(object):
     def total_next_calls(self):
         v = C.c_int64()
         _native.check(self._L.mn_total_next_calls(self._h, C.byref(v)), "mn_total_next_calls")
+        return v.value
+
+    def memo_stats(self):
+        """(restored, emulated, stored) get_initial_state() calls since creation."""
+        v = (C.c_int64 * 3)()
+        _native.check(self._L.mn_memo_stats(self._h, v), "mn_memo_stats")
+        return int(v[0]), int(v[1]), int(v[2])
+
+    def total_instructions(self):
+        v = C.c_int64()
+        _native.check(self._L.mn_total_instructions(self._h, C.byref(v)), "mn_total_instructions")
         return v.value
 
     def redo_count(self):

@@ -15,6 +15,8 @@ struct HostEnv {
   int drain_at;        // drain when this many writes are pending (tests sweep it)
   int redo_count;      // units that had to be re-run with every frame drawn
   Unit last;
+  bool last_tainted, last_alldef64;   // RAM-dependence probe of the last unit
+  uint64_t dep_lo, dep_hi;
 };
 
 // the flat loop of k_round for a single environment, with the exact fallback
@@ -30,11 +32,12 @@ static void run_unit(HostEnv* e, int kind, int action, int count, uint32_t seed,
     hot_init(u, hot);
     const Mem mm = mem_of(e->c);
     while (hot_has_work(hot)) {
-      unit_tick(e->c, mm, u, hot);
+      unit_tick<true>(e->c, mm, u, hot);
       if (e->c.fifo_n >= e->drain_at) tia_drain(e->c);
     }
     const bool bad = unit_finish(e->c);
     e->last = u;
+    e->last_tainted = hot.tainted; e->last_alldef64 = !hot.obs_bad; e->dep_lo = hot.dep_lo; e->dep_hi = hot.dep_hi;
     if (!bad) break;
     e->redo_count++;
     e->s = snap;
@@ -69,7 +72,14 @@ int he_next(void* h, int a, int skip_frames, int* pool_single) {
   if (pool_single) *pool_single = e->last.frozen_last ? 1 : 0;
   return e->last.reward;
 }
-void he_reset_game(void* h, int noops, int skip_frames) { run_unit((HostEnv*)h, U_RESET, 0, noops, 0, !skip_frames); }
+void he_reset_game(void* h, int noops, int skip_frames) {
+  HostEnv* e = (HostEnv*)h;
+  const uint32_t rnd = rng_next(e->s.rng);   // the draw that seeds the RIOT timer
+  run_unit(e, U_RESET, 0, noops, rnd, !skip_frames);
+}
+void he_reset_dependence(void* h, uint64_t* out2) { HostEnv* e = (HostEnv*)h; out2[0] = e->dep_lo; out2[1] = e->dep_hi; }
+// 1 if the last reset never read a RAM byte before writing it and had written all 128 before the settings reset
+int he_reset_was_ram_independent(void* h) { HostEnv* e = (HostEnv*)h; return (!e->last_tainted && e->last_alldef64) ? 1 : 0; }
 int he_game_over(void* h) { return (((HostEnv*)h)->s.flags & F_TERMINAL) ? 1 : 0; }
 int he_lives(void* h) { return ((HostEnv*)h)->s.lives; }
 void he_get_ram(void* h, uint8_t* out) { memcpy(out, ((HostEnv*)h)->ram, 128); }

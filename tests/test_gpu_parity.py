@@ -105,3 +105,62 @@ def test_golden_fixture(game):
         assert np.array_equal(st, d["final_states"])
     finally:
         pool.close()
+
+
+@pytest.mark.parametrize("game", ["pong", "yars_revenge", "seaquest"])
+def test_memoised_resets_match_oracle(game):
+    """get_initial_state() restored from the reset memo (same RIOT timer seed seen before) must equal the
+    emulated one: many resets of a few envs, every one compared with the oracle, and hits must have happened."""
+    n = 4
+    ora = OraclePool(game, n)
+    pool = _device_pool(game, n)
+    try:
+        assert np.array_equal(ora.initial_states(), (pool.reset_all(), pool.states.cpu().numpy())[1])
+        rng = np.random.RandomState(11)
+        for rep in range(45):
+            for e in range(n):
+                for _ in range(int(rng.randint(0, 3))):
+                    a = int(rng.randint(ora.num_actions))
+                    obs, rew, term = ora.emus[e].next(a)
+                    r2, t2 = pool.env_next(e, a)
+                    assert (rew, bool(term)) == (r2, t2)
+                    assert np.array_equal(pool.states[e].cpu().numpy(), obs)
+                want = ora.emus[e].get_initial_state()
+                pool.env_reset(e)
+                assert np.array_equal(pool.states[e].cpu().numpy(), want), (game, rep, e, "state")
+                assert np.array_equal(pool.ram(e), ora.emus[e].ale.getRAM()), (game, rep, e, "ram")
+                assert np.array_equal(pool.screen(e), ora.emus[e].ale.getScreen()), (game, rep, e, "screen")
+                assert np.array_equal(pool.cpu_state(e)[:7], ora.emus[e].ale.getCPU()[:7]), (game, rep, e, "cpu")
+        hits, misses, stored = pool.memo_stats()
+        assert hits + misses == n * 46 and stored >= 1
+        if game != "yars_revenge":   # its reset reads two RAM bytes that differ every time: exact, but never reusable
+            assert hits > 40, (hits, misses, stored)
+    finally:
+        pool.close()
+
+
+def test_memo_off_equals_memo_on():
+    """The memo is an optimisation only: identical results with it disabled."""
+    import manette_b200 as mb
+    import torch
+    game, n, k = "breakout", 32, 11
+    tab = list(range(k))
+    pools = [mb.DevicePool([(game, rom_bytes(game), n)], tab_rep=tab, reset_memo=m, draw_all_frames=not m) for m in (True, False)]
+    try:
+        for p in pools:
+            p.reset_all()
+        acts, reps = util.schedule(3, 40, n, 4, k)
+        for t in range(40):
+            outs = []
+            for p in pools:
+                p.action_idx.copy_(torch.as_tensor(acts[t].astype(np.int32)))
+                p.repetition_idx.copy_(torch.as_tensor(reps[t].astype(np.int32)))
+                p.step_async(use_indices=True)
+                p.wait()
+                outs.append((p.states.cpu().numpy(), p.rewards.cpu().numpy(), p.terminals.cpu().numpy(), p.frames.cpu().numpy()))
+            for a, b in zip(outs[0], outs[1]):
+                assert np.array_equal(a, b), t
+        assert pools[0].memo_stats()[0] > 0 and pools[1].memo_stats()[0] == 0
+    finally:
+        for p in pools:
+            p.close()

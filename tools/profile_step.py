@@ -42,12 +42,15 @@ def main():
     for _ in range(a.decorrelate):
         step()
     f0 = pool.total_next_calls()
+    i0 = pool.total_instructions()
     t0 = time.perf_counter()
     for _ in range(a.steps):
         step()
     dt = time.perf_counter() - t0
     fr = pool.total_next_calls() - f0
-    print("game=%s envs=%d steps=%d next_calls=%d seconds=%.3f frames_per_s=%.1f" % (a.game, a.envs, a.steps, fr, dt, fr / dt))
+    ins = pool.total_instructions() - i0
+    print("game=%s envs=%d epw=%d steps=%d next_calls=%d seconds=%.3f frames_per_s=%.1f instr_per_next=%.0f Minstr_per_s=%.1f redo=%d"
+          % (a.game, a.envs, a.envs_per_warp, a.steps, fr, dt, fr / dt, ins / max(fr, 1), ins / dt / 1e6, pool.redo_count()))
     pool.close()
 
 
