@@ -537,8 +537,10 @@ MN_HD MN_INLINE void tia_poke(Ctx& c, uint32_t addr, uint32_t v) {
       s.vsync = uint8_t(v);
       if (v & 0x02) s.vsync_finish_clk = clock + 228;
       else if (clock >= s.vsync_finish_clk) { s.vsync_finish_clk = MN_NEVER; s.flags = (s.flags | F_STOP) & ~F_PARTIAL; }
-      return;
-    }
+      // falls through to the FIFO: VSYNC changes nothing in the picture, but the emulated TIA draws up to the clock
+      // of EVERY access, and the VSYNC strobe that ends a frame is the last one -- it fixes where the frame's
+      // drawing stops (what stays in the buffer below that point is older)
+    } else
     if (addr == 0x01) {
       if (!(s.vblank_cpu & 0x80) && (v & 0x80)) s.flags |= F_DUMP;
       if ((s.vblank_cpu & 0x80) && !(v & 0x80)) { s.flags &= ~F_DUMP; s.dump_disabled_cycle = s.cycles; }

@@ -816,12 +816,13 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
     d.tab_rep[i] = cfg->tab_rep[i];
     if (cfg->tab_rep[i] > h->max_rep) h->max_rep = cfg->tab_rep[i];
   }
-  // env slots per warp: spread the pool over about 16 resident warps per SM
+  // env slots per warp.  Measured on B200 (profiles/): the emulation loop is latency bound per warp, so small
+  // pools want many thin warps (less opcode divergence per warp) and large pools full ones; about 1024 warps
+  // is where the two meet.
   int slots = cfg->envs_per_warp;
   if (slots <= 0) {
-    const int target_warps = prop.multiProcessorCount * 16;
     slots = 1;
-    while (slots < 32 && n > target_warps * slots) slots *= 2;
+    while (slots < 32 && n > 1024 * slots) slots *= 2;
   }
   if (slots != 1 && slots != 2 && slots != 4 && slots != 8 && slots != 16 && slots != 32) { delete h; return fail("mn_create: envs_per_warp must be 1,2,4,8,16 or 32"); }
   d.slots = slots;

@@ -30,6 +30,12 @@ void orc_minimal_actions(void* h, int* out) {
 void orc_get_ram(void* h, uint8_t* out) { std::memcpy(out, static_cast<AleEnv*>(h)->con.ram, 128); }
 void orc_set_ram(void* h, int idx, int v) { static_cast<AleEnv*>(h)->con.ram[idx & 127] = uint8_t(v); }
 void orc_get_screen(void* h, uint8_t* out) { std::memcpy(out, static_cast<AleEnv*>(h)->con.screen(), SCREEN_W * SCREEN_H); }
+// both TIA frame buffers: [0] the current one, [1] the one drawn the frame before
+void orc_get_both_screens(void* h, uint8_t* out) {
+  Console& c = static_cast<AleEnv*>(h)->con;
+  std::memcpy(out, c.fb[c.cur_fb], SCREEN_W * SCREEN_H);
+  std::memcpy(out + SCREEN_W * SCREEN_H, c.fb[c.cur_fb ^ 1], SCREEN_W * SCREEN_H);
+}
 void orc_get_screen_gray(void* h, uint8_t* out) {
   const uint8_t* s = static_cast<AleEnv*>(h)->con.screen();
   for (int i = 0; i < SCREEN_W * SCREEN_H; ++i) out[i] = palette_gray(s[i]);

@@ -35,7 +35,7 @@ def lib():
         L.orc_act.restype = C.c_int
         L.orc_console_step.argtypes = [C.c_void_p, C.c_int]
         L.orc_set_ram.argtypes = [C.c_void_p, C.c_int, C.c_int]
-        for f in ("orc_minimal_actions", "orc_get_ram", "orc_get_screen", "orc_get_screen_gray",
+        for f in ("orc_minimal_actions", "orc_get_ram", "orc_get_screen", "orc_get_both_screens", "orc_get_screen_gray",
                   "orc_get_screen_rgb", "orc_get_cpu"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_void_p]
             getattr(L, f).restype = None

@@ -78,6 +78,14 @@ void he_reset_game(void* h, int noops, int skip_frames) {
   run_unit(e, U_RESET, 0, noops, rnd, !skip_frames);
 }
 void he_reset_dependence(void* h, uint64_t* out2) { HostEnv* e = (HostEnv*)h; out2[0] = e->dep_lo; out2[1] = e->dep_hi; }
+// reset with a given RNG draw for the RIOT timer seed, then the four NOOP next() of get_initial_state()
+void he_initial_state_with_draw(void* h, uint32_t rnd, int skip_frames) {
+  HostEnv* e = (HostEnv*)h;
+  run_unit(e, U_RESET, 0, 0, rnd, !skip_frames);
+  for (int i = 0; i < 4; ++i) run_unit(e, U_ACTS, 0, 4, 0, !skip_frames);
+}
+int he_state_size() { return (int)sizeof(EnvState); }
+void he_get_state(void* h, uint8_t* out) { memcpy(out, &((HostEnv*)h)->s, sizeof(EnvState)); }
 // 1 if the last reset never read a RAM byte before writing it and had written all 128 before the settings reset
 int he_reset_was_ram_independent(void* h) { HostEnv* e = (HostEnv*)h; return (!e->last_tainted && e->last_alldef64) ? 1 : 0; }
 int he_game_over(void* h) { return (((HostEnv*)h)->s.flags & F_TERMINAL) ? 1 : 0; }
@@ -87,7 +95,13 @@ void he_get_screen(void* h, uint8_t* out) {
   HostEnv* e = (HostEnv*)h;
   memcpy(out, e->fb.data() + ((e->s.flags & F_CURFB) ? MN_FRAME_BYTES : 0), MN_FRAME_BYTES);
 }
-void he_get_both_screens(void* h, uint8_t* out) { memcpy(out, ((HostEnv*)h)->fb.data(), 2 * MN_FRAME_BYTES); }
+// [0] the current frame buffer, [1] the other one
+void he_get_both_screens(void* h, uint8_t* out) {
+  HostEnv* e = (HostEnv*)h;
+  const int cur = (e->s.flags & F_CURFB) ? 1 : 0;
+  memcpy(out, e->fb.data() + cur * MN_FRAME_BYTES, MN_FRAME_BYTES);
+  memcpy(out + MN_FRAME_BYTES, e->fb.data() + (cur ^ 1) * MN_FRAME_BYTES, MN_FRAME_BYTES);
+}
 void he_get_cpu(void* h, int32_t* out) {
   EnvState& s = ((HostEnv*)h)->s;
   out[0] = s.A; out[1] = s.X; out[2] = s.Y; out[3] = s.SP; out[4] = s.PC; out[5] = (int32_t)pack_ps(s); out[6] = s.cycles;

@@ -32,9 +32,10 @@ def libs():
     H.he_reset_game.argtypes = [C.c_void_p, C.c_int, C.c_int]
     for f in ("he_game_over", "he_lives"):
         getattr(H, f).argtypes = [C.c_void_p]
+    L = orc_loader.lib()
     for f in ("he_get_ram", "he_get_screen", "he_get_both_screens", "he_get_cpu"):
         getattr(H, f).argtypes = [C.c_void_p, C.c_void_p]
-    return orc_loader.lib(), H
+    return L, H
 
 
 def _taps(L, H, o, h):
@@ -86,8 +87,7 @@ def test_next_with_pixel_less_frames_matches_oracle(libs, game):
     L.orc_minimal_actions(o, acts.ctypes.data)
     rng = np.random.RandomState(2)
     both = np.zeros((2, 33600), np.uint8)
-    prev = np.zeros(33600, np.uint8)
-    cur = np.zeros(33600, np.uint8)
+    oboth = np.zeros((2, 33600), np.uint8)
     for i in range(220):
         a = int(acts[rng.randint(n)])
         want_r, grabs = 0, []
@@ -104,9 +104,12 @@ def test_next_with_pixel_less_frames_matches_oracle(libs, game):
         assert np.array_equal(ro, rh) and np.array_equal(co, ch), (game, i)
         assert np.array_equal(so, sh), (game, i, "current screen")
         H.he_get_both_screens(h, both.ctypes.data)
+        L.orc_get_both_screens(o, oboth.ctypes.data)
         want_max = np.maximum(grabs[0], grabs[1])
         got_max = sh if single.value else np.maximum(both[0], both[1])
         assert np.array_equal(want_max, got_max), (game, i, "pooled frames")
+        if not L.orc_game_over(o):
+            assert np.array_equal(both, oboth), (game, i, "both frame buffers")
         assert L.orc_game_over(o) == H.he_game_over(h)
         if L.orc_game_over(o) or i % 70 == 69:
             noops = int(rng.randint(0, 31))
@@ -116,4 +119,7 @@ def test_next_with_pixel_less_frames_matches_oracle(libs, game):
             H.he_reset_game(h, noops, 1)
             (ro, so, co), (rh, sh, ch) = _taps(L, H, o, h)
             assert np.array_equal(ro, rh) and np.array_equal(so, sh) and np.array_equal(co, ch), (game, i, "reset")
+            H.he_get_both_screens(h, both.ctypes.data)
+            L.orc_get_both_screens(o, oboth.ctypes.data)
+            assert np.array_equal(both, oboth), (game, i, "both frame buffers after reset")
     L.orc_destroy(o); H.he_destroy(h)
