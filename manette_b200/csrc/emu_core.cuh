@@ -755,7 +755,9 @@ MN_HD MN_INLINE void op_sbc(Cpu& r, uint32_t m) {
   } else {
     int32_t diff = int32_t(bcd_bin(a)) - int32_t(bcd_bin(m)) - int32_t(1 - cin);
     if (diff < 0) diff += 100;
-    const uint32_t res = ((uint32_t(diff % 100) / 10) << 4) | uint32_t(diff % 10);
+    // signed arithmetic on purpose: with non-BCD operands diff can still be negative here and the
+    // oracle's int expression is the behaviour to match
+    const uint32_t res = uint32_t((((diff % 100) / 10) << 4) | (diff % 10)) & 0xFFu;
     const bool carry = a >= (m + (1 - cin));
     const bool v = ((a ^ res) & 0x80) && ((res ^ m) & 0x80);
     r.A = res & 0xFF; r.nz = r.A;
@@ -847,10 +849,11 @@ MN_HD MN_INLINE void cpu_step(Ctx& c, const Mem& mm, Cpu& r) {
   const uint32_t k = mm.tab->ctl[ir];
   const uint32_t mode = d & 15, cls = (d >> 4) & 3, op = (d >> 6) & 63;
   const uint32_t len = ((k >> K_LEN) & 3u) + 1u;
+  // the whole base cycle count is charged right after the opcode fetch (operand fetches from the RIOT see it)
+  { const uint32_t cy = (d >> 12) & 7; r.cycles += int32_t(cy ? cy : 8u); }   // 0 encodes the 8-cycle forms
   if (!fast_code) { if (len >= 2) b1 = rd<TRACK>(c, mm, r, (pc + 1) & 0xFFFFu); if (len == 3) b2 = rd<TRACK>(c, mm, r, (pc + 2) & 0xFFFFu); }
   else r.dbus = (len == 1) ? ir : (len == 2) ? b1 : b2;
   r.PC = (pc + len) & 0xFFFFu;
-  { const uint32_t cy = (d >> 12) & 7; r.cycles += int32_t(cy ? cy : 8u); }   // 0 encodes the 8-cycle forms
   // ---- address phase
   uint32_t ea = 0, m = b1;
   if (mode >= AM_ZP && mode != AM_REL) {

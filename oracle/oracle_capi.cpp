@@ -69,6 +69,8 @@ void* orc_console_create(const uint8_t* rom, int n) {
   e->rom.assign(rom, rom + n);
   e->con.rom = e->rom.data(); e->con.rom_size = uint32_t(n); e->con.cart = AleEnv::detect_cart(rom, size_t(n));
   e->con.system_reset(0);
+  e->con.start_frame();            // as the first run_frame() after a reset would
+  e->con.partial_frame = true;
   return e;
 }
 void orc_console_step(void* h, int n_instr) { Console& c = static_cast<AleEnv*>(h)->con; for (int i = 0; i < n_instr; ++i) c.step(); }

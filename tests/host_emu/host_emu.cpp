@@ -84,6 +84,38 @@ void he_initial_state_with_draw(void* h, uint32_t rnd, int skip_frames) {
   run_unit(e, U_RESET, 0, 0, rnd, !skip_frames);
   for (int i = 0; i < 4; ++i) run_unit(e, U_ACTS, 0, 4, 0, !skip_frames);
 }
+// ---- raw-console taps for the 6502 conformance fuzz (no ALE layer, generic game)
+void* he_console_create(const uint8_t* rom, int n) {
+  HostEnv* e = new HostEnv();
+  memset(&e->s, 0, sizeof(e->s));
+  memset(e->ram, 0, 128);
+  build_tables(&e->tab);
+  e->rom.assign(rom, rom + n);
+  e->fb.assign(2 * MN_FRAME_BYTES, 0);
+  e->s.game = 0; e->s.cart = (uint8_t)detect_cart(rom, n); e->s.ctrl = 0;
+  e->c.s = &e->s; e->c.rom = e->rom.data(); e->c.ram = e->ram; e->c.ram_stride = 4; e->c.fb = e->fb.data(); e->c.tab = &e->tab;
+  e->c.fifo = e->fifo; e->c.fifo_n = 0; e->c.all_pixels = true;
+  e->drain_at = MN_FIFO_HIGH; e->redo_count = 0;
+  e->s.swcha = 0xFF; e->s.swchb = 0x3F; e->s.flags = F_INPT4 | F_INPT5;
+  for (int i = 0; i < 4; ++i) e->s.analog[i] = MN_RES_MAX;
+  console_reset(e->c, 0);
+  frame_begin(e->c, true);         // as the first frame job after a reset would
+  e->s.flags |= F_PARTIAL;
+  return e;
+}
+void he_set_ram(void* h, int idx, int v) { ((HostEnv*)h)->ram[idx & 127] = (uint8_t)v; }
+void he_console_step(void* h, int n_instr) {
+  HostEnv* e = (HostEnv*)h;
+  Cpu r;
+  cpu_load(e->s, r);
+  const Mem mm = mem_of(e->c);
+  for (int i = 0; i < n_instr; ++i) {
+    cpu_step<false>(e->c, mm, r);
+    if (e->c.fifo_n >= e->drain_at) tia_drain(e->c);
+  }
+  tia_drain(e->c);
+  cpu_store(e->s, r);
+}
 int he_state_size() { return (int)sizeof(EnvState); }
 void he_get_state(void* h, uint8_t* out) { memcpy(out, &((HostEnv*)h)->s, sizeof(EnvState)); }
 // 1 if the last reset never read a RAM byte before writing it and had written all 128 before the settings reset

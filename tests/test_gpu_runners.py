@@ -1,0 +1,120 @@
+"""GPU: the drop-in boundary -- Runners / AtariEmulator / ExplorationPolicy with the reference's signatures --
+driven the way paac.py drives it, against the oracle's restatement of the reference's worker pool."""
+import numpy as np
+import pytest
+
+import util
+from util import OraclePool, host_path, rom_bytes
+
+pytestmark = pytest.mark.gpu
+
+
+def _drive(game, n, workers, rgb=False, k=11, max_rep=10, single_life=False, random_start=False, steps=10, seed=3):
+    import manette_b200 as mb
+    mb.release_pools()
+    args = util.args_for(game, rgb=rgb, max_repetition=max_rep, nb_choices=k, single_life_episodes=single_life,
+                         random_start=random_start, random_seed=seed)
+    ora = OraclePool(game, n, rgb=rgb, nb_choices=k, max_repetition=max_rep, single_life=single_life,
+                     random_start=random_start, seed=seed, noops=lambda gid, ep: mb.start_noops(seed, gid, ep))
+    # --- exactly paac.py:97-106
+    creator = mb.EnvironmentCreator(args)
+    assert creator.num_actions == ora.num_actions
+    emulators = np.asarray([creator.create_environment(i) for i in range(n)])
+    explo = mb.ExplorationPolicy(args)
+    assert explo.tab_rep == ora.tab_rep
+    shared_states = np.asarray([e.get_initial_state() for e in emulators], dtype=np.uint8)
+    assert np.array_equal(shared_states, ora.initial_states())
+    variables = [shared_states, np.zeros(n, np.float32), np.asarray([False] * n, np.float32),
+                 np.zeros((n, creator.num_actions), np.float32), np.zeros((n, k), np.float32)]
+    runners = mb.Runners(explo.tab_rep, mb.EmulatorRunner, emulators, workers, variables)
+    runners.start()
+    s_states, s_rewards, s_over, s_actions, s_rep = runners.get_shared_variables()
+    assert s_states.dtype == np.uint8 and s_states.shape == (n, 84, 84, 4 * (3 if rgb else 1))
+    acts, reps = util.schedule(17, steps, n, creator.num_actions, k)
+    for t in range(steps):
+        for z in range(n):                                   # paac.py:159-161
+            s_actions[z] = np.eye(creator.num_actions)[acts[t][z]]
+            s_rep[z] = np.eye(k)[reps[t][z]]
+        runners.update_environments()
+        runners.wait_updated()
+        ws, wr, wt, _ = ora.macro_step(acts[t], reps[t])
+        assert np.array_equal(s_rewards, wr) and np.array_equal(s_over, wt), t
+        assert np.array_equal(s_states, ws), t
+    # zero-copy device views alias the same results
+    dv = runners.get_device_variables()
+    assert np.array_equal(dv[0].cpu().numpy(), s_states) and np.array_equal(dv[1].cpu().numpy(), s_rewards)
+    runners.stop()
+    mb.release_pools()
+
+
+def test_pong_paac_default_config():
+    """BASELINE config 1 in miniature: Pong, 32 emulators / 8 workers, no repetition head."""
+    _drive("pong", 32, 8, k=1, max_rep=0, steps=8)
+
+
+def test_breakout_figar10():
+    _drive("breakout", 16, 4, steps=14)
+
+
+def test_seaquest_rgb_figar10():
+    _drive("seaquest", 8, 2, rgb=True, steps=6)
+
+
+def test_single_life_episodes():
+    _drive("breakout", 8, 2, single_life=True, steps=30)
+
+
+def test_random_start_schedule():
+    _drive("breakout", 8, 2, random_start=True, steps=25)
+
+
+def test_uneven_worker_split_raises_like_np_split():
+    import manette_b200 as mb
+    mb.release_pools()
+    args = util.args_for("pong")
+    emus = [mb.AtariEmulator(i, args) for i in range(6)]
+    with pytest.raises(ValueError):
+        mb.Runners([0], mb.EmulatorRunner, emus, 4, None)
+    mb.release_pools()
+
+
+def test_test_py_style_single_emulator_loop():
+    """test.py:98-109: one emulator, FiGAR loop in the caller."""
+    import manette_b200 as mb
+    mb.release_pools()
+    args = util.args_for("pong", max_repetition=10, nb_choices=11)
+    env = mb.AtariEmulator(0, args)
+    ora = host_path.PortAtariEmulator(0, args)
+    assert list(env.get_legal_actions()) == list(ora.get_legal_actions())
+    assert np.array_equal(env.get_initial_state(), ora.get_initial_state())
+    rng = np.random.RandomState(4)
+    tab = mb.tab_repetitions(10, 11)
+    for _ in range(6):
+        a = np.eye(6)[rng.randint(6)]
+        r = np.eye(11)[rng.randint(11)]
+        act = mb.Action(tab, 0, a, r)
+        s1, r1, t1 = env.next(act.current_action)
+        s2, r2, t2 = ora.next(act.current_action)
+        assert np.array_equal(s1, s2) and r1 == r2 and t1 == t2
+        while act.is_repeated() and not t1:
+            s1, r1, t1 = env.next(act.repeat())
+            s2, r2, t2 = ora.next(act.current_action)
+            assert np.array_equal(s1, s2) and r1 == r2 and t1 == t2
+    assert env.get_noop() == [1.0, 0.0]
+    mb.release_pools()
+
+
+def test_exploration_policy_numpy_in_numpy_out():
+    import manette_b200 as mb
+    args = util.args_for("pong", max_repetition=10, nb_choices=11)
+    explo = mb.ExplorationPolicy(args, seed=42)
+    pi = np.random.RandomState(0).dirichlet(np.ones(6), size=64).astype(np.float32)
+    rho = np.random.RandomState(1).dirichlet(np.ones(11), size=64).astype(np.float32)
+    a, r = explo.choose_next_actions(pi, rho, 6)
+    wa, wr, wah, wrh = host_path.choose_next_actions(pi, rho, 0, seed=42, step=0)
+    assert a.shape == (64, 6) and r.shape == (64, 11) and a.dtype == np.float64
+    assert np.array_equal(a, wah) and np.array_equal(r, wrh)
+    assert explo.global_step == 64
+    greedy = mb.ExplorationPolicy(args, test=True)
+    a, r = greedy.choose_next_actions(pi, rho, 6)
+    assert np.array_equal(a.argmax(1), pi.argmax(1)) and np.array_equal(r.argmax(1), rho.argmax(1))
