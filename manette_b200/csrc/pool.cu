@@ -837,8 +837,9 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
   h->round_smem = ((max_rom + 15) & ~size_t(15)) + sizeof(Tables) +
                   size_t(MN_WARPS_PER_BLOCK) * slots * (MN_CORE_WORDS * 4 + 128 + (MN_FIFO_CAP + 1) * 4);
   if (h->round_smem > size_t(prop.sharedMemPerBlockOptin)) { delete h; return fail("mn_create: shared memory budget exceeded"); }
-  CU(cudaFuncSetAttribute(k_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->round_smem)));
-  CU(cudaFuncSetAttribute(k_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->round_smem)));
+  // the attribute belongs to the function, not to this pool: several pools with different needs may coexist
+  CU(cudaFuncSetAttribute(k_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(prop.sharedMemPerBlockOptin)));
+  CU(cudaFuncSetAttribute(k_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(prop.sharedMemPerBlockOptin)));
 
   const size_t N = size_t(n), D = size_t(d.depth);
   uint8_t* roms = nullptr;
