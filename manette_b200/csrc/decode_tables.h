@@ -147,13 +147,21 @@ inline void build_tables(Tables* t) {
       if (strcmp(kMnemonics[k].name, mne) == 0) mi = &kMnemonics[k];
     int cls = mi->cls;
     if (mi->op == O_NOP && mode == AM_IMP) cls = OC_NONE;   // only the multi-byte NOPs touch memory
-    t->desc[opc] = MN_DESC(mode, cls, mi->op, cyc & 7);
-    t->aux[opc] = (uint8_t)mi->aux;
-    t->ctl[opc] = datapath_control(mi->op, mode);
+    const bool has_ea = mode >= AM_ZP && mode != AM_REL;
+    const bool wide = mode == AM_ABS || mode == AM_ABX || mode == AM_ABY || mode == AM_IND;
+    uint32_t d = MN_DESC(mode, cls, mi->op, cyc) | (uint32_t(mi->aux & 0xFF) << 16);
+    if (has_ea) d |= D_EA;
+    if (mode >= AM_IZX && mode != AM_REL) d |= D_INDIRECT;
+    if (has_ea && (cls == OC_READ || cls == OC_RMW)) d |= D_READ;
+    if (cls == OC_WRITE || (cls == OC_RMW && mode != AM_ACC)) d |= D_WRITE;
+    if (has_ea && cls == OC_READ) d |= D_PAGEPEN;
+    if (mi->op == O_BRANCH) d |= D_BRANCH;
+    t->e[opc].k = datapath_control(mi->op, mode);
+    t->e[opc].d = d;
+    t->e[opc].x = has_ea ? (wide ? 0xFFFFu : 0xFFu) : 0u;
+    t->e[opc].pad = 0;
   }
 }
-// cycles 8 does not fit 3 bits: the read-modify-write undocumented (zp,X)/(zp),Y forms take 8.
-// They are encoded as 0 and fixed up here.
-inline int desc_cycles(uint16_t d) { int c = (d >> 12) & 7; return c == 0 ? 8 : c; }
+inline int desc_cycles(uint32_t d) { return int((d >> 12) & 15); }
 
 }  // namespace mn

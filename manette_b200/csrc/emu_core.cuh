@@ -29,10 +29,12 @@
 #ifdef __CUDACC__
 #define MN_HD __host__ __device__
 #define MN_NOINLINE __noinline__
+#define MN_NOINLINE_DEV __forceinline__
 #define MN_INLINE __forceinline__
 #else
 #define MN_HD
 #define MN_NOINLINE
+#define MN_NOINLINE_DEV inline
 #define MN_INLINE inline
 #endif
 
@@ -82,14 +84,25 @@ enum {  // operations
   O_ASL, O_LSR, O_ROL, O_ROR, O_INC, O_DEC, O_SLO, O_RLA, O_SRE, O_RRA, O_DCP, O_ISC,   // rmw class
   O_BRANCH, O_JMP, O_JSR, O_RTS, O_RTI, O_BRK, O_PHA, O_PHP, O_PLA, O_PLP,
   O_TAX, O_TAY, O_TXA, O_TYA, O_TSX, O_TXS, O_INX, O_INY, O_DEX, O_DEY, O_FLAG, O_KIL };
-// descriptor: [3:0] mode  [5:4] class  [11:6] op  [14:12] base cycles  [15] unused
-// branches keep their condition in a second table byte; flag ops likewise.
-#define MN_DESC(mode, cls, op, cyc) uint16_t((mode) | ((cls) << 4) | ((op) << 6) | ((cyc) << 12))
+// descriptor: [3:0] mode  [5:4] class  [11:6] op  [15:12] base cycles (2..8)
+// branches keep their condition in the aux byte of the table entry; flag ops likewise.
+#define MN_DESC(mode, cls, op, cyc) uint32_t((mode) | ((cls) << 4) | ((op) << 6) | ((cyc) << 12))
 
+// One 16-byte entry per opcode, read with a single shared-memory load:
+//   k  control word of the table-driven datapath (K_* fields, see cpu_step)
+//   d  [15:0] descriptor (MN_DESC, cycles in 4 bits)  [23:16] aux (branch: [7:6]=flag selector 0 N,1 V,2 C,3 Z,
+//      [0]=wanted value ; flag op: [7:1]=bit index in P, [0]=set)  [31:24] D_* phase flags
+//   x  operand mask: 0xFF for the zero-page forms, 0xFFFF for the absolute ones (0 when there is no operand address)
+struct alignas(16) TabEnt { uint32_t k, d, x, pad; };
+enum : uint32_t {
+  D_EA = 1u << 24       /* has an effective address (mode >= zp, not relative) */,
+  D_INDIRECT = 1u << 25 /* (zp,X) (zp),Y (abs) */,
+  D_READ = 1u << 26     /* read phase: read / read-modify-write class with an effective address */,
+  D_WRITE = 1u << 27    /* write phase: write class, or read-modify-write on memory */,
+  D_PAGEPEN = 1u << 28  /* read class, indexed: +1 cycle when the index crosses a page */,
+  D_BRANCH = 1u << 29 };
 struct Tables {          // read-only, staged in shared memory by the kernels
-  uint32_t ctl[256];     // control word of the table-driven datapath (K_* fields, see cpu_step)
-  uint16_t desc[256];
-  uint8_t aux[256];      // branch: [7:6]=flag selector (0 N,1 V,2 C,3 Z) [0]=wanted value ; flag op: [7:1]=bit index in P [0]=set
+  TabEnt e[256];
 };
 
 // ------------------------------------------------------------------ per-environment record
@@ -236,6 +249,13 @@ MN_HD MN_INLINE uint32_t perm4(uint32_t x, uint32_t sel) {   // byte i of the re
   uint32_t r = 0;
   for (int i = 0; i < 4; ++i) r |= ((x >> (8 * ((sel >> (4 * i)) & 3))) & 0xFFu) << (8 * i);
   return r;
+#endif
+}
+MN_HD MN_INLINE uint32_t byte_of(uint32_t x, uint32_t i) {   // byte i (0..3) of x
+#ifdef __CUDA_ARCH__
+  return __byte_perm(x, 0u, 0x4440u | i);
+#else
+  return (x >> (8u * i)) & 0xFFu;
 #endif
 }
 // the 8 bits of b -> bit 0 of 8 consecutive nibbles
@@ -634,6 +654,62 @@ MN_HD MN_INLINE void cart_touch(EnvState& s, uint32_t a) {   // a = addr & 0xFFF
   }
 }
 
+// ---- the memory the hot path reads and writes: cartridge ROM, RIOT RAM, decode tables, TIA write FIFO.
+// On the GPU all four live in the block's dynamic shared memory and are addressed by 32-bit offsets into it
+// (shared-space loads and stores, no generic 64-bit pointer arithmetic); the host test build uses plain addresses.
+#ifdef __CUDACC__
+typedef uint32_t maddr;
+extern __shared__ __align__(16) uint8_t mn_smem[];
+#else
+typedef uintptr_t maddr;
+#endif
+MN_HD MN_INLINE uint32_t m8(maddr a) {
+#if defined(__CUDA_ARCH__)
+  return mn_smem[a];
+#elif defined(__CUDACC__)
+  (void)a; return 0u;   // host pass of nvcc: never executed
+#else
+  return *reinterpret_cast<const uint8_t*>(a);
+#endif
+}
+MN_HD MN_INLINE void m8w(maddr a, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  mn_smem[a] = uint8_t(v);
+#elif defined(__CUDACC__)
+  (void)a; (void)v;
+#else
+  *reinterpret_cast<uint8_t*>(a) = uint8_t(v);
+#endif
+}
+MN_HD MN_INLINE void m32w(maddr a, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  *reinterpret_cast<uint32_t*>(mn_smem + a) = v;
+#elif defined(__CUDACC__)
+  (void)a; (void)v;
+#else
+  *reinterpret_cast<uint32_t*>(a) = v;
+#endif
+}
+MN_HD MN_INLINE TabEnt tab_entry(maddr tab, uint32_t ir) {
+#if defined(__CUDA_ARCH__)
+  const uint4 q = *reinterpret_cast<const uint4*>(mn_smem + tab + ir * 16u);
+  TabEnt t; t.k = q.x; t.d = q.y; t.x = q.z; t.pad = q.w; return t;
+#elif defined(__CUDACC__)
+  (void)tab; (void)ir; TabEnt t; t.k = t.d = t.x = t.pad = 0u; return t;
+#else
+  return reinterpret_cast<const TabEnt*>(tab)[ir];
+#endif
+}
+MN_HD MN_INLINE maddr maddr_of(const void* p) {
+#if defined(__CUDA_ARCH__)
+  return maddr(reinterpret_cast<const uint8_t*>(p) - mn_smem);
+#elif defined(__CUDACC__)
+  (void)p; return 0u;
+#else
+  return reinterpret_cast<maddr>(p);
+#endif
+}
+
 // The 6502 and what it needs on every instruction, register resident while a frame runs.
 struct Cpu {
   uint32_t A, X, Y, SP, PC;
@@ -641,16 +717,22 @@ struct Cpu {
   uint32_t nz;       // Z <=> (nz & 0xFF) == 0 ; N <=> nz & 0x180
   uint32_t dbus;     // last value on the data bus (the undriven bits of TIA reads)
   uint32_t segmap;   // cartridge window: byte k = 1K ROM page visible at $1000 + k * $400
+  uint32_t hot_lo;   // first cartridge offset that may be a bank-switch hot spot ($1000 = none)
   int32_t cycles;
-  bool banked, stop;
+  int32_t clk0;      // EnvState::clk_frame_start (changes only between frames)
+  int32_t fifo_n;    // pending TIA writes; Ctx::fifo_n is brought up to date around every out-of-line call
+  bool stop;
   // RAM-dependence probe (TRACK instantiations only): which RIOT RAM bytes the program has written since
   // the console reset, and whether it ever read one before writing it
   uint64_t def_lo, def_hi, dep_lo, dep_hi;   // dep: the bytes read before written
   bool tainted;
 };
-// the read-mostly pointers of the fast paths, passed by value so they stay in registers
-struct Mem { const uint8_t* rom; uint8_t* ram; uint32_t ram_stride; const Tables* tab; };
-MN_HD MN_INLINE Mem mem_of(const Ctx& c) { Mem m; m.rom = c.rom; m.ram = c.ram; m.ram_stride = uint32_t(c.ram_stride); m.tab = c.tab; return m; }
+// the read-mostly addresses of the fast paths, passed by value so they stay in registers
+struct Mem { maddr rom, ram, tab, fifo; uint32_t ram_stride; };
+MN_HD MN_INLINE Mem mem_of(const Ctx& c) {
+  Mem m; m.rom = maddr_of(c.rom); m.ram = maddr_of(c.ram); m.tab = maddr_of(c.tab); m.fifo = maddr_of(c.fifo);
+  m.ram_stride = uint32_t(c.ram_stride); return m;
+}
 MN_HD MN_INLINE uint32_t make_segmap(const EnvState& s) {
   if (s.cart == CART_2K) return 0x01000100u;
   if (s.cart == CART_4K) return 0x03020100u;
@@ -658,9 +740,11 @@ MN_HD MN_INLINE uint32_t make_segmap(const EnvState& s) {
   const uint32_t b = uint32_t(s.bank) * 4u;   // F8 / F6: one 4K bank
   return b | ((b + 1) << 8) | ((b + 2) << 16) | ((b + 3) << 24);
 }
+// does not touch fifo_n: that one is carried by the flat loop across frames
 MN_HD MN_INLINE void cpu_load(const EnvState& s, Cpu& r) {
   r.A = s.A; r.X = s.X; r.Y = s.Y; r.SP = s.SP; r.PC = s.PC; r.P = s.P; r.nz = s.nz; r.dbus = s.dbus;
-  r.cycles = s.cycles; r.segmap = make_segmap(s); r.banked = s.cart > CART_4K; r.stop = (s.flags & F_STOP) != 0;
+  r.cycles = s.cycles; r.clk0 = s.clk_frame_start; r.segmap = make_segmap(s); r.hot_lo = (s.cart > CART_4K) ? 0xFE0u : 0x1000u;
+  r.stop = (s.flags & F_STOP) != 0;
   r.def_lo = r.def_hi = r.dep_lo = r.dep_hi = 0; r.tainted = false;
 }
 MN_HD MN_INLINE void cpu_store(EnvState& s, const Cpu& r) {
@@ -668,33 +752,40 @@ MN_HD MN_INLINE void cpu_store(EnvState& s, const Cpu& r) {
   s.P = uint8_t(r.P); s.nz = uint16_t(r.nz); s.dbus = uint8_t(r.dbus); s.cycles = r.cycles;
 }
 
-// ROM and RIOT RAM both sit in shared memory: one byte load from a selected address serves either
-MN_HD MN_INLINE uint8_t* fast_ptr(const Mem& mm, uint32_t segmap, uint32_t addr) {
-  const uint32_t a = addr & 0xFFFu;
-  const uint32_t ri = (((segmap >> ((a >> 10) << 3)) & 0xFFu) << 10) | (a & 0x3FFu);
+// where a cartridge-window / RIOT RAM address lives
+MN_HD MN_INLINE maddr rom_addr(const Mem& mm, uint32_t segmap, uint32_t addr) {
+  const uint32_t page = byte_of(segmap, (addr >> 10) & 3u);
+  return mm.rom + ((page << 10) | (addr & 0x3FFu));
+}
+MN_HD MN_INLINE maddr ram_addr(const Mem& mm, uint32_t addr) {
   const uint32_t j = addr & 0x7Fu;
-  const uint32_t mi = (j >> 2) * mm.ram_stride + (j & 3u);
-  return (addr & 0x1000u) ? const_cast<uint8_t*>(mm.rom + ri) : (mm.ram + mi);
+  return mm.ram + (j >> 2) * mm.ram_stride + (j & 3u);
 }
 // the uncommon reads: bank-switch hot spots (the switch happens before the read), TIA, RIOT
 MN_HD MN_NOINLINE uint32_t rd_slow(Ctx& c, uint32_t addr, int32_t cycles, uint32_t dbus) {
   EnvState& s = *c.s;
-  if (addr & 0x1000u) { cart_touch(s, addr & 0xFFFu); return *fast_ptr(mem_of(c), make_segmap(s), addr); }
+  if (addr & 0x1000u) { cart_touch(s, addr & 0xFFFu); return m8(rom_addr(mem_of(c), make_segmap(s), addr)); }
   s.cycles = cycles; s.dbus = uint8_t(dbus);
   return (addr & 0x80u) ? riot_peek(c, addr) : tia_peek(c, addr);
 }
 template <bool TRACK>
 MN_HD MN_INLINE uint32_t rd(Ctx& c, const Mem& mm, Cpu& r, uint32_t addr) {
   const bool rom = (addr & 0x1000u) != 0;
-  const bool fast = rom ? !(r.banked && (addr & 0xFFFu) >= 0xFE0u) : ((addr & 0x0280u) == 0x0080u);
+  const bool fast = rom ? ((addr & 0xFFFu) < r.hot_lo) : ((addr & 0x0280u) == 0x0080u);
   uint32_t v;
   if (TRACK && !rom && fast) { const uint32_t j = addr & 0x7Fu; if (!((((j & 64u) ? r.def_hi : r.def_lo) >> (j & 63u)) & 1ull)) { r.tainted = true; if (j & 64u) r.dep_hi |= 1ull << (j & 63u); else r.dep_lo |= 1ull << (j & 63u); } }
-  if (fast) v = *fast_ptr(mm, r.segmap, addr);
-  else { v = rd_slow(c, addr, r.cycles, r.dbus); if (rom) r.segmap = make_segmap(*c.s); }
+  if (fast) v = m8(rom ? rom_addr(mm, r.segmap, addr) : ram_addr(mm, addr));
+  else {
+    c.fifo_n = r.fifo_n;
+    v = rd_slow(c, addr, r.cycles, r.dbus);
+    r.fifo_n = c.fifo_n;
+    if (rom) r.segmap = make_segmap(*c.s);
+  }
   r.dbus = v;
   return v;
 }
-// the writes that do not land in RIOT RAM; returns the CPU cycle count (WSYNC / RSYNC stall the 6502)
+// the writes that land neither in RIOT RAM nor (the common case) in the TIA write FIFO;
+// returns the CPU cycle count (WSYNC / RSYNC stall the 6502)
 MN_HD MN_NOINLINE int32_t wr_slow(Ctx& c, uint32_t addr, uint32_t v, int32_t cycles) {
   EnvState& s = *c.s;
   if (addr & 0x1000u) { if (s.cart > CART_4K) cart_touch(s, addr & 0xFFFu); return cycles; }
@@ -705,16 +796,25 @@ MN_HD MN_NOINLINE int32_t wr_slow(Ctx& c, uint32_t addr, uint32_t v, int32_t cyc
 template <bool TRACK>
 MN_HD MN_INLINE void wr(Ctx& c, const Mem& mm, Cpu& r, uint32_t addr, uint32_t v) {
   v &= 0xFFu;
-  if ((addr & 0x1280u) == 0x0080u) {
-    *fast_ptr(mm, r.segmap, addr) = uint8_t(v);
-    if (TRACK) { const uint32_t j = addr & 0x7Fu; if (j & 64u) r.def_hi |= 1ull << (j & 63u); else r.def_lo |= 1ull << (j & 63u); }
-  }
-  else {
-    r.cycles = wr_slow(c, addr, v, r.cycles);
-    if (addr & 0x1000u) r.segmap = make_segmap(*c.s);
-    else r.stop = (c.s->flags & F_STOP) != 0;
-  }
   r.dbus = v;
+  if ((addr & 0x1280u) == 0x0080u) {
+    m8w(ram_addr(mm, addr), v);
+    if (TRACK) { const uint32_t j = addr & 0x7Fu; if (j & 64u) r.def_hi |= 1ull << (j & 63u); else r.def_lo |= 1ull << (j & 63u); }
+    return;
+  }
+  // TIA registers $04..$2C before the scan-line overflow point: nothing the 6502 can observe, only a FIFO entry
+  // (same arithmetic as tia_poke, which stays the reference for everything else)
+  const uint32_t a6 = addr & 0x3Fu;
+  const int32_t rel = r.cycles * 3 - r.clk0;
+  if (!(addr & 0x1080u) && a6 >= 0x04u && rel < 228 * (MN_MAX_SCANLINES + 1) && r.fifo_n < MN_FIFO_CAP) {
+    if (a6 <= 0x2Cu && !(a6 >= 0x15u && a6 <= 0x1Au)) { m32w(mm.fifo + uint32_t(r.fifo_n) * 4u, uint32_t(rel) | (a6 << 17) | (v << 23)); r.fifo_n++; }
+    return;
+  }
+  c.fifo_n = r.fifo_n;
+  r.cycles = wr_slow(c, addr, v, r.cycles);
+  r.fifo_n = c.fifo_n;
+  if (addr & 0x1000u) r.segmap = make_segmap(*c.s);
+  else r.stop = (c.s->flags & F_STOP) != 0;
 }
 
 // ------------------------------------------------------------------ 6502
@@ -777,7 +877,7 @@ MN_HD MN_INLINE uint32_t stk_pull(Ctx& c, const Mem& mm, Cpu& r) { r.SP = (r.SP 
 // The opcodes outside the table-driven datapath (stack / flow / flag ops, BIT, decimal ADC/SBC, undocumented).
 // Returns the value of the write phase for the write / read-modify-write classes.
 template <bool TRACK>
-MN_HD MN_INLINE uint32_t cpu_special(Ctx& c, const Mem& mm, Cpu& r, uint32_t ir, uint32_t op, uint32_t m, uint32_t ea, uint32_t b1) {
+MN_HD MN_NOINLINE_DEV uint32_t cpu_special(Ctx& c, const Mem& mm, Cpu& r, uint32_t ax, uint32_t op, uint32_t m, uint32_t ea) {
   uint32_t w = 0;
   switch (op) {
     case O_ADC: op_adc(r, m); break;
@@ -820,10 +920,9 @@ MN_HD MN_INLINE uint32_t cpu_special(Ctx& c, const Mem& mm, Cpu& r, uint32_t ir,
     case O_PHP: stk_push<TRACK>(c, mm, r, pack_ps(r.P, r.nz) | 0x10); break;
     case O_PLA: r.A = stk_pull<TRACK>(c, mm, r); r.nz = r.A; break;
     case O_PLP: unpack_ps(r, stk_pull<TRACK>(c, mm, r)); break;
-    case O_FLAG: { const uint32_t ax = mm.tab->aux[ir]; const uint32_t mask = 1u << (ax >> 1); r.P = (ax & 1) ? (r.P | mask) : (r.P & ~mask); break; }
+    case O_FLAG: { const uint32_t mask = 1u << (ax >> 1); r.P = (ax & 1) ? (r.P | mask) : (r.P & ~mask); break; }
     default: break;   // O_KIL, O_NOP
   }
-  (void)b1;
   return w;
 }
 
@@ -840,45 +939,44 @@ enum { BS_M = 0, BS_ONE, BS_FF, BS_ZERO };
 template <bool TRACK>
 MN_HD MN_INLINE void cpu_step(Ctx& c, const Mem& mm, Cpu& r) {
   const uint32_t pc = r.PC;
-  // ---- fetch: code almost always runs from cartridge ROM away from the bank-switch hot spots
-  const bool fast_code = (pc & 0x1000u) && ((pc & 0xFFFu) < 0xFDEu);
+  // ---- fetch: code almost always runs from cartridge ROM, away from the bank-switch hot spots and not across
+  // a 1K page of the cartridge window (pages need not be contiguous in the ROM image)
+  const bool fast_code = (pc & 0x1000u) && ((pc & 0xFFFu) < 0xFDEu) && ((pc & 0x3FFu) < 0x3FEu);
   uint32_t ir, b1 = 0, b2 = 0;
-  if (fast_code) { ir = *fast_ptr(mm, r.segmap, pc); b1 = *fast_ptr(mm, r.segmap, pc + 1); b2 = *fast_ptr(mm, r.segmap, pc + 2); }
+  if (fast_code) { const maddr a = rom_addr(mm, r.segmap, pc); ir = m8(a); b1 = m8(a + 1); b2 = m8(a + 2); }
   else ir = rd<TRACK>(c, mm, r, pc);
-  const uint32_t d = mm.tab->desc[ir];
-  const uint32_t k = mm.tab->ctl[ir];
-  const uint32_t mode = d & 15, cls = (d >> 4) & 3, op = (d >> 6) & 63;
-  const uint32_t len = ((k >> K_LEN) & 3u) + 1u;
+  const TabEnt t = tab_entry(mm.tab, ir);
+  const uint32_t k = t.k, d = t.d;
+  const uint32_t len1 = (k >> K_LEN) & 3u;   // length - 1
   // the whole base cycle count is charged right after the opcode fetch (operand fetches from the RIOT see it)
-  { const uint32_t cy = (d >> 12) & 7; r.cycles += int32_t(cy ? cy : 8u); }   // 0 encodes the 8-cycle forms
-  if (!fast_code) { if (len >= 2) b1 = rd<TRACK>(c, mm, r, (pc + 1) & 0xFFFFu); if (len == 3) b2 = rd<TRACK>(c, mm, r, (pc + 2) & 0xFFFFu); }
-  else r.dbus = (len == 1) ? ir : (len == 2) ? b1 : b2;
-  r.PC = (pc + len) & 0xFFFFu;
-  // ---- address phase
-  uint32_t ea = 0, m = b1;
-  if (mode >= AM_ZP && mode != AM_REL) {
-    uint32_t base;
-    if (mode >= AM_IZX) {   // (zp,X)  (zp),Y  (abs)
-      uint32_t p0, p1;
-      if (mode == AM_IND) { p0 = b1 | (b2 << 8); p1 = ((p0 & 0xFF) == 0xFF) ? (p0 & 0xFF00u) : ((p0 + 1) & 0xFFFFu); }
-      else { p0 = (mode == AM_IZX) ? ((b1 + r.X) & 0xFFu) : b1; p1 = (p0 + 1) & 0xFFu; }
-      const uint32_t lo = rd<TRACK>(c, mm, r, p0);
-      base = lo | (rd<TRACK>(c, mm, r, p1) << 8);
-      ea = (mode == AM_IZY) ? ((base + r.Y) & 0xFFFFu) : base;
-    } else {
-      const uint32_t isel = (k >> K_ISEL) & 3u;
-      const uint32_t idx = (isel == 1) ? r.X : (isel == 2) ? r.Y : 0u;
-      const bool wide = mode >= AM_ABS;
-      base = wide ? (b1 | (b2 << 8)) : b1;
-      ea = (base + idx) & (wide ? 0xFFFFu : 0xFFu);
-    }
-    if (cls == OC_READ && ((base ^ ea) & 0xFF00u)) r.cycles += 1;
-    // ---- read phase
-    if (cls == OC_READ || cls == OC_RMW) m = rd<TRACK>(c, mm, r, ea);
+  r.cycles += int32_t((d >> 12) & 15u);
+  if (!fast_code) { if (len1 >= 1) b1 = rd<TRACK>(c, mm, r, (pc + 1) & 0xFFFFu); if (len1 == 2) b2 = rd<TRACK>(c, mm, r, (pc + 2) & 0xFFFFu); }
+  else r.dbus = (len1 == 0) ? ir : (len1 == 1) ? b1 : b2;
+  r.PC = (pc + len1 + 1u) & 0xFFFFu;
+  // ---- address phase: zero-page / absolute, optionally indexed, from the operand mask of the entry
+  const uint32_t isel = (k >> K_ISEL) & 3u;
+  const uint32_t idx = (isel == 1) ? r.X : (isel == 2) ? r.Y : 0u;
+  uint32_t base = (b1 | (b2 << 8)) & t.x;
+  uint32_t ea = (base + idx) & t.x;
+  if (d & D_INDIRECT) {   // (zp,X)  (zp),Y  (abs)
+    const uint32_t mode = d & 15u;
+    uint32_t p0, p1;
+    if (mode == AM_IND) { p0 = b1 | (b2 << 8); p1 = ((p0 & 0xFF) == 0xFF) ? (p0 & 0xFF00u) : ((p0 + 1) & 0xFFFFu); }
+    else { p0 = (mode == AM_IZX) ? ((b1 + r.X) & 0xFFu) : b1; p1 = (p0 + 1) & 0xFFu; }
+    const uint32_t lo = rd<TRACK>(c, mm, r, p0);
+    base = lo | (rd<TRACK>(c, mm, r, p1) << 8);
+    ea = (mode == AM_IZY) ? ((base + r.Y) & 0xFFFFu) : base;
   }
-  // ---- operate phase
+  if ((d & D_PAGEPEN) && ((base ^ ea) & 0xFF00u)) r.cycles += 1;
+  // ---- read phase
+  uint32_t m = b1;
+  if (d & D_READ) m = rd<TRACK>(c, mm, r, ea);
+  // ---- operate phase.  The datapath runs for every opcode; what it may change is in the control word, which is
+  // all zero for the opcodes it cannot express (and is ignored for ADC / SBC in decimal mode).
+  const bool generic = (k & K_GENERIC) && !((k & K_DECIMAL) && (r.P & 0x08u));
+  const uint32_t kk = generic ? k : 0u;
   uint32_t w;
-  if ((k & K_GENERIC) && !((k & K_DECIMAL) && (r.P & 0x08u))) {
+  {
     const uint32_t asel = k & 7u, bsel = (k >> K_BSEL) & 3u, csel = (k >> K_CSEL) & 3u, fn = (k >> K_FN) & 7u;
     const uint32_t a = (asel == AS_A) ? r.A : (asel == AS_X) ? r.X : (asel == AS_Y) ? r.Y : (asel == AS_SP) ? r.SP :
                        (asel == AS_M) ? m : (asel == AS_AX) ? (r.A & r.X) : 0u;
@@ -892,27 +990,29 @@ MN_HD MN_INLINE void cpu_step(Ctx& c, const Mem& mm, Cpu& r) {
     const uint32_t res = (fn == FN_ADD) ? (sum & 0xFFu) : (fn == FN_OR) ? (a | b) : (fn == FN_AND) ? (a & b) :
                          (fn == FN_EOR) ? (a ^ b) : (fn == FN_ASL || fn == FN_ROL) ? left : right;
     const uint32_t cout = (fn == FN_ADD) ? (sum >> 8) : (fn == FN_ASL || fn == FN_ROL) ? (a >> 7) : (a & 1u);
-    if (k & K_NZ) r.nz = res;
-    if (k & K_C) r.P = (r.P & ~1u) | cout;
-    if (k & K_V) r.P = (r.P & ~0x40u) | (((~(a ^ b)) & (a ^ sum) & 0x80u) >> 1);
-    if (k & K_DA) r.A = res;
-    if (k & K_DX) r.X = res;
-    if (k & K_DY) r.Y = res;
-    if (k & K_DSP) r.SP = res;
+    if (kk & K_NZ) r.nz = res;
+    if (kk & K_C) r.P = (r.P & ~1u) | cout;
+    if (kk & K_V) r.P = (r.P & ~0x40u) | (((~(a ^ b)) & (a ^ sum) & 0x80u) >> 1);
+    if (kk & K_DA) r.A = res;
+    if (kk & K_DX) r.X = res;
+    if (kk & K_DY) r.Y = res;
+    if (kk & K_DSP) r.SP = res;
     w = res;
-  } else if (op == O_BRANCH) {
-    const uint32_t ax = mm.tab->aux[ir];
-    const uint32_t sel = ax >> 6;
-    const bool flag = (sel == 0) ? ((r.nz & 0x180u) != 0) : (sel == 1) ? ((r.P & 0x40u) != 0) : (sel == 2) ? ((r.P & 1u) != 0) : ((r.nz & 0xFFu) == 0);
-    if (flag == ((ax & 1u) != 0)) {
-      const uint32_t target = (r.PC + uint32_t(int32_t(int8_t(b1)))) & 0xFFFFu;
-      r.cycles += ((r.PC ^ target) & 0xFF00u) ? 2 : 1;
-      r.PC = target;
-    }
-    w = 0;
-  } else w = cpu_special<TRACK>(c, mm, r, ir, op, m, ea, b1);
+  }
+  if (!generic) {
+    if (d & D_BRANCH) {
+      const uint32_t ax = (d >> 16) & 0xFFu;
+      const uint32_t sel = ax >> 6;
+      const bool flag = (sel == 0) ? ((r.nz & 0x180u) != 0) : (sel == 1) ? ((r.P & 0x40u) != 0) : (sel == 2) ? ((r.P & 1u) != 0) : ((r.nz & 0xFFu) == 0);
+      if (flag == ((ax & 1u) != 0)) {
+        const uint32_t target = (r.PC + uint32_t(int32_t(int8_t(b1)))) & 0xFFFFu;
+        r.cycles += ((r.PC ^ target) & 0xFF00u) ? 2 : 1;
+        r.PC = target;
+      }
+    } else w = cpu_special<TRACK>(c, mm, r, (d >> 16) & 0xFFu, (d >> 6) & 63u, m, ea);
+  }
   // ---- write phase
-  if (cls == OC_WRITE || (cls == OC_RMW && mode != AM_ACC)) wr<TRACK>(c, mm, r, ea, w);
+  if (d & D_WRITE) wr<TRACK>(c, mm, r, ea, w);
 }
 
 
@@ -1092,6 +1192,7 @@ MN_HD MN_INLINE void console_reset(Ctx& c, uint32_t rnd) {
   {   // reset vector (a hot-spot free cartridge read)
     Cpu r;
     cpu_load(s, r);
+    r.fifo_n = c.fifo_n;
     const Mem mm = mem_of(c);
     const uint32_t lo = rd<false>(c, mm, r, 0xFFFC);
     s.PC = uint16_t(lo | (rd<false>(c, mm, r, 0xFFFD) << 8));
@@ -1179,7 +1280,7 @@ MN_HD MN_NOINLINE void unit_job_begin(Ctx& c, Unit& u) {
   }
 }
 MN_HD MN_INLINE void hot_init(const Unit& u, Hot& h) {
-  h.in_frame = false; h.more = u.idx < u.total; h.budget = 0; h.cpu.stop = false; h.instr = 0;
+  h.in_frame = false; h.more = u.idx < u.total; h.budget = 0; h.cpu.stop = false; h.cpu.fifo_n = 0; h.instr = 0;
   h.def_lo = h.def_hi = h.dep_lo = h.dep_hi = 0; h.tainted = false; h.obs_bad = false;
 }
 MN_HD MN_INLINE bool hot_has_work(const Hot& h) { return h.in_frame || h.more; }
@@ -1187,7 +1288,9 @@ MN_HD MN_INLINE bool hot_has_work(const Hot& h) { return h.in_frame || h.more; }
 template <bool TRACK>
 MN_HD MN_INLINE void unit_tick(Ctx& c, const Mem& mm, Unit& u, Hot& h) {
   if (!h.in_frame) {
+    c.fifo_n = h.cpu.fifo_n;
     unit_job_begin(c, u);
+    h.cpu.fifo_n = c.fifo_n;
     h.in_frame = u.in_frame; h.more = u.idx < u.total;
     if (h.in_frame) {
       cpu_load(*c.s, h.cpu); h.cpu.stop = false; h.budget = 25000;
@@ -1209,10 +1312,13 @@ MN_HD MN_INLINE void unit_tick(Ctx& c, const Mem& mm, Unit& u, Hot& h) {
   }
 }
 
+// the flat loop's drain: every queued write of this env goes through the picture
+MN_HD MN_INLINE void hot_drain(Ctx& c, Hot& h) { c.fifo_n = h.cpu.fifo_n; tia_drain(c); h.cpu.fifo_n = 0; }
+
 // after the unit's last tick: flush the picture and report whether the pixel-less frames were harmless
-MN_HD MN_INLINE bool unit_finish(Ctx& c) {
+MN_HD MN_INLINE bool unit_finish(Ctx& c, Hot& h) {
   EnvState& s = *c.s;
-  tia_drain(c);
+  hot_drain(c, h);
   picture_close_frame(s);
   const bool bad = (s.flags & F_ANOMALY) || s.pend_len[0] != 0 || s.pend_len[1] != 0;
   s.flags &= ~F_ANOMALY;

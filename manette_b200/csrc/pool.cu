@@ -32,7 +32,7 @@
 namespace mn {
 
 #define MN_MAX_GAMES 16
-#define MN_WARPS_PER_BLOCK 8
+#define MN_WARPS_PER_BLOCK 4
 #define MN_THREADS (MN_WARPS_PER_BLOCK * 32)
 #define MN_CORE_WORDS 43   // EnvState (42 words) padded to an odd stride: conflict-free across slots
 #define MN_PLANE (MN_IMG * MN_IMG)
@@ -288,10 +288,10 @@ __global__ void __launch_bounds__(MN_THREADS, 2) k_round(PoolDev p, int mode, in
       const bool work = hot_has_work(hot);
       if (!__any_sync(wmask, work)) break;
       if (work) unit_tick<TRACK>(c, mm, u, hot);
-      if (__any_sync(wmask, c.fifo_n >= MN_FIFO_HIGH)) tia_drain(c);
+      if (__any_sync(wmask, hot.cpu.fifo_n >= MN_FIFO_HIGH)) hot_drain(c, hot);
     }
     if (mine) {
-      bad = unit_finish(c); res = u; atomicAdd(p.total_instr, (unsigned long long)hot.instr);
+      bad = unit_finish(c, hot); res = u; atomicAdd(p.total_instr, (unsigned long long)hot.instr);
       // an env whose game ended inside this macro step is reset before anyone can look at its frames
       if (mode == ROUND_FIGAR && (s->flags & F_TERMINAL)) bad = false;
       if (TRACK) {

@@ -33,9 +33,9 @@ static void run_unit(HostEnv* e, int kind, int action, int count, uint32_t seed,
     const Mem mm = mem_of(e->c);
     while (hot_has_work(hot)) {
       unit_tick<true>(e->c, mm, u, hot);
-      if (e->c.fifo_n >= e->drain_at) tia_drain(e->c);
+      if (hot.cpu.fifo_n >= e->drain_at) hot_drain(e->c, hot);
     }
-    const bool bad = unit_finish(e->c);
+    const bool bad = unit_finish(e->c, hot);
     e->last = u;
     e->last_tainted = hot.tainted; e->last_alldef64 = !hot.obs_bad; e->dep_lo = hot.dep_lo; e->dep_hi = hot.dep_hi;
     if (!bad) break;
@@ -108,11 +108,13 @@ void he_console_step(void* h, int n_instr) {
   HostEnv* e = (HostEnv*)h;
   Cpu r;
   cpu_load(e->s, r);
+  r.fifo_n = e->c.fifo_n;
   const Mem mm = mem_of(e->c);
   for (int i = 0; i < n_instr; ++i) {
     cpu_step<false>(e->c, mm, r);
-    if (e->c.fifo_n >= e->drain_at) tia_drain(e->c);
+    if (r.fifo_n >= e->drain_at) { e->c.fifo_n = r.fifo_n; tia_drain(e->c); r.fifo_n = 0; }
   }
+  e->c.fifo_n = r.fifo_n;
   tia_drain(e->c);
   cpu_store(e->s, r);
 }
