@@ -1217,6 +1217,7 @@ struct Unit {
 // the part of a running unit the flat loop keeps in registers
 struct Hot {
   Cpu cpu; int budget; bool in_frame, more;
+  int jobs;                       // jobs begun so far (lane time = job, CPU cycle within its frame)
   uint32_t instr;                 // 6502 instructions executed
   uint64_t def_lo, def_hi, dep_lo, dep_hi;   // RAM-dependence probe, carried from frame to frame (see Cpu)
   bool tainted, obs_bad;          // obs_bad: the RAM scrape looked at a byte the program had not written yet
@@ -1280,10 +1281,14 @@ MN_HD MN_NOINLINE void unit_job_begin(Ctx& c, Unit& u) {
   }
 }
 MN_HD MN_INLINE void hot_init(const Unit& u, Hot& h) {
-  h.in_frame = false; h.more = u.idx < u.total; h.budget = 0; h.cpu.stop = false; h.cpu.fifo_n = 0; h.instr = 0;
+  h.in_frame = false; h.more = u.idx < u.total; h.budget = 0; h.cpu.stop = false; h.cpu.fifo_n = 0; h.instr = 0; h.jobs = 0;
   h.def_lo = h.def_hi = h.dep_lo = h.dep_hi = 0; h.tainted = false; h.obs_bad = false;
 }
 MN_HD MN_INLINE bool hot_has_work(const Hot& h) { return h.in_frame || h.more; }
+// Emulated time of a lane, comparable across the lanes of a warp: (job, CPU cycle since the frame of that job began).
+// The flat loop only advances the lanes that are not ahead of the slowest one by more than a few cycles: programs
+// are scan-line structured (WSYNC), so lanes kept together in time mostly sit at the same program counter.
+MN_HD MN_INLINE int32_t hot_time(const Hot& h) { return h.in_frame ? ((h.jobs << 16) + h.cpu.cycles) : ((h.jobs + 1) << 16); }
 // one tick: start the next job, or run one instruction of the frame in progress
 template <bool TRACK>
 MN_HD MN_INLINE void unit_tick(Ctx& c, const Mem& mm, Unit& u, Hot& h) {
@@ -1291,6 +1296,7 @@ MN_HD MN_INLINE void unit_tick(Ctx& c, const Mem& mm, Unit& u, Hot& h) {
     c.fifo_n = h.cpu.fifo_n;
     unit_job_begin(c, u);
     h.cpu.fifo_n = c.fifo_n;
+    h.jobs++;
     h.in_frame = u.in_frame; h.more = u.idx < u.total;
     if (h.in_frame) {
       cpu_load(*c.s, h.cpu); h.cpu.stop = false; h.budget = 25000;

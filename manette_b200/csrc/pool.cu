@@ -85,6 +85,7 @@ struct PoolDev {             // kernel argument block (by value)
   GameDev games[MN_MAX_GAMES];
   int32_t n_games, n_envs, slots /* env slots per warp */, depth, num_actions, nb_choices;
   int32_t single_life, random_start, seed, env_id_offset, draw_all_frames;
+  int32_t sync_slack;        // lanes of a warp stay within this many CPU cycles of the slowest one (see hot_time)
   int32_t tab_rep[32];
   const uint8_t* roms;
   EnvState* env;
@@ -286,8 +287,10 @@ __global__ void __launch_bounds__(MN_THREADS, 2) k_round(PoolDev p, int mode, in
     const Mem mm = mem_of(c);
     for (;;) {
       const bool work = hot_has_work(hot);
-      if (!__any_sync(wmask, work)) break;
-      if (work) unit_tick<TRACK>(c, mm, u, hot);
+      const int now = work ? hot_time(hot) : 0x7FFFFFFF;
+      const int first = __reduce_min_sync(wmask, now);
+      if (first == 0x7FFFFFFF) break;
+      if (work && now - first <= p.sync_slack) unit_tick<TRACK>(c, mm, u, hot);
       if (__any_sync(wmask, hot.cpu.fifo_n >= MN_FIFO_HIGH)) hot_drain(c, hot);
     }
     if (mine) {
@@ -810,6 +813,8 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
   d.nb_choices = cfg->nb_choices > 0 ? cfg->nb_choices : 1;
   d.single_life = cfg->single_life_episodes; d.random_start = cfg->random_start; d.seed = cfg->random_seed; d.env_id_offset = cfg->env_id_offset;
   d.draw_all_frames = cfg->draw_all_frames;
+  d.sync_slack = 12;
+  if (const char* ev = getenv("MN_SYNC_SLACK")) d.sync_slack = atoi(ev) < 0 ? 0x3FFFFFFF : atoi(ev);
   h->max_rep = 0;
   for (int i = 0; i < cfg->nb_choices; ++i) {
     if (cfg->tab_rep[i] < 0 || cfg->tab_rep[i] > 1000) { delete h; return fail("mn_create: tab_rep entries must be 0..1000"); }
