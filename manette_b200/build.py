@@ -6,9 +6,9 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libmanette_b200.so")
 SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("pool.cu",)]
-HEADERS = [os.path.join(_PKG, "csrc", f) for f in ("emu_core.cuh", "atari_env.cuh", "decode_tables.h", "game_db.h")] + \
+HEADERS = [os.path.join(_PKG, "csrc", f) for f in ("emu_core.cuh", "cpu_defs.h", "atari_env.cuh", "decode_tables.h", "game_db.h")] + \
           [os.path.join(os.path.dirname(_PKG), "include", "manette_b200.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
               "-Xcompiler", "-fPIC", "-shared"]
 
 

@@ -25,18 +25,8 @@
 // The product never runs the host build.
 #pragma once
 #include <stdint.h>
+#include "cpu_defs.h"
 
-#ifdef __CUDACC__
-#define MN_HD __host__ __device__
-#define MN_NOINLINE __noinline__
-#define MN_NOINLINE_DEV __forceinline__
-#define MN_INLINE __forceinline__
-#else
-#define MN_HD
-#define MN_NOINLINE
-#define MN_NOINLINE_DEV inline
-#define MN_INLINE inline
-#endif
 
 namespace mn {
 
@@ -73,37 +63,6 @@ enum : uint32_t {
   F_TIMER_IRQ_READ = 1u << 21, F_TERMINAL = 1u << 22, F_STARTED = 1u << 23,
   F_PIXELS = 1u << 24 /* picture side: the frame being drawn keeps its pixels */,
   F_ANOMALY = 1u << 25 /* picture side: a pixel-less frame would have been visible -> re-run with pixels */ };
-
-// addressing modes / operation classes of the packed decode descriptor
-enum { AM_IMP = 0, AM_ACC, AM_IMM, AM_ZP, AM_ZPX, AM_ZPY, AM_ABS, AM_ABX, AM_ABY, AM_IZX, AM_IZY, AM_REL, AM_IND };
-enum { OC_NONE = 0, OC_READ = 1, OC_WRITE = 2, OC_RMW = 3 };   // what the operate phase needs from memory
-enum {  // operations
-  O_NOP = 0, O_ORA, O_AND, O_EOR, O_ADC, O_SBC, O_CMP, O_CPX, O_CPY, O_BIT, O_LDA, O_LDX, O_LDY, O_LAX, O_LXA, O_ANC,
-  O_ALR, O_ARR, O_XAA, O_AXS, O_LAS,                                   // read class
-  O_STA, O_STX, O_STY, O_SAX, O_AHX, O_SHY, O_SHX, O_TAS,              // write class
-  O_ASL, O_LSR, O_ROL, O_ROR, O_INC, O_DEC, O_SLO, O_RLA, O_SRE, O_RRA, O_DCP, O_ISC,   // rmw class
-  O_BRANCH, O_JMP, O_JSR, O_RTS, O_RTI, O_BRK, O_PHA, O_PHP, O_PLA, O_PLP,
-  O_TAX, O_TAY, O_TXA, O_TYA, O_TSX, O_TXS, O_INX, O_INY, O_DEX, O_DEY, O_FLAG, O_KIL };
-// descriptor: [3:0] mode  [5:4] class  [11:6] op  [15:12] base cycles (2..8)
-// branches keep their condition in the aux byte of the table entry; flag ops likewise.
-#define MN_DESC(mode, cls, op, cyc) uint32_t((mode) | ((cls) << 4) | ((op) << 6) | ((cyc) << 12))
-
-// One 16-byte entry per opcode, read with a single shared-memory load:
-//   k  control word of the table-driven datapath (K_* fields, see cpu_step)
-//   d  [15:0] descriptor (MN_DESC, cycles in 4 bits)  [23:16] aux (branch: [7:6]=flag selector 0 N,1 V,2 C,3 Z,
-//      [0]=wanted value ; flag op: [7:1]=bit index in P, [0]=set)  [31:24] D_* phase flags
-//   x  operand mask: 0xFF for the zero-page forms, 0xFFFF for the absolute ones (0 when there is no operand address)
-struct alignas(16) TabEnt { uint32_t k, d, x, pad; };
-enum : uint32_t {
-  D_EA = 1u << 24       /* has an effective address (mode >= zp, not relative) */,
-  D_INDIRECT = 1u << 25 /* (zp,X) (zp),Y (abs) */,
-  D_READ = 1u << 26     /* read phase: read / read-modify-write class with an effective address */,
-  D_WRITE = 1u << 27    /* write phase: write class, or read-modify-write on memory */,
-  D_PAGEPEN = 1u << 28  /* read class, indexed: +1 cycle when the index crosses a page */,
-  D_BRANCH = 1u << 29 };
-struct Tables {          // read-only, staged in shared memory by the kernels
-  TabEnt e[256];
-};
 
 // ------------------------------------------------------------------ per-environment record
 struct EnvState {
@@ -248,6 +207,17 @@ MN_HD MN_INLINE uint32_t perm4(uint32_t x, uint32_t sel) {   // byte i of the re
 #else
   uint32_t r = 0;
   for (int i = 0; i < 4; ++i) r |= ((x >> (8 * ((sel >> (4 * i)) & 3))) & 0xFFu) << (8 * i);
+  return r;
+#endif
+}
+// byte i of the result = byte sel[4i+2:4i] of the 8 bytes {x (0..3), y (4..7)}
+MN_HD MN_INLINE uint32_t perm8(uint32_t x, uint32_t y, uint32_t sel) {
+#ifdef __CUDA_ARCH__
+  return __byte_perm(x, y, sel);
+#else
+  const uint64_t v = uint64_t(x) | (uint64_t(y) << 32);
+  uint32_t r = 0;
+  for (int i = 0; i < 4; ++i) r |= uint32_t((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xFFu) << (8 * i);
   return r;
 #endif
 }
@@ -693,9 +663,9 @@ MN_HD MN_INLINE void m32w(maddr a, uint32_t v) {
 MN_HD MN_INLINE TabEnt tab_entry(maddr tab, uint32_t ir) {
 #if defined(__CUDA_ARCH__)
   const uint4 q = *reinterpret_cast<const uint4*>(mn_smem + tab + ir * 16u);
-  TabEnt t; t.k = q.x; t.d = q.y; t.x = q.z; t.pad = q.w; return t;
+  TabEnt t; t.k = q.x; t.d = q.y; t.x = q.z; t.dm = q.w; return t;
 #elif defined(__CUDACC__)
-  (void)tab; (void)ir; TabEnt t; t.k = t.d = t.x = t.pad = 0u; return t;
+  (void)tab; (void)ir; TabEnt t; t.k = t.d = t.x = t.dm = 0u; return t;
 #else
   return reinterpret_cast<const TabEnt*>(tab)[ir];
 #endif
@@ -712,7 +682,8 @@ MN_HD MN_INLINE maddr maddr_of(const void* p) {
 
 // The 6502 and what it needs on every instruction, register resident while a frame runs.
 struct Cpu {
-  uint32_t A, X, Y, SP, PC;
+  uint32_t axys;     // A | X << 8 | Y << 16 | SP << 24: one byte permute picks any of them as an ALU operand
+  uint32_t PC;
   uint32_t P;        // C(0x01) I(0x04) D(0x08) B(0x10) V(0x40); N/Z live in nz
   uint32_t nz;       // Z <=> (nz & 0xFF) == 0 ; N <=> nz & 0x180
   uint32_t dbus;     // last value on the data bus (the undriven bits of TIA reads)
@@ -733,6 +704,13 @@ MN_HD MN_INLINE Mem mem_of(const Ctx& c) {
   Mem m; m.rom = maddr_of(c.rom); m.ram = maddr_of(c.ram); m.tab = maddr_of(c.tab); m.fifo = maddr_of(c.fifo);
   m.ram_stride = uint32_t(c.ram_stride); return m;
 }
+MN_HD MN_INLINE uint32_t cpuA(const Cpu& r) { return r.axys & 0xFFu; }
+MN_HD MN_INLINE uint32_t cpuX(const Cpu& r) { return (r.axys >> 8) & 0xFFu; }
+MN_HD MN_INLINE uint32_t cpuY(const Cpu& r) { return (r.axys >> 16) & 0xFFu; }
+MN_HD MN_INLINE uint32_t cpuSP(const Cpu& r) { return r.axys >> 24; }
+MN_HD MN_INLINE void setA(Cpu& r, uint32_t v) { r.axys = (r.axys & 0xFFFFFF00u) | (v & 0xFFu); }
+MN_HD MN_INLINE void setX(Cpu& r, uint32_t v) { r.axys = (r.axys & 0xFFFF00FFu) | ((v & 0xFFu) << 8); }
+MN_HD MN_INLINE void setSP(Cpu& r, uint32_t v) { r.axys = (r.axys & 0x00FFFFFFu) | (v << 24); }
 MN_HD MN_INLINE uint32_t make_segmap(const EnvState& s) {
   if (s.cart == CART_2K) return 0x01000100u;
   if (s.cart == CART_4K) return 0x03020100u;
@@ -742,13 +720,13 @@ MN_HD MN_INLINE uint32_t make_segmap(const EnvState& s) {
 }
 // does not touch fifo_n: that one is carried by the flat loop across frames
 MN_HD MN_INLINE void cpu_load(const EnvState& s, Cpu& r) {
-  r.A = s.A; r.X = s.X; r.Y = s.Y; r.SP = s.SP; r.PC = s.PC; r.P = s.P; r.nz = s.nz; r.dbus = s.dbus;
+  r.axys = uint32_t(s.A) | (uint32_t(s.X) << 8) | (uint32_t(s.Y) << 16) | (uint32_t(s.SP) << 24); r.PC = s.PC; r.P = s.P; r.nz = s.nz; r.dbus = s.dbus;
   r.cycles = s.cycles; r.clk0 = s.clk_frame_start; r.segmap = make_segmap(s); r.hot_lo = (s.cart > CART_4K) ? 0xFE0u : 0x1000u;
   r.stop = (s.flags & F_STOP) != 0;
   r.def_lo = r.def_hi = r.dep_lo = r.dep_hi = 0; r.tainted = false;
 }
 MN_HD MN_INLINE void cpu_store(EnvState& s, const Cpu& r) {
-  s.A = uint8_t(r.A); s.X = uint8_t(r.X); s.Y = uint8_t(r.Y); s.SP = uint8_t(r.SP); s.PC = uint16_t(r.PC);
+  s.A = uint8_t(r.axys); s.X = uint8_t(r.axys >> 8); s.Y = uint8_t(r.axys >> 16); s.SP = uint8_t(r.axys >> 24); s.PC = uint16_t(r.PC);
   s.P = uint8_t(r.P); s.nz = uint16_t(r.nz); s.dbus = uint8_t(r.dbus); s.cycles = r.cycles;
 }
 
@@ -829,28 +807,28 @@ MN_HD MN_INLINE void unpack_ps(EnvState& s, uint32_t p) {
 }
 MN_HD MN_INLINE uint32_t bcd_bin(uint32_t v) { return (v >> 4) * 10 + (v & 15); }
 MN_HD MN_INLINE void op_adc(Cpu& r, uint32_t m) {
-  const uint32_t a = r.A, cin = r.P & 1;
+  const uint32_t a = cpuA(r), cin = r.P & 1;
   if (!(r.P & 0x08)) {
     const uint32_t sum = a + m + cin;
     const bool v = ((~(a ^ m)) & (a ^ sum) & 0x80) != 0;
-    r.A = sum & 0xFF; r.nz = r.A;
+    setA(r, sum); r.nz = sum & 0xFF;
     r.P = (r.P & ~0x41u) | (sum > 0xFF ? 1u : 0u) | (v ? 0x40u : 0u);
   } else {
     const uint32_t sum = bcd_bin(a) + bcd_bin(m) + cin;
     const uint32_t low = sum & 0xFF;
     const uint32_t res = (((low % 100) / 10) << 4) | (low % 10);
     const bool v = ((a ^ res) & 0x80) && ((res ^ m) & 0x80);
-    r.A = res & 0xFF; r.nz = r.A;
+    setA(r, res); r.nz = res & 0xFF;
     r.P = (r.P & ~0x41u) | (sum > 99 ? 1u : 0u) | (v ? 0x40u : 0u);
   }
 }
 MN_HD MN_INLINE void op_sbc(Cpu& r, uint32_t m) {
-  const uint32_t a = r.A, cin = r.P & 1;
+  const uint32_t a = cpuA(r), cin = r.P & 1;
   if (!(r.P & 0x08)) {
     const uint32_t nm = (~m) & 0xFF;
     const uint32_t sum = a + nm + cin;
     const bool v = ((~(a ^ nm)) & (a ^ sum) & 0x80) != 0;
-    r.A = sum & 0xFF; r.nz = r.A;
+    setA(r, sum); r.nz = sum & 0xFF;
     r.P = (r.P & ~0x41u) | (sum > 0xFF ? 1u : 0u) | (v ? 0x40u : 0u);
   } else {
     int32_t diff = int32_t(bcd_bin(a)) - int32_t(bcd_bin(m)) - int32_t(1 - cin);
@@ -860,7 +838,7 @@ MN_HD MN_INLINE void op_sbc(Cpu& r, uint32_t m) {
     const uint32_t res = uint32_t((((diff % 100) / 10) << 4) | (diff % 10)) & 0xFFu;
     const bool carry = a >= (m + (1 - cin));
     const bool v = ((a ^ res) & 0x80) && ((res ^ m) & 0x80);
-    r.A = res & 0xFF; r.nz = r.A;
+    setA(r, res); r.nz = res & 0xFF;
     r.P = (r.P & ~0x41u) | (carry ? 1u : 0u) | (v ? 0x40u : 0u);
   }
 }
@@ -870,9 +848,9 @@ MN_HD MN_INLINE void op_cmp(Cpu& r, uint32_t reg, uint32_t m) {
   r.P = (r.P & ~1u) | ((d & 0x100) ? 0u : 1u);
 }
 template <bool TRACK>
-MN_HD MN_INLINE void stk_push(Ctx& c, const Mem& mm, Cpu& r, uint32_t v) { wr<TRACK>(c, mm, r, 0x0100u | r.SP, v); r.SP = (r.SP - 1) & 0xFFu; }
+MN_HD MN_INLINE void stk_push(Ctx& c, const Mem& mm, Cpu& r, uint32_t v) { wr<TRACK>(c, mm, r, 0x0100u | cpuSP(r), v); r.axys -= 0x01000000u; }
 template <bool TRACK>
-MN_HD MN_INLINE uint32_t stk_pull(Ctx& c, const Mem& mm, Cpu& r) { r.SP = (r.SP + 1) & 0xFFu; return rd<TRACK>(c, mm, r, 0x0100u | r.SP); }
+MN_HD MN_INLINE uint32_t stk_pull(Ctx& c, const Mem& mm, Cpu& r) { r.axys += 0x01000000u; return rd<TRACK>(c, mm, r, 0x0100u | cpuSP(r)); }
 
 // The opcodes outside the table-driven datapath (stack / flow / flag ops, BIT, decimal ADC/SBC, undocumented).
 // Returns the value of the write phase for the write / read-modify-write classes.
@@ -882,28 +860,29 @@ MN_HD MN_NOINLINE_DEV uint32_t cpu_special(Ctx& c, const Mem& mm, Cpu& r, uint32
   switch (op) {
     case O_ADC: op_adc(r, m); break;
     case O_SBC: op_sbc(r, m); break;
-    case O_BIT: r.nz = ((m & 0x80) << 1) | ((r.A & m) ? 1u : 0u); r.P = (r.P & ~0x40u) | (m & 0x40); break;
-    case O_LXA: r.A = r.X = (r.A | 0xEE) & m; r.nz = r.A; break;
-    case O_ANC: r.A &= m; r.nz = r.A; r.P = (r.P & ~1u) | (r.A >> 7); break;
-    case O_ALR: r.A &= m; r.P = (r.P & ~1u) | (r.A & 1); r.A >>= 1; r.nz = r.A; break;
+    case O_BIT: r.nz = ((m & 0x80) << 1) | ((cpuA(r) & m) ? 1u : 0u); r.P = (r.P & ~0x40u) | (m & 0x40); break;
+    case O_LXA: { const uint32_t v = (cpuA(r) | 0xEE) & m; setA(r, v); setX(r, v); r.nz = v; break; }
+    case O_ANC: { const uint32_t v = cpuA(r) & m; setA(r, v); r.nz = v; r.P = (r.P & ~1u) | (v >> 7); break; }
+    case O_ALR: { uint32_t v = cpuA(r) & m; r.P = (r.P & ~1u) | (v & 1); v >>= 1; setA(r, v); r.nz = v; break; }
     case O_ARR: {
-      uint32_t a = r.A & m; a = ((a >> 1) & 0x7F) | ((r.P & 1) << 7);
-      r.A = a; r.nz = a;
+      uint32_t a = cpuA(r) & m; a = ((a >> 1) & 0x7F) | ((r.P & 1) << 7);
+      setA(r, a); r.nz = a;
       r.P = (r.P & ~0x41u) | ((a >> 6) & 1) | ((((a >> 6) ^ (a >> 5)) & 1) ? 0x40u : 0u);
       break;
     }
-    case O_XAA: r.A = r.X & m; r.nz = r.A; break;
-    case O_AXS: { const uint32_t dd = ((r.X & r.A) - m) & 0x1FF; r.X = dd & 0xFF; r.nz = r.X; r.P = (r.P & ~1u) | ((dd & 0x100) ? 0u : 1u); break; }
-    case O_LAS: r.A = r.X = r.SP = m & r.SP; r.nz = r.A; break;
-    case O_AHX: w = r.A & r.X & (((ea >> 8) + 1) & 0xFF); break;
-    case O_SHY: w = r.Y & (((ea >> 8) + 1) & 0xFF); break;
-    case O_SHX: w = r.X & (((ea >> 8) + 1) & 0xFF); break;
-    case O_TAS: r.SP = r.A & r.X; w = r.SP & (((ea >> 8) + 1) & 0xFF); break;
-    case O_SLO: r.P = (r.P & ~1u) | (m >> 7); w = (m << 1) & 0xFF; r.A |= w; r.nz = r.A; break;
-    case O_SRE: r.P = (r.P & ~1u) | (m & 1); w = m >> 1; r.A ^= w; r.nz = r.A; break;
-    case O_RLA: { const uint32_t cin = r.P & 1; r.P = (r.P & ~1u) | (m >> 7); w = ((m << 1) | cin) & 0xFF; r.A &= w; r.nz = r.A; break; }
+    case O_XAA: { const uint32_t v = cpuX(r) & m; setA(r, v); r.nz = v; break; }
+    case O_AXS: { const uint32_t dd = ((cpuX(r) & cpuA(r)) - m) & 0x1FF; setX(r, dd); r.nz = dd & 0xFF; r.P = (r.P & ~1u) | ((dd & 0x100) ? 0u : 1u); break; }
+    case O_LAS: { const uint32_t v = m & cpuSP(r); setA(r, v); setX(r, v); setSP(r, v); r.nz = v; break; }
+    case O_SAX: w = cpuA(r) & cpuX(r); break;
+    case O_AHX: w = cpuA(r) & cpuX(r) & (((ea >> 8) + 1) & 0xFF); break;
+    case O_SHY: w = cpuY(r) & (((ea >> 8) + 1) & 0xFF); break;
+    case O_SHX: w = cpuX(r) & (((ea >> 8) + 1) & 0xFF); break;
+    case O_TAS: { const uint32_t v = cpuA(r) & cpuX(r); setSP(r, v); w = v & (((ea >> 8) + 1) & 0xFF); break; }
+    case O_SLO: r.P = (r.P & ~1u) | (m >> 7); w = (m << 1) & 0xFF; { const uint32_t v = cpuA(r) | w; setA(r, v); r.nz = v; } break;
+    case O_SRE: r.P = (r.P & ~1u) | (m & 1); w = m >> 1; { const uint32_t v = cpuA(r) ^ w; setA(r, v); r.nz = v; } break;
+    case O_RLA: { const uint32_t cin = r.P & 1; r.P = (r.P & ~1u) | (m >> 7); w = ((m << 1) | cin) & 0xFF; const uint32_t v = cpuA(r) & w; setA(r, v); r.nz = v; break; }
     case O_RRA: { const uint32_t cin = r.P & 1; r.P = (r.P & ~1u) | (m & 1); w = (m >> 1) | (cin << 7); op_adc(r, w); break; }
-    case O_DCP: w = (m - 1) & 0xFF; op_cmp(r, r.A, w); break;
+    case O_DCP: w = (m - 1) & 0xFF; op_cmp(r, cpuA(r), w); break;
     case O_ISC: w = (m + 1) & 0xFF; op_sbc(r, w); break;
     case O_JMP: r.PC = ea; break;
     case O_JSR: { const uint32_t ret = (r.PC - 1) & 0xFFFF; stk_push<TRACK>(c, mm, r, ret >> 8); stk_push<TRACK>(c, mm, r, ret & 0xFF); r.PC = ea; break; }
@@ -916,9 +895,9 @@ MN_HD MN_NOINLINE_DEV uint32_t cpu_special(Ctx& c, const Mem& mm, Cpu& r, uint32
       const uint32_t lo = rd<TRACK>(c, mm, r, 0xFFFE); r.PC = lo | (rd<TRACK>(c, mm, r, 0xFFFF) << 8);
       break;
     }
-    case O_PHA: stk_push<TRACK>(c, mm, r, r.A); break;
+    case O_PHA: stk_push<TRACK>(c, mm, r, cpuA(r)); break;
     case O_PHP: stk_push<TRACK>(c, mm, r, pack_ps(r.P, r.nz) | 0x10); break;
-    case O_PLA: r.A = stk_pull<TRACK>(c, mm, r); r.nz = r.A; break;
+    case O_PLA: { const uint32_t v = stk_pull<TRACK>(c, mm, r); setA(r, v); r.nz = v; break; }
     case O_PLP: unpack_ps(r, stk_pull<TRACK>(c, mm, r)); break;
     case O_FLAG: { const uint32_t mask = 1u << (ax >> 1); r.P = (ax & 1) ? (r.P | mask) : (r.P & ~mask); break; }
     default: break;   // O_KIL, O_NOP
@@ -926,14 +905,81 @@ MN_HD MN_NOINLINE_DEV uint32_t cpu_special(Ctx& c, const Mem& mm, Cpu& r, uint32
   return w;
 }
 
-// control word of the table-driven datapath (Tables::ctl), see decode_tables.h
-enum : uint32_t {
-  K_ASEL = 0, K_BSEL = 3, K_BINV = 1u << 5, K_CSEL = 6, K_FN = 8, K_NZ = 1u << 11, K_C = 1u << 12, K_V = 1u << 13,
-  K_DA = 1u << 14, K_DX = 1u << 15, K_DY = 1u << 16, K_DSP = 1u << 17, K_GENERIC = 1u << 18, K_DECIMAL = 1u << 19,
-  K_ISEL = 20, K_LEN = 22 };
-enum { FN_ADD = 0, FN_OR, FN_AND, FN_EOR, FN_ASL, FN_LSR, FN_ROL, FN_ROR };
-enum { AS_A = 0, AS_X, AS_Y, AS_SP, AS_M, AS_AX, AS_ZERO };
-enum { BS_M = 0, BS_ONE, BS_FF, BS_ZERO };
+// Everything of one instruction after the opcode fetch, for a decode entry: the table-driven datapath.  Every
+// opcode runs the same instruction sequence, and inside it nothing is chosen by a branch: operands, function and
+// carry source are byte-permute selections, results are committed through masks (cpu_defs.h).
+template <bool TRACK>
+MN_HD MN_INLINE void cpu_exec(Ctx& c, const Mem& mm, Cpu& r, const uint32_t pc, const uint32_t ir, uint32_t b1, uint32_t b2,
+                              const bool fast_code, const TabEnt t) {
+  const uint32_t k = t.k, d = t.d;
+  const uint32_t len1 = (k >> K_LEN) & 3u;   // length - 1
+  // the whole base cycle count is charged right after the opcode fetch (operand fetches from the RIOT see it)
+  r.cycles += int32_t((d >> 12) & 15u);
+  if (!fast_code) { if (len1 >= 1) b1 = rd<TRACK>(c, mm, r, (pc + 1) & 0xFFFFu); if (len1 == 2) b2 = rd<TRACK>(c, mm, r, (pc + 2) & 0xFFFFu); }
+  else r.dbus = byte_of(ir | (b1 << 8) | (b2 << 16), len1);
+  r.PC = (pc + len1 + 1u) & 0xFFFFu;
+  // ---- address phase: zero-page / absolute, optionally indexed, from the operand mask of the entry
+  const uint32_t xm = t.x & 0xFFFFu;
+  const uint32_t idx = perm8(r.axys, 0u, ((k >> K_ISEL) & 7u) | 0x7770u);
+  uint32_t base = (b1 | (b2 << 8)) & xm;
+  uint32_t ea = (base + idx) & xm;
+  if (d & D_INDIRECT) {   // (zp,X)  (zp),Y  (abs)
+    const uint32_t mode = d & 15u;
+    uint32_t p0, p1;
+    if (mode == AM_IND) { p0 = b1 | (b2 << 8); p1 = ((p0 & 0xFF) == 0xFF) ? (p0 & 0xFF00u) : ((p0 + 1) & 0xFFFFu); }
+    else { p0 = (mode == AM_IZX) ? ((b1 + cpuX(r)) & 0xFFu) : b1; p1 = (p0 + 1) & 0xFFu; }
+    const uint32_t lo = rd<TRACK>(c, mm, r, p0);
+    base = lo | (rd<TRACK>(c, mm, r, p1) << 8);
+    ea = (mode == AM_IZY) ? ((base + cpuY(r)) & 0xFFFFu) : base;
+  }
+  if ((d & D_PAGEPEN) && ((base ^ ea) & 0xFF00u)) r.cycles += 1;
+  // ---- read phase
+  uint32_t m = b1;
+  if (d & D_READ) m = rd<TRACK>(c, mm, r, ea);
+  // ---- operate phase.  The datapath runs for every opcode; what it may change is in the masks of the entry, which
+  // are all zero for the opcodes it cannot express (and are ignored for ADC / SBC in decimal mode).
+  const bool generic = (k & K_GENERIC) && !((k & K_DECIMAL) && (r.P & 0x08u));
+  uint32_t w;
+  {
+    const uint32_t live = generic ? 0xFFFFFFFFu : 0u;
+    const uint32_t s2 = m | 0x00FF0100u;                                   // bytes 4..7 of the operand pool: M, 1, 0xFF, 0
+    const uint32_t a = perm8(r.axys, s2, (k & 7u) | 0x7770u);
+    const uint32_t b = perm8(r.axys, s2, ((k >> K_BSEL) & 7u) | 0x7770u) ^ ((t.x >> 16) & 0xFFu);
+    const uint32_t carry = r.P & 1u;
+    const uint32_t cin = ((k >> K_CSEL) & 1u) | ((k >> (K_CSEL + 1)) & carry);
+    const uint32_t sum = a + b + cin;                                      // bit 8 = carry out
+    const uint32_t rot = (k >> 11) & carry;                                // K_ROT
+    const uint32_t left = (a << 1) | rot;                                  // bit 8 = carry out
+    const uint32_t right = ((a | (rot << 8)) >> 1) | ((a & 1u) << 8);      // bit 8 = carry out
+    const uint32_t lo_sum_or = perm8(sum, a | b, 0x7740u), lo_and_xor = perm8(a & b, a ^ b, 0x7740u);
+    const uint32_t fn_pool0 = perm8(lo_sum_or, lo_and_xor, 0x5410u);      // sum, or, and, xor
+    const uint32_t fn_pool1 = perm8(left, right, 0x7740u);                // left, right, 0, 0
+    const uint32_t res = perm8(fn_pool0, fn_pool1, ((k >> K_FN) & 7u) | 0x7770u);
+    const uint32_t c_pool = perm8(perm8(sum, left, 0x7751u), right, 0x7510u);   // carry out of sum, left, right
+    const uint32_t cout = perm8(c_pool, 0u, ((k >> K_CSRC) & 3u) | 0x4440u);
+    const uint32_t vbit = ((~(a ^ b)) & (a ^ sum) & 0x80u) >> 1;
+    const uint32_t pm = (t.x >> 24) & live;                                // bits of P to rewrite
+    r.P = (r.P & ~pm) | ((cout | vbit) & pm);
+    if (k & live & K_NZ) r.nz = res;
+    const uint32_t dm = t.dm & live;
+    r.axys = (r.axys & ~dm) | ((res * 0x01010101u) & dm);
+    w = res;
+  }
+  if (!generic) {
+    if (d & D_BRANCH) {
+      const uint32_t ax = (d >> 16) & 0xFFu;
+      // N V C Z as bits 0..3
+      const uint32_t fl = ((r.nz & 0x180u) ? 1u : 0u) | ((r.P >> 5) & 2u) | ((r.P & 1u) << 2) | ((r.nz & 0xFFu) ? 0u : 8u);
+      if (((fl >> (ax >> 6)) & 1u) == (ax & 1u)) {
+        const uint32_t target = (r.PC + uint32_t(int32_t(int8_t(b1)))) & 0xFFFFu;
+        r.cycles += ((r.PC ^ target) & 0xFF00u) ? 2 : 1;
+        r.PC = target;
+      }
+    } else w = cpu_special<TRACK>(c, mm, r, (d >> 16) & 0xFFu, (d >> 6) & 63u, m, ea);
+  }
+  // ---- write phase
+  if (d & D_WRITE) wr<TRACK>(c, mm, r, ea, w);
+}
 
 // one instruction
 template <bool TRACK>
@@ -945,74 +991,9 @@ MN_HD MN_INLINE void cpu_step(Ctx& c, const Mem& mm, Cpu& r) {
   uint32_t ir, b1 = 0, b2 = 0;
   if (fast_code) { const maddr a = rom_addr(mm, r.segmap, pc); ir = m8(a); b1 = m8(a + 1); b2 = m8(a + 2); }
   else ir = rd<TRACK>(c, mm, r, pc);
-  const TabEnt t = tab_entry(mm.tab, ir);
-  const uint32_t k = t.k, d = t.d;
-  const uint32_t len1 = (k >> K_LEN) & 3u;   // length - 1
-  // the whole base cycle count is charged right after the opcode fetch (operand fetches from the RIOT see it)
-  r.cycles += int32_t((d >> 12) & 15u);
-  if (!fast_code) { if (len1 >= 1) b1 = rd<TRACK>(c, mm, r, (pc + 1) & 0xFFFFu); if (len1 == 2) b2 = rd<TRACK>(c, mm, r, (pc + 2) & 0xFFFFu); }
-  else r.dbus = (len1 == 0) ? ir : (len1 == 1) ? b1 : b2;
-  r.PC = (pc + len1 + 1u) & 0xFFFFu;
-  // ---- address phase: zero-page / absolute, optionally indexed, from the operand mask of the entry
-  const uint32_t isel = (k >> K_ISEL) & 3u;
-  const uint32_t idx = (isel == 1) ? r.X : (isel == 2) ? r.Y : 0u;
-  uint32_t base = (b1 | (b2 << 8)) & t.x;
-  uint32_t ea = (base + idx) & t.x;
-  if (d & D_INDIRECT) {   // (zp,X)  (zp),Y  (abs)
-    const uint32_t mode = d & 15u;
-    uint32_t p0, p1;
-    if (mode == AM_IND) { p0 = b1 | (b2 << 8); p1 = ((p0 & 0xFF) == 0xFF) ? (p0 & 0xFF00u) : ((p0 + 1) & 0xFFFFu); }
-    else { p0 = (mode == AM_IZX) ? ((b1 + r.X) & 0xFFu) : b1; p1 = (p0 + 1) & 0xFFu; }
-    const uint32_t lo = rd<TRACK>(c, mm, r, p0);
-    base = lo | (rd<TRACK>(c, mm, r, p1) << 8);
-    ea = (mode == AM_IZY) ? ((base + r.Y) & 0xFFFFu) : base;
-  }
-  if ((d & D_PAGEPEN) && ((base ^ ea) & 0xFF00u)) r.cycles += 1;
-  // ---- read phase
-  uint32_t m = b1;
-  if (d & D_READ) m = rd<TRACK>(c, mm, r, ea);
-  // ---- operate phase.  The datapath runs for every opcode; what it may change is in the control word, which is
-  // all zero for the opcodes it cannot express (and is ignored for ADC / SBC in decimal mode).
-  const bool generic = (k & K_GENERIC) && !((k & K_DECIMAL) && (r.P & 0x08u));
-  const uint32_t kk = generic ? k : 0u;
-  uint32_t w;
-  {
-    const uint32_t asel = k & 7u, bsel = (k >> K_BSEL) & 3u, csel = (k >> K_CSEL) & 3u, fn = (k >> K_FN) & 7u;
-    const uint32_t a = (asel == AS_A) ? r.A : (asel == AS_X) ? r.X : (asel == AS_Y) ? r.Y : (asel == AS_SP) ? r.SP :
-                       (asel == AS_M) ? m : (asel == AS_AX) ? (r.A & r.X) : 0u;
-    uint32_t b = (bsel == BS_M) ? m : (bsel == BS_ONE) ? 1u : (bsel == BS_FF) ? 0xFFu : 0u;
-    if (k & K_BINV) b ^= 0xFFu;
-    const uint32_t carry = r.P & 1u;
-    const uint32_t cin = (csel == 2) ? carry : csel;
-    const uint32_t sum = a + b + cin;
-    const uint32_t rot = (fn >= FN_ROL) ? carry : 0u;
-    const uint32_t left = ((a << 1) | rot) & 0xFFu, right = (a >> 1) | (rot << 7);
-    const uint32_t res = (fn == FN_ADD) ? (sum & 0xFFu) : (fn == FN_OR) ? (a | b) : (fn == FN_AND) ? (a & b) :
-                         (fn == FN_EOR) ? (a ^ b) : (fn == FN_ASL || fn == FN_ROL) ? left : right;
-    const uint32_t cout = (fn == FN_ADD) ? (sum >> 8) : (fn == FN_ASL || fn == FN_ROL) ? (a >> 7) : (a & 1u);
-    if (kk & K_NZ) r.nz = res;
-    if (kk & K_C) r.P = (r.P & ~1u) | cout;
-    if (kk & K_V) r.P = (r.P & ~0x40u) | (((~(a ^ b)) & (a ^ sum) & 0x80u) >> 1);
-    if (kk & K_DA) r.A = res;
-    if (kk & K_DX) r.X = res;
-    if (kk & K_DY) r.Y = res;
-    if (kk & K_DSP) r.SP = res;
-    w = res;
-  }
-  if (!generic) {
-    if (d & D_BRANCH) {
-      const uint32_t ax = (d >> 16) & 0xFFu;
-      const uint32_t sel = ax >> 6;
-      const bool flag = (sel == 0) ? ((r.nz & 0x180u) != 0) : (sel == 1) ? ((r.P & 0x40u) != 0) : (sel == 2) ? ((r.P & 1u) != 0) : ((r.nz & 0xFFu) == 0);
-      if (flag == ((ax & 1u) != 0)) {
-        const uint32_t target = (r.PC + uint32_t(int32_t(int8_t(b1)))) & 0xFFFFu;
-        r.cycles += ((r.PC ^ target) & 0xFF00u) ? 2 : 1;
-        r.PC = target;
-      }
-    } else w = cpu_special<TRACK>(c, mm, r, (d >> 16) & 0xFFu, (d >> 6) & 63u, m, ea);
-  }
-  // ---- write phase
-  if (d & D_WRITE) wr<TRACK>(c, mm, r, ea, w);
+  // (A switch over per-opcode bodies folded from this same source was measured: 2-3x slower. Even with lanes
+  // kept together in time, its ~600 KB of code thrashes the instruction cache of an SM that runs 4 warps.)
+  cpu_exec<TRACK>(c, mm, r, pc, ir, b1, b2, fast_code, tab_entry(mm.tab, ir));
 }
 
 

@@ -813,7 +813,7 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
   d.nb_choices = cfg->nb_choices > 0 ? cfg->nb_choices : 1;
   d.single_life = cfg->single_life_episodes; d.random_start = cfg->random_start; d.seed = cfg->random_seed; d.env_id_offset = cfg->env_id_offset;
   d.draw_all_frames = cfg->draw_all_frames;
-  d.sync_slack = 12;
+  d.sync_slack = 4;
   if (const char* ev = getenv("MN_SYNC_SLACK")) d.sync_slack = atoi(ev) < 0 ? 0x3FFFFFFF : atoi(ev);
   h->max_rep = 0;
   for (int i = 0; i < cfg->nb_choices; ++i) {
