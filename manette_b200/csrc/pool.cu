@@ -821,13 +821,15 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
     d.tab_rep[i] = cfg->tab_rep[i];
     if (cfg->tab_rep[i] > h->max_rep) h->max_rep = cfg->tab_rep[i];
   }
-  // env slots per warp.  Measured on B200 (profiles/): the emulation loop is latency bound per warp, so small
-  // pools want many thin warps (less opcode divergence per warp) and large pools full ones; about 1024 warps
-  // is where the two meet.
+  // env slots per warp.  Measured on B200 (profiles/): the emulation loop is bound by the latency of ONE warp's
+  // instruction stream, and lanes kept together in time (hot_time) mostly share their control flow, so a full warp
+  // costs little more than a thin one.  Use the fewest warps that still give every SM sub-partition (4 x SMs) at
+  // most one: thin warps while the pool is small, full ones from 32 x 4 x SMs environments on.
   int slots = cfg->envs_per_warp;
   if (slots <= 0) {
+    const int subparts = 4 * prop.multiProcessorCount;
     slots = 1;
-    while (slots < 32 && n > 1024 * slots) slots *= 2;
+    while (slots < 32 && n > subparts * slots) slots *= 2;
   }
   if (slots != 1 && slots != 2 && slots != 4 && slots != 8 && slots != 16 && slots != 32) { delete h; return fail("mn_create: envs_per_warp must be 1,2,4,8,16 or 32"); }
   d.slots = slots;

@@ -49,8 +49,8 @@ class OraclePool(object):
         for i in range(n):
             sched = None
             if random_start:
-                gid = env_id_offset + i
-                sched = (noops(gid, ep) for ep in range(1 << 30))
+                # bind this environment's id now: a bare generator expression would read `gid` when first advanced
+                sched = (lambda gid: (noops(gid, ep) for ep in range(1 << 30)))(env_id_offset + i)
             self.emus.append(host_path.PortAtariEmulator(env_id_offset + i, self.args, noop_schedule=sched))
         self.tab_rep = host_path.tab_repetitions(max_repetition, nb_choices)
         self.n = n
