@@ -976,6 +976,9 @@ MN_HD MN_INLINE void cpu_exec(Ctx& c, const Mem& mm, Cpu& r, const uint32_t pc, 
         r.PC = target;
       }
     } else w = cpu_special<TRACK>(c, mm, r, (d >> 16) & 0xFFu, (d >> 6) & 63u, m, ea);
+    // (Everything here stays inline although it makes the loop ~30 KB of code.  Measured on B200: cpu_special out of
+    // line, only its stack / undocumented cases out of line, or stack and pointer accesses through out-of-line bus
+    // functions all LOSE 5-15 %: call sites in the loop cost more registers / spills than the code costs in fetch.)
   }
   // ---- write phase
   if (d & D_WRITE) wr<TRACK>(c, mm, r, ea, w);
