@@ -42,6 +42,12 @@ DEFAULT_WORKLOAD = "ms_pacman_figar10_n16384"
 # algorithmic HBM bytes of one next() for the emulation kernel: the two pooled raw frames it
 # must leave in HBM (2 x 33,600) + machine state in and out (2 x (168 + 128)); K3: 2 raw frames read + one plane
 ROUND_BYTES_PER_NEXT = 2 * 33600 + 2 * (168 + 128)
+# ncu --set full, one k_round launch of 16,384 Ms Pacman next() calls (profiles/r1_k_round_summary.txt):
+# dram__bytes_read.sum + dram__bytes_write.sum = 11.6 MB + 1,061.0 MB -> per next(); warp instructions issued per
+# next() and the share of the kernel's warp-state samples that wait for an instruction fetch
+NCU_ROUND_DRAM_BYTES_PER_NEXT = (11.627264e6 + 1.060982e9) / 16384
+NCU_ROUND_WARP_INST_PER_NEXT = 4543828503 / 16384
+PEAK_WARP_INST_PER_S = 148 * 4 * 1.965e9   # 148 SMs x 4 sub-partitions x 1 warp instruction per clock
 
 
 def k3_bytes(depth):
@@ -352,11 +358,20 @@ def main():
     achieved = frames * ROUND_BYTES_PER_NEXT / (round_ms / 1000.0) / 1e9 if round_ms > 0 else 0.0
     k3_achieved = (frames * k3_bytes(pool.depth)) / (push_ms / 1000.0) / 1e9 if push_ms > 0 else 0.0
     roofline = {"kernel": "k_round (6502+TIA emulation, one next() per listed env)", "bound": "hbm", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": NCU_ROUND_DRAM_BYTES_PER_NEXT * frames / max(round_launches, 1),
+                "traffic_source": "ncu dram bytes per next() of one k_round launch (profiles/r1_k_round_summary.txt) x next() calls "
+                                  "per launch of this run; algorithmic bytes per next() = %d" % ROUND_BYTES_PER_NEXT,
+                "peak_source": peak_src,
                 "avg_launch_ms": round_ms / max(round_launches, 1), "launches": int(round_launches),
                 "share_of_step": round_ms / ms if ms > 0 else None,
-                "note": "emulation is SM integer-issue bound, not HBM bound: the HBM fraction is reported as the contract "
-                        "asks; issue-slot utilisation and warp execution efficiency are in profiles/"}
+                "note": "emulation is bound by the latency of one warp's instruction stream (SM issue / instruction fetch), "
+                        "not by HBM: the HBM fraction is reported as the contract asks; see sm_issue and profiles/",
+                "sm_issue": {"warp_inst_per_s": NCU_ROUND_WARP_INST_PER_NEXT * frames / (round_ms / 1000.0) if round_ms > 0 else 0.0,
+                             "peak_warp_inst_per_s": PEAK_WARP_INST_PER_S,
+                             "frac": (NCU_ROUND_WARP_INST_PER_NEXT * frames / (round_ms / 1000.0) / PEAK_WARP_INST_PER_S) if round_ms > 0 else 0.0,
+                             "source": "warp instructions per next() from ncu (smsp__inst_executed.sum of one launch) x next() "
+                                       "calls of this run / k_round CUDA-event time"}}
     extra = {"k3_push_frames": {"bound": "hbm", "achieved": k3_achieved, "peak": peak, "unit": "GB/s",
                                 "frac": k3_achieved / peak, "ms": push_ms, "launches": int(push_launches),
                                 "share_of_step": push_ms / ms if ms > 0 else None},
