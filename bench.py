@@ -35,7 +35,8 @@ WORKLOADS = {
     "pong_paac_n32": dict(games=["pong"], n=32, rgb=False, nb_choices=1, max_rep=0),
     "breakout_figar10_n256": dict(games=["breakout"], n=256, rgb=False, nb_choices=11, max_rep=10),
     "seaquest_figar10_rgb_n4096": dict(games=["seaquest"], n=4096, rgb=True, nb_choices=11, max_rep=10),
-    "ms_pacman_figar10_n16384": dict(games=["ms_pacman"], n=16384, rgb=False, nb_choices=11, max_rep=10),
+    # C4 is the LSTM configuration: the learner's 5-deep observation history (paac.py:107-112) is kept by the pool
+    "ms_pacman_figar10_n16384": dict(games=["ms_pacman"], n=16384, rgb=False, nb_choices=11, max_rep=10, history=5),
     "mixed12_figar10_n16384": dict(games=GAMES12, n=16384, rgb=False, nb_choices=11, max_rep=10, allreduce=3400000),
 }
 DEFAULT_WORKLOAD = "ms_pacman_figar10_n16384"
@@ -205,7 +206,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": args.workload, "games": cfg["games"], "envs_per_gpu": cfg["n"], "rgb": cfg["rgb"],
               "nb_choices": cfg["nb_choices"], "max_repetition": cfg["max_rep"], "policy": "uniform random (counter-based)",
-              "decorrelate_steps": args.decorrelate,
+              "decorrelate_steps": args.decorrelate, "observation_history": cfg.get("history", 0),
               "frame_unit": "1 preprocessed frame = 1 next() = 4 emulated frames + one 84x84xD plane"}
 
     if args.impl == "reference":
@@ -241,8 +242,14 @@ def main():
     tab_rep = tab_repetitions(cfg["max_rep"], cfg["nb_choices"])
     groups = [(g, rom_bytes(g), k) for g, k in split_games(cfg["games"], n)]
     pool = mb.DevicePool(groups, rgb=cfg["rgb"], tab_rep=tab_rep, device=local_rank, env_id_offset=rank * n,
-                         envs_per_warp=args.envs_per_warp)
+                         envs_per_warp=args.envs_per_warp, history=cfg.get("history", 0))
     pool.reset_all()
+    # the caller's per-step bookkeeping (paac.py:173-205) and n-step returns (paac.py:226-231) ride along: K6 every
+    # macro step, K5 every T = max_local_steps = 5 steps
+    T_LOCAL = 5
+    rollout = mb.Rollout(n, T_LOCAL, pool.num_actions, tab_rep, device=local_rank)
+    boot = torch.zeros(n, device=dev)
+    extra_launches = [0]
     # the random policy's choices, resident in HBM before the timed region
     gen = torch.Generator(device=dev)
     gen.manual_seed(1000 + rank)
@@ -258,6 +265,13 @@ def main():
             pool.action_idx.copy_(acts[t], non_blocking=True)
             pool.repetition_idx.copy_(reps[t], non_blocking=True)
             pool.step_async(use_indices=True, stream=stream)
+            if t % T_LOCAL == 0:
+                rollout.begin(stream)
+            rollout.record(t % T_LOCAL, pool.rewards, pool.terminals, pool.action_idx, pool.repetition_idx, stream)
+            extra_launches[0] += 1
+            if (t + 1) % T_LOCAL == 0:
+                rollout.returns(boot, 0.99, stream)
+                extra_launches[0] += 2                      # mask flip + K5
             if grad is not None and (t + 1) % 5 == 0:      # synchronous-PAAC gradient allreduce every T=5 macro steps
                 dist.all_reduce(grad)
 
@@ -273,6 +287,7 @@ def main():
     pool.wait()
     barrier()
     f0, l0, i0 = pool.total_next_calls(), pool.launch_count(), pool.total_instructions()
+    extra_launches[0] = 0
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -288,7 +303,16 @@ def main():
     ms = e0.elapsed_time(e1)
     prof = pool.profile_end()
     frames = pool.total_next_calls() - f0
-    launches = pool.launch_count() - l0
+    launches = pool.launch_count() - l0 + extra_launches[0]
+    # K6 alone: microseconds per launch (launch-latency bound, like K4 / K5)
+    k6a, k6b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        k6a.record(stream)
+        for i in range(50):
+            rollout.record(i % T_LOCAL, pool.rewards, pool.terminals, pool.action_idx, pool.repetition_idx, stream)
+        k6b.record(stream)
+    stream.synchronize()
+    k6_us = 1000.0 * k6a.elapsed_time(k6b) / 50.0
     ins_timed = pool.total_instructions() - i0
     stat = torch.tensor([ms, float(frames), float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -375,7 +399,9 @@ def main():
     extra = {"k3_push_frames": {"bound": "hbm", "achieved": k3_achieved, "peak": peak, "unit": "GB/s",
                                 "frac": k3_achieved / peak, "ms": push_ms, "launches": int(push_launches),
                                 "share_of_step": push_ms / ms if ms > 0 else None},
-             "k_emit": {"ms": emit_ms, "launches": int(emit_launches), "share_of_step": emit_ms / ms if ms > 0 else None}}
+             "k_emit": {"ms": emit_ms, "launches": int(emit_launches), "share_of_step": emit_ms / ms if ms > 0 else None,
+                        "history_depth": int(cfg.get("history", 0))},
+             "k6_rollout_record": {"us_per_launch": k6_us, "bound": "launch latency", "envs": n}}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -7,6 +7,8 @@
  *   atari_emulator.py:17-136 AtariEmulator               (get_initial_state / next / get_legal_actions)
  *   exploration_policy.py:70-116 ExplorationPolicy.choose_next_actions   (mn_sample_figar)
  *   paac.py:176,180,226-231 + actor_learner.py:108-114   (mn_nstep)
+ *   paac.py:79-83,107-112 PAACLearner.update_memory       (observation history ring, mn_config.history)
+ *   paac.py:140-205 rollout bookkeeping of PAACLearner.train (mn_rollout_*)
  *
  * Conventions: every call returns 0 on success, <0 on error (mn_last_error() gives the text);
  * no exceptions cross the boundary; all calls on one handle come from one host thread; device
@@ -45,6 +47,7 @@ typedef struct {
   int envs_per_warp;         /* tuning: 1,2,4,8,16,32 lanes of a warp that own an environment (0 = default) */
   int draw_all_frames;       /* debug: draw the pixels of all four frames of a next(), not only the two pooled ones */
   int no_reset_memo;         /* debug: emulate every get_initial_state() instead of restoring memoised ones */
+  int history;               /* H > 0: keep the learner's H-deep observation history (LSTM nets: n_steps = 5, paac.py:107-112) */
 } mn_config;
 
 /* device-resident arrays (the reference's five shared variables, paac.py:97-102, + index forms) */
@@ -60,6 +63,8 @@ typedef struct {
   int32_t* next_calls;       /* (N,)  number of next() calls each env executed in the last macro step */
   uint8_t* frames;           /* (N, 2, 210, 160) raw palette-index screens of the last two frames */
   uint8_t* ring;             /* (N, 4, 84, 84, depth) observation ring */
+  uint8_t* history;          /* (N, H, 84, 84, 4*depth) ring over H of published states, slot mn_history_head() newest; NULL if off */
+  int history_depth;
 } mn_buffers;
 
 const char* mn_last_error(void);
@@ -112,6 +117,42 @@ int mn_sample_figar(const float* pi_dev, const float* rho_dev, int n, int a, int
 /* K5: reward clip + n-step return / advantage.  rewards/terminals/values (T,N) f32, bootstrap (N,) f32 */
 int mn_nstep(const float* rewards_dev, const float* terminals_dev, const float* values_dev, const float* bootstrap_dev,
              double gamma, int clip, int t, int n, float* y_dev, float* adv_dev, void* stream);
+
+/* Observation history of PAACLearner (paac.py:79-83 update_memory, :107-112 initialisation, :200-201 zeroing): kept
+ * by mn_reset_all / mn_step_async when mn_config.history = H.  The reference shifts an (N,H,...) array every step; here
+ * the new state is written into the next slot of a ring by the kernel that publishes it, and an env whose episode
+ * ended has its H entries zeroed (newest included, as the reference does).  Reference order memory[e][j], j oldest ->
+ * newest, is ring slot (head + 1 + j) % H.  mn_history_gather materialises that order: out_dev (N,H,84,84,4*depth). */
+int mn_history_head(mn_handle h, int* head);
+int mn_history_gather(mn_handle h, uint8_t* out_dev, void* stream);
+
+/* K6: the per-step bookkeeping of PAACLearner.train (paac.py:173-205) for all environments in one launch */
+typedef struct mn_rollout* mn_rollout_handle;
+typedef struct {
+  int n_envs, max_local_steps /* T */, num_actions /* A */, nb_choices /* K */;
+  float* rewards;            /* (T,N) clipped macro-step rewards            (paac.py:180, actor_learner.py:108-114) */
+  float* masks;              /* (T,N) 1 - episode_over                      (paac.py:176) */
+  int32_t* actions;          /* (T,N) index of the action taken             (paac.py:163) */
+  int32_t* repetitions;      /* (T,N) index of the repetition taken         (paac.py:166) */
+  double* episode_reward;    /* (N,)  total_episode_rewards                 (paac.py:179) */
+  int32_t* episode_steps;    /* (N,)  emulator_steps                        (paac.py:183) */
+  float* actions_sum;        /* (N,A) actions_sum                           (paac.py:154,203) */
+  uint64_t* action_rep;      /* (A,K) total_action_rep since mn_rollout_begin (paac.py:142,187-189) */
+  double* stats;             /* [episodes finished, sum of their rewards, sum of their lengths, min reward, max reward,
+                                global_step]: what the episode-statistics all-reduce carries */
+  float* finished_reward;    /* (N,)  total reward of the episodes that ended in the last recorded step, env order (paac.py:192) */
+  int32_t* finished_steps;   /* (N,)  their lengths (paac.py:193) */
+  int32_t* finished_count;   /* (1,) */
+} mn_rollout_buffers;
+int mn_rollout_create(int device, int n_envs, int max_local_steps, int num_actions, int nb_choices, const int* tab_rep,
+                      mn_rollout_handle* out);
+int mn_rollout_destroy(mn_rollout_handle r);
+int mn_rollout_get_buffers(mn_rollout_handle r, mn_rollout_buffers* out);
+/* start of a rollout (paac.py:142): zero the action x repetition histogram */
+int mn_rollout_begin(mn_rollout_handle r, void* stream);
+/* local step t: rewards/terminals (N,) f32 as published by the pool, the indices the policy chose (N,) i32 */
+int mn_rollout_record(mn_rollout_handle r, int t, const float* rewards_dev, const float* terminals_dev,
+                      const int32_t* action_idx_dev, const int32_t* rep_idx_dev, int clip, void* stream);
 
 /* per-kernel device timing with CUDA events on the launching stream, for bench.py's roofline object.
  * kinds: 0 = k_round (emulation), 1 = k_push_frames (K3), 2 = k_emit (stack + publish), 3 = other.

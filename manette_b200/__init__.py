@@ -9,8 +9,9 @@ from .exploration_policy import Action, ExplorationPolicy, sample_figar
 from .pool import DevicePool, load_rom, palette, start_noops, tab_repetitions
 from .preprocess import preprocess
 from .returns import nstep_returns
+from .rollout import Rollout
 from .runners import Runners
 
 __all__ = ["AtariEmulator", "EmulatorRunner", "EnvironmentCreator", "Action", "ExplorationPolicy", "sample_figar",
            "DevicePool", "load_rom", "palette", "start_noops", "tab_repetitions", "preprocess", "nstep_returns", "Runners",
-           "release_pools", "emulators_for_pool"]
+           "release_pools", "emulators_for_pool", "Rollout"]

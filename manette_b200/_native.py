@@ -21,14 +21,23 @@ class MnConfig(C.Structure):
     _fields_ = [("device", C.c_int), ("n_games", C.c_int), ("games", C.POINTER(MnGame)), ("rgb", C.c_int),
                 ("single_life_episodes", C.c_int), ("random_start", C.c_int), ("random_seed", C.c_int),
                 ("env_id_offset", C.c_int), ("nb_choices", C.c_int), ("tab_rep", C.POINTER(C.c_int)),
-                ("envs_per_warp", C.c_int), ("draw_all_frames", C.c_int), ("no_reset_memo", C.c_int)]
+                ("envs_per_warp", C.c_int), ("draw_all_frames", C.c_int), ("no_reset_memo", C.c_int), ("history", C.c_int)]
 
 
 class MnBuffers(C.Structure):
     _fields_ = [("n_envs", C.c_int), ("num_actions", C.c_int), ("nb_choices", C.c_int), ("depth", C.c_int),
                 ("states", C.c_void_p), ("rewards", C.c_void_p), ("terminals", C.c_void_p), ("actions", C.c_void_p),
                 ("repetitions", C.c_void_p), ("action_idx", C.c_void_p), ("repetition_idx", C.c_void_p),
-                ("next_calls", C.c_void_p), ("frames", C.c_void_p), ("ring", C.c_void_p)]
+                ("next_calls", C.c_void_p), ("frames", C.c_void_p), ("ring", C.c_void_p), ("history", C.c_void_p),
+                ("history_depth", C.c_int)]
+
+
+class MnRolloutBuffers(C.Structure):
+    _fields_ = [("n_envs", C.c_int), ("max_local_steps", C.c_int), ("num_actions", C.c_int), ("nb_choices", C.c_int),
+                ("rewards", C.c_void_p), ("masks", C.c_void_p), ("actions", C.c_void_p), ("repetitions", C.c_void_p),
+                ("episode_reward", C.c_void_p), ("episode_steps", C.c_void_p), ("actions_sum", C.c_void_p),
+                ("action_rep", C.c_void_p), ("stats", C.c_void_p), ("finished_reward", C.c_void_p),
+                ("finished_steps", C.c_void_p), ("finished_count", C.c_void_p)]
 
 
 # every symbol include/manette_b200.h declares: name -> (restype, argtypes)
@@ -59,6 +68,13 @@ SYMBOLS = {
     "mn_preprocess": (_I, [_VP, _VP, _I, _I, _VP]),
     "mn_sample_figar": (_I, [_VP, _VP, _I, _I, _I, _I, _F, _U64, _U32, _VP, _VP, _VP, _VP, _VP]),
     "mn_nstep": (_I, [_VP, _VP, _VP, _VP, _D, _I, _I, _I, _VP, _VP, _VP]),
+    "mn_history_head": (_I, [_VP, C.POINTER(_I)]),
+    "mn_history_gather": (_I, [_VP, _VP, _VP]),
+    "mn_rollout_create": (_I, [_I, _I, _I, _I, _I, C.POINTER(_I), C.POINTER(_VP)]),
+    "mn_rollout_destroy": (_I, [_VP]),
+    "mn_rollout_get_buffers": (_I, [_VP, C.POINTER(MnRolloutBuffers)]),
+    "mn_rollout_begin": (_I, [_VP, _VP]),
+    "mn_rollout_record": (_I, [_VP, _I, _VP, _VP, _VP, _VP, _I, _VP]),
     "mn_profile_begin": (_I, [_VP]),
     "mn_profile_end": (_I, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "mn_launch_count": (_I, [_VP, C.POINTER(C.c_int64)]),

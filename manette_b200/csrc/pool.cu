@@ -118,6 +118,8 @@ struct PoolDev {             // kernel argument block (by value)
   unsigned long long* memo_stats;   // hits, misses, inserts
   unsigned long long* total_instr;  // emulated 6502 instructions
   unsigned long long* redo_count;   // units re-run with every frame drawn (exact fallback of the pixel-less frames)
+  uint8_t* history;          // (N, H, 84, 84, 4D) ring of the last H published states (paac.py:79-83,107-112), or null
+  int32_t history_depth;
   const Tables* tables;
 };
 
@@ -567,13 +569,20 @@ __global__ void __launch_bounds__(256) k_preprocess(const uint8_t* __restrict__ 
 
 // ring -> stacked observation (environment.py:73-76): states[e][y][x][d*4 + k] = ring[(head + k) & 3][y][x][d],
 // 4 pixels per thread, 16-byte stores.  Also publishes rewards / terminals.
+// `hist_slot` >= 0: also the learner's observation history (PAACLearner.update_memory, paac.py:79-83): the new state
+// goes into ring slot `hist_slot` of the env's H-deep history; an env whose episode ended in this step has its whole
+// history zeroed AFTER that -- newest entry included -- exactly as paac.py:200-201 does.
 template <int D>
-__global__ void __launch_bounds__(256) k_emit(PoolDev p, int env_lo, int env_hi, int publish) {
+__global__ void __launch_bounds__(256) k_emit(PoolDev p, int env_lo, int env_hi, int publish, int hist_slot) {
   const int e = env_lo + blockIdx.x;
   if (e >= env_hi) return;
   const int head = p.env[e].ring_head;
   const uint8_t* ring = p.ring + size_t(e) * MN_STACK * (MN_PLANE * D);
   uint4* out = reinterpret_cast<uint4*>(p.states + size_t(e) * (MN_PLANE * D * MN_STACK));
+  const bool hist = hist_slot >= 0 && p.history != nullptr;
+  const bool wipe = hist && publish && p.over[e];
+  const size_t state_q = size_t(MN_PLANE) * D * MN_STACK / 16;   // uint4 per stacked state
+  uint4* hout = hist ? reinterpret_cast<uint4*>(p.history) + (size_t(e) * p.history_depth + hist_slot) * state_q : nullptr;
   for (int q = threadIdx.x; q < MN_PLANE / 4; q += blockDim.x) {
     uint32_t in[MN_STACK][D];   // [k][word]: 4 pixels x D bytes of ring plane (head + k)
 #pragma unroll
@@ -591,6 +600,7 @@ __global__ void __launch_bounds__(256) k_emit(PoolDev p, int env_lo, int env_hi,
       o.x = __byte_perm(ab_lo, cd_lo, 0x5410); o.y = __byte_perm(ab_lo, cd_lo, 0x7632);
       o.z = __byte_perm(ab_hi, cd_hi, 0x5410); o.w = __byte_perm(ab_hi, cd_hi, 0x7632);
       out[q] = o;
+      if (hist && !wipe) hout[q] = o;
     } else {
       // 4 pixels x (3 colours x 4 steps) = 48 bytes = 3 x uint4
       uint8_t bytes[MN_STACK][12];
@@ -605,15 +615,112 @@ __global__ void __launch_bounds__(256) k_emit(PoolDev p, int env_lo, int env_hi,
         for (int d = 0; d < 3; ++d)
           w[px * 3 + d] = uint32_t(bytes[0][px * 3 + d]) | (uint32_t(bytes[1][px * 3 + d]) << 8) |
                           (uint32_t(bytes[2][px * 3 + d]) << 16) | (uint32_t(bytes[3][px * 3 + d]) << 24);
-      out[3 * q + 0] = make_uint4(w[0], w[1], w[2], w[3]);
-      out[3 * q + 1] = make_uint4(w[4], w[5], w[6], w[7]);
-      out[3 * q + 2] = make_uint4(w[8], w[9], w[10], w[11]);
+      const uint4 o0 = make_uint4(w[0], w[1], w[2], w[3]), o1 = make_uint4(w[4], w[5], w[6], w[7]), o2 = make_uint4(w[8], w[9], w[10], w[11]);
+      out[3 * q + 0] = o0; out[3 * q + 1] = o1; out[3 * q + 2] = o2;
+      if (hist && !wipe) { hout[3 * q + 0] = o0; hout[3 * q + 1] = o1; hout[3 * q + 2] = o2; }
     }
+  }
+  if (wipe) {
+    uint4* all = reinterpret_cast<uint4*>(p.history) + size_t(e) * p.history_depth * state_q;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (size_t i = threadIdx.x; i < state_q * p.history_depth; i += blockDim.x) all[i] = z;
   }
   if (publish && threadIdx.x == 0) {
     p.rewards[e] = float(p.reward_acc[e]);
     p.terminals[e] = p.over[e] ? 1.0f : 0.0f;
   }
+}
+
+// the history ring in the reference's order (oldest -> newest): out (N, H, 84, 84, 4D)
+__global__ void __launch_bounds__(256) k_history_gather(const uint8_t* __restrict__ hist, uint8_t* __restrict__ out, int n, int depth,
+                                                        int head, size_t state_q) {
+  const int e = blockIdx.x / depth, j = blockIdx.x % depth;
+  if (e >= n) return;
+  const int slot = (head + 1 + j) % depth;
+  const uint4* src = reinterpret_cast<const uint4*>(hist) + (size_t(e) * depth + slot) * state_q;
+  uint4* dst = reinterpret_cast<uint4*>(out) + (size_t(e) * depth + j) * state_q;
+  for (size_t i = threadIdx.x; i < state_q; i += blockDim.x) dst[i] = src[i];
+}
+
+// ----------------------------------------------------------------------------- K6: rollout bookkeeping
+// paac.py:173-205 for one local step t of every environment: clipped reward and mask rows of the rollout, per-env
+// episode accumulators, the action x repetition histogram, and -- in ENVIRONMENT ORDER, like the reference's Python
+// loop -- the log and running statistics of the episodes that ended in this step.  One block: the work is a few
+// bytes per env; what matters is that the order of the log and of the double sums is fixed.
+struct RolloutDev {
+  int32_t n, T, A, K;
+  float *rewards, *masks;            // (T,N)
+  int32_t *actions, *repetitions;    // (T,N)
+  double* ep_reward;                 // (N,)
+  int32_t* ep_steps;                 // (N,)
+  float* actions_sum;                // (N,A)
+  unsigned long long* action_rep;    // (A,K)
+  double* stats;                     // count, sum reward, sum length, min reward, max reward, global_step
+  float* fin_reward; int32_t* fin_steps; int32_t* fin_count;   // (N,) (N,) (1,): the episodes that ended in the last recorded step
+  int32_t tab_rep[32];
+};
+__global__ void __launch_bounds__(1024) k_rollout_record(RolloutDev r, int t, const float* __restrict__ rewards,
+                                                         const float* __restrict__ terminals, const int32_t* __restrict__ a_idx,
+                                                         const int32_t* __restrict__ r_idx, int clip) {
+  __shared__ int s_warp_cnt[32];
+  __shared__ int s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int e0 = 0; e0 < r.n; e0 += blockDim.x) {
+    const int e = e0 + threadIdx.x;
+    bool over = false;
+    double tot = 0.0; int steps = 0;
+    if (e < r.n) {
+      const float raw = rewards[e];
+      over = terminals[e] != 0.0f;
+      int a = a_idx[e], k = r_idx[e];
+      a = a < 0 ? 0 : (a >= r.A ? r.A - 1 : a);
+      k = k < 0 ? 0 : (k >= r.K ? r.K - 1 : k);
+      tot = r.ep_reward[e] + double(raw);                                     // total_episode_rewards[e] += actual_reward
+      float c = raw;
+      if (clip) c = c > 1.0f ? 1.0f : (c < -1.0f ? -1.0f : c);                // rescale_reward (actor_learner.py:108-114)
+      const size_t i = size_t(t) * r.n + e;
+      r.rewards[i] = c;
+      r.masks[i] = 1.0f - (over ? 1.0f : 0.0f);                               // paac.py:176
+      r.actions[i] = a; r.repetitions[i] = k;
+      steps = r.ep_steps[e] + r.tab_rep[k] + 1;                               // emulator_steps[e] += tab_rep[argmax] + 1
+      atomicAdd(&r.action_rep[size_t(a) * r.K + k], 1ull);                    // total_action_rep[a][r] += 1 (integer: order-free)
+      float* as = r.actions_sum + size_t(e) * r.A;
+      if (over) { for (int j = 0; j < r.A; ++j) as[j] = 0.f; }                // actions_sum[e] = zeros (after += new_actions)
+      else as[a] += 1.0f;
+      r.ep_reward[e] = over ? 0.0 : tot;
+      r.ep_steps[e] = over ? 0 : steps;
+    }
+    // finished episodes of this chunk, compacted in env order
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, over);
+    if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int before = s_base;
+    for (int w = 0; w < warp; ++w) before += s_warp_cnt[w];
+    if (over) {
+      const int pos = before + __popc(bal & ((1u << lane) - 1u));
+      r.fin_reward[pos] = float(tot); r.fin_steps[pos] = steps;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int add = 0;
+      for (int w = 0; w < nwarps; ++w) add += s_warp_cnt[w];
+      // running statistics in env order (fixed order of the double sums)
+      double cnt = r.stats[0], sr = r.stats[1], sl = r.stats[2], mn = r.stats[3], mx = r.stats[4];
+      for (int j = 0; j < add; ++j) {
+        const int pos = s_base + j;
+        const double v = double(r.fin_reward[pos]);
+        sr += v; sl += double(r.fin_steps[pos]);
+        mn = (cnt == 0.0 || v < mn) ? v : mn; mx = (cnt == 0.0 || v > mx) ? v : mx;
+        cnt += 1.0;
+      }
+      r.stats[0] = cnt; r.stats[1] = sr; r.stats[2] = sl; r.stats[3] = mn; r.stats[4] = mx;
+      s_base += add;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { *r.fin_count = s_base; r.stats[5] += double(r.n); }   // self.global_step += 1 per env
 }
 
 // ----------------------------------------------------------------------------- K4: FiGAR sampling
@@ -712,6 +819,7 @@ struct mn_pool {
   std::vector<int> env_game_host;
   GameDev games_host[MN_MAX_GAMES];
   Tables* tables_dev;
+  int hist_head;             // ring slot of the newest state of the observation history
   // optional per-kernel timing (mn_profile_begin / mn_profile_end)
   bool profiling;
   std::vector<cudaEvent_t> ev_pool;
@@ -788,7 +896,7 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
   mn_pool* h = new mn_pool();
   memset(&h->d, 0, sizeof(h->d));
   h->device = cfg->device; h->done = nullptr; h->pending = false; h->launches = 0; h->pin_ram = nullptr;
-  h->profiling = false; h->ev_used = 0;
+  h->profiling = false; h->ev_used = 0; h->hist_head = 0;
   PoolDev& d = h->d;
   int n = 0, max_actions = 0;
   size_t rom_total = 0, max_rom = 0;
@@ -887,6 +995,9 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
   rc |= dev_alloc(h, &d.track, N * 5);
   rc |= dev_alloc(h, &d.memo_stats, size_t(4));
   rc |= dev_alloc(h, &h->tables_dev, size_t(1));
+  d.history_depth = cfg->history > 0 ? cfg->history : 0;
+  if (d.history_depth > 64) { mn_destroy(h); return fail("mn_create: history must be 0..64"); }
+  if (d.history_depth) rc |= dev_alloc(h, &d.history, N * size_t(d.history_depth) * MN_STACK * MN_PLANE * D);
   if (rc) { mn_destroy(h); return -1; }
   d.roms = roms;
   d.tables = h->tables_dev;
@@ -924,6 +1035,7 @@ int mn_get_buffers(mn_handle h, mn_buffers* out) {
   out->states = d.states; out->rewards = d.rewards; out->terminals = d.terminals; out->actions = d.actions;
   out->repetitions = d.repetitions; out->action_idx = d.action_idx; out->repetition_idx = d.repetition_idx;
   out->next_calls = d.next_calls; out->frames = d.frames; out->ring = d.ring;
+  out->history = d.history; out->history_depth = d.history_depth;
   return 0;
 }
 
@@ -961,10 +1073,10 @@ static void launch_round(mn_pool* h, int mode, int in, int out, cudaStream_t st,
   prof_mark(h, PK_ROUND, st, false);
   h->launches++;
 }
-static void launch_emit(mn_pool* h, int lo, int hi, int publish, cudaStream_t st) {
+static void launch_emit(mn_pool* h, int lo, int hi, int publish, cudaStream_t st, int hist_slot = -1) {
   prof_mark(h, PK_EMIT, st, true);
-  if (h->d.depth == 1) k_emit<1><<<hi - lo, 256, 0, st>>>(h->d, lo, hi, publish);
-  else k_emit<3><<<hi - lo, 256, 0, st>>>(h->d, lo, hi, publish);
+  if (h->d.depth == 1) k_emit<1><<<hi - lo, 256, 0, st>>>(h->d, lo, hi, publish, hist_slot);
+  else k_emit<3><<<hi - lo, 256, 0, st>>>(h->d, lo, hi, publish, hist_slot);
   prof_mark(h, PK_EMIT, st, false);
   h->launches++;
 }
@@ -1006,7 +1118,12 @@ int mn_reset_all(mn_handle h, void* stream) {
   k_fill_list<<<gb, tb, 0, st>>>(h->d, 2);
   h->launches++;
   launch_initial_state(h, st);
-  launch_emit(h, 0, n, 1, st);
+  if (h->d.history) {   // paac.py:107-112: memory = zeros, memory[e, -1] = shared_states[e]
+    CU(cudaMemsetAsync(h->d.history, 0, size_t(n) * h->d.history_depth * MN_STACK * MN_PLANE * h->d.depth, st));
+    h->hist_head = 0;
+  }
+  // over[] is zero here (k_fill_list), so nothing is wiped
+  launch_emit(h, 0, n, 1, st, h->d.history ? h->hist_head : -1);
   CU(cudaGetLastError());
   CU(cudaEventRecord(h->done, st));
   h->pending = true;
@@ -1029,7 +1146,8 @@ int mn_step_async(mn_handle h, int use_indices, void* stream) {
     in = out;
   }
   launch_initial_state(h, st);
-  launch_emit(h, 0, n, 1, st);
+  if (h->d.history) h->hist_head = (h->hist_head + 1) % h->d.history_depth;   // update_memory: shift, newest last
+  launch_emit(h, 0, n, 1, st, h->d.history ? h->hist_head : -1);
   CU(cudaGetLastError());
   CU(cudaEventRecord(h->done, st));
   h->pending = true;
@@ -1229,6 +1347,118 @@ int mn_nstep(const float* rewards_dev, const float* terminals_dev, const float* 
   if (n <= 0 || t <= 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   k_nstep<<<(n + 255) / 256, 256, 0, st>>>(rewards_dev, terminals_dev, values_dev, bootstrap_dev, gamma, clip, t, n, y_dev, adv_dev);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int mn_history_head(mn_handle h, int* head) {
+  if (!h || !head) return fail("mn_history_head: null argument");
+  if (!h->d.history) return fail("mn_history_head: the pool was created without an observation history");
+  *head = h->hist_head;
+  return 0;
+}
+
+int mn_history_gather(mn_handle h, uint8_t* out_dev, void* stream) {
+  if (!h || !out_dev) return fail("mn_history_gather: null argument");
+  if (!h->d.history) return fail("mn_history_gather: the pool was created without an observation history");
+  CU(cudaSetDevice(h->device));
+  const size_t state_q = size_t(MN_PLANE) * h->d.depth * MN_STACK / 16;
+  k_history_gather<<<h->d.n_envs * h->d.history_depth, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      h->d.history, out_dev, h->d.n_envs, h->d.history_depth, h->hist_head, state_q);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"
+
+// ---- K6: rollout bookkeeping (paac.py:140-205)
+struct mn_rollout {
+  RolloutDev d;
+  int device;
+  std::vector<void*> allocs;
+};
+template <typename T>
+static int ro_alloc(mn_rollout* r, T** out, size_t count) {
+  void* ptr = nullptr;
+  cudaError_t e = cudaMalloc(&ptr, count * sizeof(T) > 0 ? count * sizeof(T) : 16);
+  if (e != cudaSuccess) return fail(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  e = cudaMemset(ptr, 0, count * sizeof(T));
+  if (e != cudaSuccess) return fail(std::string("cudaMemset: ") + cudaGetErrorString(e));
+  r->allocs.push_back(ptr);
+  *out = static_cast<T*>(ptr);
+  return 0;
+}
+
+extern "C" {
+
+int mn_rollout_destroy(mn_rollout_handle r) {
+  if (!r) return 0;
+  cudaSetDevice(r->device);
+  cudaDeviceSynchronize();
+  for (void* p : r->allocs) cudaFree(p);
+  delete r;
+  return 0;
+}
+
+int mn_rollout_create(int device, int n_envs, int max_local_steps, int num_actions, int nb_choices, const int* tab_rep,
+                      mn_rollout_handle* out) {
+  if (!out || !tab_rep) return fail("mn_rollout_create: null argument");
+  if (n_envs < 1 || max_local_steps < 1 || num_actions < 1 || nb_choices < 1 || nb_choices > 32)
+    return fail("mn_rollout_create: bad shape (n_envs, max_local_steps, num_actions >= 1, nb_choices 1..32)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("mn_rollout_create: no CUDA device (the product has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail("mn_rollout_create: bad device ordinal");
+  CU(cudaSetDevice(device));
+  mn_rollout* r = new mn_rollout();
+  memset(&r->d, 0, sizeof(r->d));
+  r->device = device;
+  RolloutDev& d = r->d;
+  d.n = n_envs; d.T = max_local_steps; d.A = num_actions; d.K = nb_choices;
+  for (int i = 0; i < nb_choices; ++i) d.tab_rep[i] = tab_rep[i];
+  const size_t N = size_t(n_envs), T = size_t(max_local_steps);
+  int rc = 0;
+  rc |= ro_alloc(r, &d.rewards, T * N);
+  rc |= ro_alloc(r, &d.masks, T * N);
+  rc |= ro_alloc(r, &d.actions, T * N);
+  rc |= ro_alloc(r, &d.repetitions, T * N);
+  rc |= ro_alloc(r, &d.ep_reward, N);
+  rc |= ro_alloc(r, &d.ep_steps, N);
+  rc |= ro_alloc(r, &d.actions_sum, N * size_t(num_actions));
+  rc |= ro_alloc(r, &d.action_rep, size_t(num_actions) * nb_choices);
+  rc |= ro_alloc(r, &d.stats, size_t(6));
+  rc |= ro_alloc(r, &d.fin_reward, N);
+  rc |= ro_alloc(r, &d.fin_steps, N);
+  rc |= ro_alloc(r, &d.fin_count, size_t(1));
+  if (rc) { mn_rollout_destroy(r); return -1; }
+  *out = r;
+  return 0;
+}
+
+int mn_rollout_get_buffers(mn_rollout_handle r, mn_rollout_buffers* out) {
+  if (!r || !out) return fail("mn_rollout_get_buffers: null argument");
+  const RolloutDev& d = r->d;
+  out->n_envs = d.n; out->max_local_steps = d.T; out->num_actions = d.A; out->nb_choices = d.K;
+  out->rewards = d.rewards; out->masks = d.masks; out->actions = d.actions; out->repetitions = d.repetitions;
+  out->episode_reward = d.ep_reward; out->episode_steps = d.ep_steps; out->actions_sum = d.actions_sum;
+  out->action_rep = reinterpret_cast<uint64_t*>(d.action_rep); out->stats = d.stats;
+  out->finished_reward = d.fin_reward; out->finished_steps = d.fin_steps; out->finished_count = d.fin_count;
+  return 0;
+}
+
+int mn_rollout_begin(mn_rollout_handle r, void* stream) {
+  if (!r) return fail("mn_rollout_begin: null handle");
+  CU(cudaSetDevice(r->device));
+  CU(cudaMemsetAsync(r->d.action_rep, 0, size_t(r->d.A) * r->d.K * sizeof(unsigned long long), static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int mn_rollout_record(mn_rollout_handle r, int t, const float* rewards_dev, const float* terminals_dev,
+                      const int32_t* action_idx_dev, const int32_t* rep_idx_dev, int clip, void* stream) {
+  if (!r || !rewards_dev || !terminals_dev || !action_idx_dev || !rep_idx_dev) return fail("mn_rollout_record: null argument");
+  if (t < 0 || t >= r->d.T) return fail("mn_rollout_record: t outside 0..max_local_steps-1");
+  CU(cudaSetDevice(r->device));
+  k_rollout_record<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(r->d, t, rewards_dev, terminals_dev, action_idx_dev, rep_idx_dev, clip);
   CU(cudaGetLastError());
   return 0;
 }

@@ -43,7 +43,7 @@ class DevicePool(object):
     """games: list of (name, rom_bytes, n_envs) groups laid out back to back (env ids 0..N-1)."""
 
     def __init__(self, games, rgb=False, single_life_episodes=False, random_start=False, random_seed=3,
-                 env_id_offset=0, tab_rep=None, device=None, envs_per_warp=0, draw_all_frames=False, reset_memo=True):
+                 env_id_offset=0, tab_rep=None, device=None, envs_per_warp=0, draw_all_frames=False, reset_memo=True, history=0):
         if not torch.cuda.is_available():
             raise _native.NativeError("manette_b200 needs a CUDA device (there is no CPU fallback)")
         self._L = _native.load()
@@ -64,7 +64,7 @@ class DevicePool(object):
         cfg = _native.MnConfig(device=self.device.index, n_games=len(self._games), games=arr, rgb=int(bool(rgb)),
                                single_life_episodes=int(bool(single_life_episodes)), random_start=int(bool(random_start)),
                                random_seed=int(random_seed), env_id_offset=int(env_id_offset), nb_choices=len(tab),
-                               tab_rep=ctab, envs_per_warp=int(envs_per_warp), draw_all_frames=int(bool(draw_all_frames)), no_reset_memo=int(not reset_memo))
+                               tab_rep=ctab, envs_per_warp=int(envs_per_warp), draw_all_frames=int(bool(draw_all_frames)), no_reset_memo=int(not reset_memo), history=int(history))
         h = C.c_void_p()
         _native.check(self._L.mn_create(C.byref(cfg), C.byref(h)), "mn_create")
         self._h = h
@@ -91,6 +91,23 @@ class DevicePool(object):
         self.next_calls = _alias(b.next_calls, (n,), "<i4", dev, self)
         self.frames = _alias(b.frames, (n, 2, 210, 160), "|u1", dev, self)
         self.ring = _alias(b.ring, (n, STACK, IMG, IMG, d), "|u1", dev, self)
+        # the learner's observation history (paac.py:79-83,107-112) as a ring over its depth H: slot `history_head`
+        # holds the newest state; memory[e][j] of the reference (j oldest -> newest) is slot (head + 1 + j) % H
+        self.history_depth = int(b.history_depth)
+        self.history = _alias(b.history, (n, self.history_depth, IMG, IMG, STACK * d), "|u1", dev, self) if b.history else None
+
+    @property
+    def history_head(self):
+        head = C.c_int()
+        _native.check(self._L.mn_history_head(self._h, C.byref(head)), "mn_history_head")
+        return head.value
+
+    def history_ordered(self, out=None, stream=None):
+        """The reference's `memory` array (paac.py:107-112): (N, H, 84, 84, 4D), oldest -> newest."""
+        if out is None:
+            out = torch.empty_like(self.history)
+        _native.check(self._L.mn_history_gather(self._h, C.c_void_p(out.data_ptr()), self._stream_ptr(stream)), "mn_history_gather")
+        return out
 
     def set_tab_rep(self, tab_rep):
         tab = [int(x) for x in tab_rep]

@@ -352,3 +352,91 @@ def choose_next_actions(pi, rho, mode, seed, step, eps=0.0):
     else:
         a, r = np.argmax(pi, axis=1).astype(np.int32), np.argmax(rho, axis=1).astype(np.int32)
     return a, r, np.eye(pi.shape[1], dtype=np.float32)[a], np.eye(rho.shape[1], dtype=np.float32)[r]
+
+
+# ----------------------------------------------------------------------------- rollout bookkeeping (paac.py:79-83,107-205)
+class PortRollout(object):
+    """The bookkeeping of `PAACLearner.train` restated with the reference's own loops and array types
+    (TEST INFRASTRUCTURE: the checker of mn_rollout_record / the observation history ring).
+
+    paac.py:107-112  memory / whole_memory initialisation (LSTM nets, n_steps = 5)
+    paac.py:79-83    update_memory
+    paac.py:114-127  accumulators and rollout arrays
+    paac.py:142-143  per-rollout histogram
+    paac.py:149-205  one local step
+    """
+
+    def __init__(self, shared_states, emulator_counts, num_actions, tab_rep, max_local_steps, lstm=False, n_steps=5):
+        self.emulator_counts = emulator_counts
+        self.num_actions = num_actions
+        self.tab_rep = list(tab_rep)
+        self.total_repetitions = len(self.tab_rep)
+        self.max_local_steps = max_local_steps
+        self.lstm_bool = lstm
+        self.global_step = 0
+        self.total_rewards = []
+        self.total_steps = []
+        if self.lstm_bool:                                                       # :107-112
+            self.n_steps = n_steps
+            self.memory = np.zeros(([emulator_counts, self.n_steps] + list(shared_states.shape)[1:]), dtype=np.uint8)
+            self.whole_memory = np.zeros(([max_local_steps, emulator_counts, self.n_steps] + list(shared_states.shape)[1:]),
+                                         dtype=np.uint8)
+            for e in range(emulator_counts):
+                self.memory[e, -1, :, :, :] = shared_states[e]
+        self.emulator_steps = [0] * emulator_counts                              # :116-117
+        self.total_episode_rewards = emulator_counts * [0]
+        self.actions_sum = np.zeros((emulator_counts, num_actions))             # :119
+        self.rewards = np.zeros((max_local_steps, emulator_counts))             # :122
+        self.actions = np.zeros((max_local_steps, emulator_counts, num_actions))
+        self.repetitions = np.zeros((max_local_steps, emulator_counts, self.total_repetitions))
+        self.episodes_over_masks = np.zeros((max_local_steps, emulator_counts))
+        self.begin()
+
+    def begin(self):                                                             # :142-143
+        self.total_action_rep = np.zeros((self.num_actions, self.total_repetitions))
+        self.nb_actions = 0
+
+    @staticmethod
+    def rescale_reward(reward):                                                  # actor_learner.py:108-114
+        if reward > 1.0:
+            reward = 1.0
+        elif reward < -1.0:
+            reward = -1.0
+        return reward
+
+    def update_memory(self, shared_states, t):                                   # :79-83
+        self.whole_memory[t] = self.memory
+        self.memory[:, :-1, :, :, :] = self.memory[:, 1:, :, :, :]
+        self.memory[:, -1, :, :, :] = shared_states
+
+    def before_step(self, t, new_actions, new_repetitions):                      # :154-166
+        self.actions_sum += new_actions
+        for e in range(self.emulator_counts):
+            self.nb_actions += np.argmax(new_repetitions[e]) + 1
+        self.actions[t] = new_actions
+        self.repetitions[t] = new_repetitions
+
+    def after_step(self, t, new_actions, new_repetitions, shared_states, shared_rewards, shared_episode_over):   # :173-203
+        finished = []
+        if self.lstm_bool:
+            self.update_memory(shared_states, t)
+        self.episodes_over_masks[t] = 1.0 - shared_episode_over.astype(np.float32)
+        for e, (actual_reward, episode_over) in enumerate(zip(shared_rewards, shared_episode_over)):
+            self.total_episode_rewards[e] += actual_reward
+            actual_reward = self.rescale_reward(actual_reward)
+            self.rewards[t, e] = actual_reward
+            self.emulator_steps[e] += self.tab_rep[np.argmax(new_repetitions[e])] + 1
+            self.global_step += 1
+            a = np.argmax(new_actions[e])
+            r = np.argmax(new_repetitions[e])
+            self.total_action_rep[a][r] += 1
+            if episode_over:
+                self.total_rewards.append(self.total_episode_rewards[e])
+                self.total_steps.append(self.emulator_steps[e])
+                finished.append((self.total_episode_rewards[e], self.emulator_steps[e]))
+                self.total_episode_rewards[e] = 0
+                self.emulator_steps[e] = 0
+                if self.lstm_bool:
+                    self.memory[e] = np.zeros(([self.n_steps] + list(shared_states.shape)[1:]), dtype=np.uint8)
+                self.actions_sum[e] = np.zeros(self.num_actions)
+        return finished
