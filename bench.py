@@ -186,7 +186,7 @@ def cpu_pool_run(cfg, steps, warmup, budget_s=None, envs_per_core=4):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -294,13 +294,20 @@ def main():
     pool.profile_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    step_marks = []
     for t in range(args.warmup, total):
         device_step(t)
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(stream)
+        step_marks.append(ev)
     e1.record(stream)
     pool.wait()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
+    per_step = np.diff([0.0] + [e0.elapsed_time(ev) for ev in step_marks])
+    step_latency = {"mean": float(per_step.mean()), "p50": float(np.percentile(per_step, 50)),
+                    "p99": float(np.percentile(per_step, 99)), "max": float(per_step.max()), "unit": "ms", "rank": 0}
     prof = pool.profile_end()
     frames = pool.total_next_calls() - f0
     launches = pool.launch_count() - l0 + extra_launches[0]
@@ -413,7 +420,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
                 "raw_emulated_frames_per_s": 4.0 * value, "macro_steps_per_s": world * n * args.steps / (ms_max / 1000.0),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline, "kernels": extra,
+                "step_latency": step_latency, "clocks": clocks, "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline, "kernels": extra,
                 "cpu_baseline": cpu, "envs_per_warp": int(args.envs_per_warp),
                 "reset_memo": dict(zip(("restored", "emulated", "stored"), pool.memo_stats())), "exact_reruns": pool.redo_count(),
                 "emulated_6502_instr_per_s": world * ins_timed / (ms_max / 1000.0)}
