@@ -712,11 +712,10 @@ MN_HD MN_INLINE void setA(Cpu& r, uint32_t v) { r.axys = (r.axys & 0xFFFFFF00u) 
 MN_HD MN_INLINE void setX(Cpu& r, uint32_t v) { r.axys = (r.axys & 0xFFFF00FFu) | ((v & 0xFFu) << 8); }
 MN_HD MN_INLINE void setSP(Cpu& r, uint32_t v) { r.axys = (r.axys & 0x00FFFFFFu) | (v << 24); }
 MN_HD MN_INLINE uint32_t make_segmap(const EnvState& s) {
-  if (s.cart == CART_2K) return 0x01000100u;
-  if (s.cart == CART_4K) return 0x03020100u;
-  if (s.cart == CART_E0) return uint32_t(s.slice0) | (uint32_t(s.slice1) << 8) | (uint32_t(s.slice2) << 16) | (7u << 24);
-  const uint32_t b = uint32_t(s.bank) * 4u;   // F8 / F6: one 4K bank
-  return b | ((b + 1) << 8) | ((b + 2) << 16) | ((b + 3) << 24);
+  // 4K: pages 0..3; F8 / F6: the four pages of the selected 4K bank; 2K: its two pages twice; E0: three 1K slices + page 7
+  const uint32_t banked = uint32_t(s.bank) * 0x04040404u + 0x03020100u;   // bank is 0 for 4K
+  const uint32_t sliced = uint32_t(s.slice0) | (uint32_t(s.slice1) << 8) | (uint32_t(s.slice2) << 16) | (7u << 24);
+  return (s.cart == CART_E0) ? sliced : (s.cart == CART_2K) ? 0x01000100u : banked;
 }
 // does not touch fifo_n: that one is carried by the flat loop across frames
 MN_HD MN_INLINE void cpu_load(const EnvState& s, Cpu& r) {
