@@ -38,7 +38,9 @@ class _PoolGroup(object):
             self.pool = DevicePool([(a.game, rom, n)], rgb=bool(getattr(a, "rgb", False)),
                                    single_life_episodes=bool(a.single_life_episodes), random_start=bool(a.random_start),
                                    random_seed=int(a.random_seed), device=getattr(a, "cuda_device", None),
-                                   envs_per_warp=int(getattr(a, "envs_per_warp", 0)))
+                                   envs_per_warp=int(getattr(a, "envs_per_warp", 0)),
+                                   env_id_offset=int(getattr(a, "env_id_offset", 0)),      # rank * emulator_counts (multi-GPU)
+                                   history=int(getattr(a, "history", 0)))                  # 5 for the LSTM net (paac.py:107-112)
             self.fresh = np.zeros(n, bool)
         return self.pool
 
@@ -48,7 +50,8 @@ _GROUPS = {}
 
 def _group_for(args):
     key = (args.rom_path, args.game, bool(getattr(args, "rgb", False)), bool(args.single_life_episodes),
-           bool(args.random_start), int(args.random_seed), getattr(args, "cuda_device", None))
+           bool(args.random_start), int(args.random_seed), getattr(args, "cuda_device", None),
+           int(getattr(args, "env_id_offset", 0)), int(getattr(args, "history", 0)))
     g = _GROUPS.get(key)
     if g is None or (g.pool is not None and g.closed_to_new):
         g = _PoolGroup(key, args)
@@ -126,11 +129,18 @@ class AtariEmulator(object):
     def _observation(self):
         return self.pool.states[self.actor_id].cpu().numpy()
 
-    def _visualize(self):
+    def _visualize(self, frames=2):
+        """atari_emulator.py:60-62,96-99: the RGB screen of each of the FRAMES_IN_POOL grabbed frames of an
+        __action_repeat goes to on_new_frame, older first."""
         if self.call_on_new_frame:
             from .pool import palette
             _, rgb = palette()
-            self.on_new_frame(rgb[self.pool.screen(self.actor_id) >> 1])
+            newest = self.pool.screen(self.actor_id)
+            if frames > 1:
+                both = self.pool.frames[self.actor_id].cpu().numpy()
+                older = both[1] if np.array_equal(both[0], newest) else both[0]
+                self.on_new_frame(rgb[older >> 1])
+            self.on_new_frame(rgb[newest >> 1])
 
     def get_initial_state(self):
         """atari_emulator.py:102-110.  The first call on a fresh pool resets EVERY environment of the pool in

@@ -72,7 +72,7 @@ class ExplorationPolicy(object):
         self.softmax_temp = args.softmax_temp
         self.keep_percentage = args.keep_percentage
         self.annealed = args.annealed
-        self.annealing_steps = 80000000
+        self.annealing_steps = 80000000                # hard-coded in the reference too (:50); --annealed_steps is unused
         self.max_repetition = args.max_repetition
         self.nb_choices = args.nb_choices
         self.tab_rep = self.get_tab_repetitions()
@@ -87,6 +87,19 @@ class ExplorationPolicy(object):
             return self.initial_epsilon - (self.global_step * self.initial_epsilon / self.annealing_steps)
         return 0.0
 
+    def _mode(self):
+        return MODE_ARGMAX if self.test else (MODE_EGREEDY if self.egreedy_policy else MODE_MULTINOMIAL)
+
+    def choose_next_indices(self, pi, rho, num_actions):
+        """choose_next_actions for device-resident callers: CUDA (N,A), (N,K) -> int32 index tensors (no one-hots)."""
+        assert pi.shape[1] == num_actions and rho.shape[1] == self.nb_choices
+        a_idx, r_idx, _, _ = sample_figar(pi, rho, self._mode(), self.epsilon, self.seed, self._calls, onehot=False)
+        self._calls += 1
+        self.global_step += len(pi)
+        if self.annealed:
+            self.epsilon = self.get_epsilon()
+        return a_idx, r_idx
+
     def choose_next_actions(self, network_output_pi, network_output_rep, num_actions):
         """Returns (new_actions (N,A), new_repetitions (N,K)) one-hot.  CUDA tensors in -> CUDA tensors out;
         numpy in -> numpy out (float64 like np.eye in the reference)."""
@@ -94,8 +107,7 @@ class ExplorationPolicy(object):
         pi = torch.as_tensor(np.asarray(network_output_pi, np.float32)).cuda() if as_numpy else network_output_pi
         rho = torch.as_tensor(np.asarray(network_output_rep, np.float32)).cuda() if as_numpy else network_output_rep
         assert pi.shape[1] == num_actions and rho.shape[1] == self.nb_choices
-        mode = MODE_ARGMAX if self.test else (MODE_EGREEDY if self.egreedy_policy else MODE_MULTINOMIAL)
-        _, _, a_hot, r_hot = sample_figar(pi, rho, mode, self.epsilon, self.seed, self._calls)
+        _, _, a_hot, r_hot = sample_figar(pi, rho, self._mode(), self.epsilon, self.seed, self._calls)
         self._calls += 1
         self.global_step += len(pi)
         if self.annealed:

@@ -17,14 +17,18 @@ from .rollout import Rollout
 class PAACLearner(object):
     def __init__(self, pool, arch="NIPS", gamma=0.99, initial_lr=0.0224, lr_annealing_steps=80000000, alpha=0.99, e=0.1,
                  clip_norm=3.0, clip_norm_type="global", max_local_steps=5, entropy_regularisation_strength=0.02,
-                 softmax_temp=1.0, mode="multinomial", epsilon=0.05, seed=0, world_envs=None):
+                 softmax_temp=1.0, mode="multinomial", epsilon=0.05, seed=0, world_envs=None, network=None, explo_policy=None,
+                 on_step=None):
         self.pool, self.device = pool, pool.device
         self.T, self.gamma = int(max_local_steps), float(gamma)
         self.lstm = arch.upper() == "LSTM"
         if self.lstm and pool.history is None:
             raise ValueError("the LSTM architecture needs a pool created with history=5 (paac.py:107-112)")
-        self.network = PolicyVNetwork(arch, pool.num_actions, pool.nb_choices, pool.depth, softmax_temp,
-                                      entropy_regularisation_strength=entropy_regularisation_strength).to(self.device)
+        if network is None:
+            network = PolicyVNetwork(arch, pool.num_actions, pool.nb_choices, pool.depth, softmax_temp,
+                                     entropy_regularisation_strength=entropy_regularisation_strength)
+        self.network = network.to(self.device)
+        self.explo_policy, self.on_step = explo_policy, on_step
         self.optimizer = TFRMSProp(self.network.parameters(), initial_lr, alpha, e)
         self.initial_lr, self.lr_annealing_steps = float(initial_lr), int(lr_annealing_steps)
         self.clip_norm, self.clip_norm_type = float(clip_norm), clip_norm_type
@@ -51,8 +55,11 @@ class PAACLearner(object):
         pool, ro = self.pool, self.rollout
         x = self._net_input()
         v, pi, rho = self.network(x)
-        a_idx, r_idx, _, _ = sample_figar(pi.contiguous(), rho.contiguous(), mode=self.mode, epsilon=self.epsilon,
-                                          seed=self.seed, step=self.draws, onehot=False)
+        if self.explo_policy is not None:              # the reference's object decides mode / epsilon / annealing
+            a_idx, r_idx = self.explo_policy.choose_next_indices(pi, rho, pool.num_actions)
+        else:
+            a_idx, r_idx, _, _ = sample_figar(pi.contiguous(), rho.contiguous(), mode=self.mode, epsilon=self.epsilon,
+                                              seed=self.seed, step=self.draws, onehot=False)
         self.draws += 1
         self.states[t].copy_(x)
         ro.values[t].copy_(v)
@@ -70,6 +77,8 @@ class PAACLearner(object):
             st.wait_stream(pool.stream)
             ro.record(t, pool.rewards, pool.terminals, pool.action_idx, pool.repetition_idx)
             self.global_step += self.step_increment
+            if self.on_step is not None:
+                self.on_step(t)
         pool.wait()
         with torch.no_grad():
             boot, _, _ = self.network(self._net_input())                           # paac.py:217-222
@@ -90,7 +99,7 @@ class PAACLearner(object):
         if self.clip_norm_type == "global":                                        # tf.clip_by_global_norm (actor_learner.py:57-60)
             scale = self.clip_norm / torch.maximum(global_norm, torch.as_tensor(self.clip_norm, device=self.device))
             torch._foreach_mul_(grads, scale)
-        elif self.clip_norm_type == "local":                                       # tf.clip_by_norm per tensor (:62-65)
+        elif self.clip_norm_type == "local":          # 'ignore' leaves the gradients alone (actor_learner.py:52-54)                                       # tf.clip_by_norm per tensor (:62-65)
             for g in grads:
                 g.mul_(self.clip_norm / torch.maximum(torch.linalg.vector_norm(g), torch.as_tensor(self.clip_norm, device=self.device)))
         for grp in self.optimizer.param_groups:

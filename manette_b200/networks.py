@@ -5,6 +5,7 @@ states can be consumed where they are:
   networks.py:10-125   Operations (conv2d / fc / softmax with the "torch" uniform(+-1/sqrt(fan_in)) initialiser)
   networks.py:178-190  NIPSNetwork      networks.py:266-281 NatureNetwork      networks.py:205-225 PpwwyyxxNetwork
   networks.py:227-263  LSTMNetwork (memory (N,5,84,84,4D) -> conv stack per step -> LSTM(32) -> fc 128)
+  networks.py:194-204  BayesianNetwork (NIPS + dropout(keep_percentage) + fc 256; the dropout is always on)
   policy_v_network.py:19-74  critic / actor / repetition heads and the loss
 Input is the pool's uint8 NHWC tensor with channel c = d*4 + k; `permute(0,3,1,2)` of it is a channels-last view,
 so nothing is copied before the first convolution.
@@ -49,10 +50,10 @@ def _apply_conv(conv, x):
 
 
 class PolicyVNetwork(nn.Module):
-    ARCHS = ("NIPS", "NATURE", "PWYX", "LSTM")
+    ARCHS = ("NIPS", "NATURE", "PWYX", "LSTM", "BAYESIAN")
 
     def __init__(self, arch, num_actions, nb_choices, depth=1, softmax_temp=1.0, activation="relu", alpha_leaky_relu=0.1,
-                 entropy_regularisation_strength=0.02):
+                 entropy_regularisation_strength=0.02, keep_percentage=0.9):
         super().__init__()
         arch = arch.upper()
         assert arch in self.ARCHS, arch
@@ -60,7 +61,8 @@ class PolicyVNetwork(nn.Module):
         self.softmax_temp, self.beta, self.loss_scaling = float(softmax_temp), float(entropy_regularisation_strength), 5.0
         self.act = _Act(activation, alpha_leaky_relu)
         c = 4 * depth
-        if arch == "NIPS":
+        self.keep = float(keep_percentage)
+        if arch in ("NIPS", "BAYESIAN"):
             self.convs = nn.ModuleList([_conv(c, 16, 8, 4), _conv(16, 32, 4, 2)])
             self.pool_after, flat, hidden = (), 32 * 9 * 9, 256
         elif arch == "NATURE":
@@ -81,6 +83,8 @@ class PolicyVNetwork(nn.Module):
             self.fc = _fc(n_hidden, hidden)
         else:
             self.fc = _fc(flat, hidden)
+        if arch == "BAYESIAN":                         # networks.py:194-204: dropout(keep) on fc3, then fc4 256
+            self.fc4 = _fc(hidden, 256)
         self.critic = _fc(hidden, 1)
         self.actor = _fc(hidden, self.num_actions)
         self.repetition = _fc(hidden, self.nb_choices)
@@ -104,6 +108,8 @@ class PolicyVNetwork(nn.Module):
             h = self.act(self.fc(self.lstm_out(out[:, -1])))
         else:
             h = self.act(self.fc(self._features(states)))
+        if self.arch == "BAYESIAN":                    # tf.nn.dropout sits in the graph: active when acting too
+            h = self.act(self.fc4(F.dropout(h, 1.0 - self.keep, training=True)))
         v = self.critic(h).reshape(-1)
         pi = F.softmax(self.actor(h) / self.softmax_temp, dim=1)
         rho = F.softmax(self.repetition(h) / self.softmax_temp, dim=1)

@@ -8,19 +8,21 @@ import util  # noqa: F401
 from manette_b200.networks import PolicyVNetwork, TFRMSProp
 
 
-@pytest.mark.parametrize("arch,shape", [("NIPS", (6, 84, 84, 4)), ("NATURE", (3, 84, 84, 12)), ("PWYX", (2, 84, 84, 4)),
+@pytest.mark.parametrize("arch,shape", [("NIPS", (6, 84, 84, 4)), ("NATURE", (3, 84, 84, 12)), ("PWYX", (2, 84, 84, 4)), ("BAYESIAN", (3, 84, 84, 4)),
                                         ("LSTM", (2, 5, 84, 84, 4))])
 def test_shapes_and_loss_formula(arch, shape):
     torch.manual_seed(0)
     A, K = 9, 11
     net = PolicyVNetwork(arch, A, K, depth=shape[-1] // 4)
     x = torch.randint(0, 256, shape, dtype=torch.uint8)
+    torch.manual_seed(7)                                                  # BAYESIAN: the dropout mask is part of the graph
     v, pi, rho = net(x)
     n = shape[0]
     assert v.shape == (n,) and pi.shape == (n, A) and rho.shape == (n, K)
     assert torch.allclose(pi.sum(1), torch.ones(n), atol=1e-5) and torch.allclose(rho.sum(1), torch.ones(n), atol=1e-5)
     a, r = torch.randint(0, A, (n,)), torch.randint(0, K, (n,))
     y, adv = torch.randn(n), torch.randn(n)
+    torch.manual_seed(7)
     loss, _ = net.loss(x, a, r, y, adv)
     # policy_v_network.py:24-74 in numpy, with one-hot targets like the reference feeds
     V, P, R = v.detach().numpy().astype(np.float64), pi.detach().numpy().astype(np.float64), rho.detach().numpy().astype(np.float64)
