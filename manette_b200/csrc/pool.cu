@@ -497,49 +497,72 @@ __global__ void __launch_bounds__(256) k_memo_insert(PoolDev p) {
   }
 }
 
-// K3 core: one output word = 4 horizontally adjacent pixels of one channel-interleaved plane row.
-// a, b: the two raw palette-index screens (210x160).  mode 0: max of both, 1: a only, 2: b only.
+// K3 core, one block of 256 threads per environment.  a, b: the two raw palette-index screens (210x160);
+// mode 0: max of both, 1: a only, 2: b only.  Only the 84 source rows the nearest-neighbour map keeps are read, each
+// as whole 160-byte rows (8-byte loads, one warp per row), mapped through a shared-memory palette (128 luminance
+// bytes fill the 32 banks exactly once: conflict-free; the RGB table is 128 words), reduced with max, and gathered
+// into the output plane in shared memory; the plane leaves with 16-byte stores.  Ends with a barrier (callers loop).
 template <int D>
 __device__ __forceinline__ void preprocess_plane(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int mode,
-                                                 uint8_t* __restrict__ plane, int tid, int nthreads) {
+                                                 uint8_t* __restrict__ plane) {
+  __shared__ __align__(16) uint32_t s_pal[D == 1 ? 32 : 128];
+  __shared__ __align__(16) uint32_t s_row[8][D == 1 ? MN_SCREEN_W / 4 : MN_SCREEN_W];
+  __shared__ __align__(16) uint32_t s_out[MN_PLANE * D / 4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (mode == 1) b = a; else if (mode == 2) a = b;
-  if (D == 1) {
-    uint32_t* out = reinterpret_cast<uint32_t*>(plane);
-    for (int w = tid; w < MN_PLANE / 4; w += nthreads) {
-      const int y = w / (MN_IMG / 4), xq = (w - y * (MN_IMG / 4)) * 4;
-      const int row = ((2 * y + 1) * 5) >> 2;   // floor((y + 0.5) * 2.5)
-      const uint8_t* ra = a + row * MN_SCREEN_W;
-      const uint8_t* rb = b + row * MN_SCREEN_W;
-      uint32_t v = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int x = c_xmap[xq + k];
-        const uint32_t la = c_pal[ra[x] >> 1] & 0xFF, lb = c_pal[rb[x] >> 1] & 0xFF;
-        v |= (la > lb ? la : lb) << (8 * k);
-      }
-      out[w] = v;
-    }
-  } else {
-    // 84 x 84 x 3: one thread per pixel triple pair -> handle one pixel (3 bytes) at a time, 4 pixels = 3 words
-    uint32_t* out = reinterpret_cast<uint32_t*>(plane);
-    for (int w = tid; w < MN_PLANE / 4; w += nthreads) {
-      const int y = w / (MN_IMG / 4), xq = (w - y * (MN_IMG / 4)) * 4;
-      const int row = ((2 * y + 1) * 5) >> 2;
-      const uint8_t* ra = a + row * MN_SCREEN_W;
-      const uint8_t* rb = b + row * MN_SCREEN_W;
-      uint32_t px[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int x = c_xmap[xq + k];
-        const uint32_t ca = c_pal[ra[x] >> 1] >> 8, cb = c_pal[rb[x] >> 1] >> 8;   // 0x00BBGGRR
-        px[k] = __vmaxu4(ca, cb);
-      }
-      // bytes R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
-      out[3 * w + 0] = px[0] | (px[1] << 24);
-      out[3 * w + 1] = (px[1] >> 8) | (px[2] << 16);
-      out[3 * w + 2] = (px[2] >> 16) | (px[3] << 8);
-    }
+  if (tid < 128) {
+    if (D == 1) reinterpret_cast<uint8_t*>(s_pal)[tid] = uint8_t(c_pal[tid]);
+    else s_pal[tid] = c_pal[tid] >> 8;                                     // 0x00BBGGRR
   }
+  // output word `lane` of a row = these four source columns (PIL's nearest map, the same for every row)
+  int x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+  if (lane < MN_IMG / 4) { x0 = c_xmap[4 * lane]; x1 = c_xmap[4 * lane + 1]; x2 = c_xmap[4 * lane + 2]; x3 = c_xmap[4 * lane + 3]; }
+  __syncthreads();
+  for (int y = warp; y < MN_IMG; y += 8) {
+    const int row = ((2 * y + 1) * 5) >> 2;   // floor((y + 0.5) * 2.5)
+    const uint8_t* ra = a + row * MN_SCREEN_W;
+    const uint8_t* rb = b + row * MN_SCREEN_W;
+    if (D == 1) {
+      if (lane < MN_SCREEN_W / 8) {
+        const uint2 va = *reinterpret_cast<const uint2*>(ra + lane * 8), vb = *reinterpret_cast<const uint2*>(rb + lane * 8);
+        const uint8_t* pal = reinterpret_cast<const uint8_t*>(s_pal);
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t la = pal[(va.x >> (8 * k + 1)) & 0x7Fu], lb = pal[(vb.x >> (8 * k + 1)) & 0x7Fu];
+          const uint32_t ha = pal[(va.y >> (8 * k + 1)) & 0x7Fu], hb = pal[(vb.y >> (8 * k + 1)) & 0x7Fu];
+          lo |= (la > lb ? la : lb) << (8 * k);
+          hi |= (ha > hb ? ha : hb) << (8 * k);
+        }
+        *reinterpret_cast<uint2*>(&s_row[warp][lane * 2]) = make_uint2(lo, hi);
+      }
+      __syncwarp();
+      if (lane < MN_IMG / 4) {
+        const uint8_t* r = reinterpret_cast<const uint8_t*>(s_row[warp]);
+        s_out[y * (MN_IMG / 4) + lane] = uint32_t(r[x0]) | (uint32_t(r[x1]) << 8) | (uint32_t(r[x2]) << 16) | (uint32_t(r[x3]) << 24);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < MN_SCREEN_W / 32; ++j) {
+        const int x = lane + 32 * j;
+        s_row[warp][x] = __vmaxu4(s_pal[ra[x] >> 1], s_pal[rb[x] >> 1]);
+      }
+      __syncwarp();
+      if (lane < MN_IMG / 4) {
+        const uint32_t p0 = s_row[warp][x0], p1 = s_row[warp][x1], p2 = s_row[warp][x2], p3 = s_row[warp][x3];
+        uint32_t* o = s_out + y * (3 * MN_IMG / 4) + 3 * lane;   // bytes R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+        o[0] = p0 | (p1 << 24);
+        o[1] = (p1 >> 8) | (p2 << 16);
+        o[2] = (p2 >> 16) | (p3 << 8);
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  uint4* dst = reinterpret_cast<uint4*>(plane);
+  const uint4* src = reinterpret_cast<const uint4*>(s_out);
+  for (int i = tid; i < MN_PLANE * D / 16; i += 256) dst[i] = src[i];
+  __syncthreads();
 }
 
 // K3 over a work list: one block per (game, list entry)
@@ -555,7 +578,7 @@ __global__ void __launch_bounds__(256) k_push_frames(PoolDev p, int in) {
   const uint8_t info = p.push_info[e];
   const uint8_t* fb = p.frames + size_t(e) * (2 * MN_FRAME_BYTES);
   uint8_t* plane = p.ring + (size_t(e) * MN_STACK + (info & 3)) * (MN_PLANE * D);
-  preprocess_plane<D>(fb, fb + MN_FRAME_BYTES, info >> 2, plane, threadIdx.x, blockDim.x);
+  preprocess_plane<D>(fb, fb + MN_FRAME_BYTES, info >> 2, plane);
 }
 
 // K3 stand-alone (mn_preprocess)
@@ -563,7 +586,7 @@ template <int D>
 __global__ void __launch_bounds__(256) k_preprocess(const uint8_t* __restrict__ frames, uint8_t* __restrict__ planes, int n) {
   for (int e = blockIdx.x; e < n; e += gridDim.x) {
     const uint8_t* fb = frames + size_t(e) * (2 * MN_FRAME_BYTES);
-    preprocess_plane<D>(fb, fb + MN_FRAME_BYTES, 0, planes + size_t(e) * (MN_PLANE * D), threadIdx.x, blockDim.x);
+    preprocess_plane<D>(fb, fb + MN_FRAME_BYTES, 0, planes + size_t(e) * (MN_PLANE * D));
   }
 }
 
