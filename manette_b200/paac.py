@@ -36,6 +36,7 @@ class PAACLearner(object):
         self.lstm_bool = args.arch == "LSTM"
         self.rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        explo_policy.seed = int(getattr(explo_policy, "seed", 0)) + 0x9E3779B1 * self.rank   # ranks draw different streams
         args.history = 5 if self.lstm_bool else 0                      # paac.py:107-112 -> the pool's history ring
         args.env_id_offset = self.rank * self.emulator_counts          # ALE seeds stay random_seed * (global id + 1)
         self.emulators = [environment_creator.create_environment(i) for i in range(self.emulator_counts)]

@@ -129,5 +129,11 @@ if __name__ == "__main__":
     logging.basicConfig(stream=sys.stdout, level=logging.INFO)
     cli = get_arg_parser().parse_args()
     from . import logger_utils
-    logger_utils.save_args(cli, cli.debugging_folder)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:      # torchrun: one process per GPU, synchronous PAAC over NCCL
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+    if int(os.environ.get("RANK", "0")) == 0:
+        logger_utils.save_args(cli, cli.debugging_folder)
     main(cli)

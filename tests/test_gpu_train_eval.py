@@ -94,3 +94,21 @@ def test_gif_hook_receives_both_pooled_frames(tmp_path, monkeypatch):
     gif = Image.open(os.path.join(str(tmp_path), "ep0.gif"))
     assert gif.size == (160, 210)
     mb.release_pools()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_rank_training_keeps_replicas_identical(tmp_path):
+    """Synchronous PAAC over NCCL: rank 0's initial variables are broadcast, gradients averaged, so the replicas stay
+    bit-identical; each rank steps its own environments (global ids offset by rank x emulator_counts)."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(os.path.dirname(__file__), "dp_worker.py"), str(tmp_path)]
+    subprocess.run(cmd, check=True, timeout=600)
+    r0, r1 = (json.load(open(tmp_path / ("rank%d.json" % r))) for r in (0, 1))
+    assert r0["global_step"] == r1["global_step"] == 2 * 5 * 32 * 2
+    assert r0["digest"] == r1["digest"]
+    assert r0["steps_recorded"] == r1["steps_recorded"] == 2 * 5 * 32 * 2      # all-reduced episode statistics
+    assert (r0["offset"], r1["offset"]) == (0, 32)
+    assert os.path.exists(tmp_path / "run" / "checkpoints" / "-640.pt")
