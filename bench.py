@@ -48,6 +48,9 @@ ROUND_BYTES_PER_NEXT = 2 * 33600 + 2 * (168 + 128)
 # next() and the share of the kernel's warp-state samples that wait for an instruction fetch
 NCU_ROUND_DRAM_BYTES_PER_NEXT = (12.480256e6 + 1.059751e9) / 16384
 NCU_ROUND_WARP_INST_PER_NEXT = 4546313415 / 16384
+# ncu --set full, one k_push_frames launch over 16,384 gray Ms Pacman envs (profiles/r1_k3_push_frames_summary.txt):
+# 705.2 MB read + 105.8 MB written -> per next(): the 126 source rows the nearest map drops are never read
+NCU_K3_DRAM_BYTES_PER_NEXT = (705.19296e6 + 105.80096e6) / 16384
 PEAK_WARP_INST_PER_S = 148 * 4 * 1.965e9   # 148 SMs x 4 sub-partitions x 1 warp instruction per clock
 
 
@@ -405,7 +408,11 @@ def main():
                                        "calls of this run / k_round CUDA-event time"}}
     extra = {"k3_push_frames": {"bound": "hbm", "achieved": k3_achieved, "peak": peak, "unit": "GB/s",
                                 "frac": k3_achieved / peak, "ms": push_ms, "launches": int(push_launches),
-                                "share_of_step": push_ms / ms if ms > 0 else None},
+                                "share_of_step": push_ms / ms if ms > 0 else None,
+                                "algorithmic_bytes_per_next": k3_bytes(pool.depth),
+                                "traffic_per_next": NCU_K3_DRAM_BYTES_PER_NEXT if pool.depth == 1 else None,
+                                "traffic_source": "ncu dram bytes of one launch over 16,384 gray envs "
+                                                  "(profiles/r1_k3_push_frames_summary.txt)"},
              "k_emit": {"ms": emit_ms, "launches": int(emit_launches), "share_of_step": emit_ms / ms if ms > 0 else None,
                         "history_depth": int(cfg.get("history", 0))},
              "k6_rollout_record": {"us_per_launch": k6_us, "bound": "launch latency", "envs": n}}
