@@ -18,7 +18,7 @@ class PAACLearner(object):
     def __init__(self, pool, arch="NIPS", gamma=0.99, initial_lr=0.0224, lr_annealing_steps=80000000, alpha=0.99, e=0.1,
                  clip_norm=3.0, clip_norm_type="global", max_local_steps=5, entropy_regularisation_strength=0.02,
                  softmax_temp=1.0, mode="multinomial", epsilon=0.05, seed=0, world_envs=None, network=None, explo_policy=None,
-                 on_step=None):
+                 on_step=None, micro_batch=16384):
         self.pool, self.device = pool, pool.device
         self.T, self.gamma = int(max_local_steps), float(gamma)
         self.lstm = arch.upper() == "LSTM"
@@ -29,6 +29,9 @@ class PAACLearner(object):
                                      entropy_regularisation_strength=entropy_regularisation_strength)
         self.network = network.to(self.device)
         self.explo_policy, self.on_step = explo_policy, on_step
+        # frames per forward / backward chunk: activations of the PWYX stack are ~1.3 MB per frame in fp32, so pools of
+        # 16,384 environments (81,920 frames per acting pass of the LSTM net, 409,600 per update) go through in slices
+        self.micro_rows = max(1, int(micro_batch) // (5 if self.lstm else 1))
         self.optimizer = TFRMSProp(self.network.parameters(), initial_lr, alpha, e)
         self.initial_lr, self.lr_annealing_steps = float(initial_lr), int(lr_annealing_steps)
         self.clip_norm, self.clip_norm_type = float(clip_norm), clip_norm_type
@@ -47,6 +50,13 @@ class PAACLearner(object):
             return self.initial_lr - (self.global_step * self.initial_lr / self.lr_annealing_steps)
         return 0.0
 
+    def _forward(self, x):
+        """(v, pi, rho) of the network over all rows of x, in slices of `micro_rows`."""
+        if x.shape[0] <= self.micro_rows:
+            return self.network(x)
+        outs = [self.network(x[lo:lo + self.micro_rows]) for lo in range(0, x.shape[0], self.micro_rows)]
+        return tuple(torch.cat(o) for o in zip(*outs))
+
     def _net_input(self):
         return self.pool.history_ordered() if self.lstm else self.pool.states
 
@@ -54,7 +64,7 @@ class PAACLearner(object):
     def _act(self, t):
         pool, ro = self.pool, self.rollout
         x = self._net_input()
-        v, pi, rho = self.network(x)
+        v, pi, rho = self._forward(x)
         if self.explo_policy is not None:              # the reference's object decides mode / epsilon / annealing
             a_idx, r_idx = self.explo_policy.choose_next_indices(pi, rho, pool.num_actions)
         else:
@@ -81,13 +91,20 @@ class PAACLearner(object):
                 self.on_step(t)
         pool.wait()
         with torch.no_grad():
-            boot, _, _ = self.network(self._net_input())                           # paac.py:217-222
+            boot, _, _ = self._forward(self._net_input())                          # paac.py:217-222
         y, adv = ro.returns(boot.contiguous(), self.gamma)
         n_rows = self.T * pool.n_envs
         flat_states = self.states.reshape((n_rows,) + tuple(self.states.shape[2:]))
         self.network.zero_grad(set_to_none=False)
-        loss, parts = self.network.loss(flat_states, ro.actions.reshape(-1), ro.repetitions.reshape(-1), y.reshape(-1), adv.reshape(-1))
-        loss.backward()
+        fa, fr, fy, fadv = ro.actions.reshape(-1), ro.repetitions.reshape(-1), y.reshape(-1), adv.reshape(-1)
+        loss, parts = None, None
+        for lo in range(0, n_rows, self.micro_rows):                               # the loss is a mean over rows: slices add up
+            hi = min(n_rows, lo + self.micro_rows)
+            l_c, p_c = self.network.loss(flat_states[lo:hi], fa[lo:hi], fr[lo:hi], fy[lo:hi], fadv[lo:hi])
+            w = (hi - lo) / n_rows
+            (l_c * w).backward()
+            loss = l_c.detach() * w if loss is None else loss + l_c.detach() * w
+            parts = {k: v * w for k, v in p_c.items()} if parts is None else {k: parts[k] + v * w for k, v in p_c.items()}
         grads = [p.grad for p in self.network.parameters()]
         if self.world > 1:                                                         # synchronous PAAC across GPUs: mean gradient
             flat = torch._utils._flatten_dense_tensors(grads)
@@ -99,13 +116,13 @@ class PAACLearner(object):
         if self.clip_norm_type == "global":                                        # tf.clip_by_global_norm (actor_learner.py:57-60)
             scale = self.clip_norm / torch.maximum(global_norm, torch.as_tensor(self.clip_norm, device=self.device))
             torch._foreach_mul_(grads, scale)
-        elif self.clip_norm_type == "local":          # 'ignore' leaves the gradients alone (actor_learner.py:52-54)                                       # tf.clip_by_norm per tensor (:62-65)
+        elif self.clip_norm_type == "local":          # tf.clip_by_norm per tensor (:62-65); 'ignore' leaves them alone
             for g in grads:
                 g.mul_(self.clip_norm / torch.maximum(torch.linalg.vector_norm(g), torch.as_tensor(self.clip_norm, device=self.device)))
         for grp in self.optimizer.param_groups:
             grp["lr"] = self.get_lr()
         self.optimizer.step()
-        return {"loss": loss.detach(), "global_norm": global_norm, "lr": self.get_lr(), **parts}
+        return {"loss": loss, "global_norm": global_norm, "lr": self.get_lr(), **parts}
 
     def close(self):
         self.rollout.close()

@@ -47,7 +47,7 @@ class PAACLearner(object):
                                    lr_annealing_steps=args.lr_annealing_steps, alpha=args.alpha, e=args.e,
                                    clip_norm=args.clip_norm, clip_norm_type=args.clip_norm_type,
                                    max_local_steps=args.max_local_steps, network=self.network, explo_policy=explo_policy,
-                                   on_step=self._after_step)
+                                   on_step=self._after_step, micro_batch=int(getattr(args, "micro_batch", 16384)))
         if self.world > 1:                                             # every replica starts from rank 0's variables
             for p in self.network.parameters():
                 dist.broadcast(p.data, 0)

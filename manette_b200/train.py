@@ -7,7 +7,8 @@ either side drives the other; `main(args)` follows train.py:15-29: exploration p
 creators -> PAACLearner -> train() with SIGINT/SIGTERM saving a checkpoint first (train.py:32-43).
 `-d/--device` accepts the reference's TensorFlow names ('/gpu:1', '/cpu:0') and maps '/gpu:k' to cuda:k; there is
 no CPU path, so '/cpu:0' (the reference's default) selects cuda:0.  Extra flags (absent from the reference, all
-optional): --seed (counter-based sampler key), --envs_per_warp (kernel layout override)."""
+optional): --seed (counter-based sampler key), --envs_per_warp (kernel layout override), --micro_batch (frames per
+network slice)."""
 import argparse
 import copy
 import logging
@@ -53,6 +54,7 @@ _FLAGS = [
 _EXTRA = [
     (("--seed",), "seed", 0, int, "key of the counter-based action sampler"),
     (("--envs_per_warp",), "envs_per_warp", 0, int, "emulation kernel layout override (0 = automatic)"),
+    (("--micro_batch",), "micro_batch", 16384, int, "frames per forward/backward slice of the network (memory bound)"),
 ]
 
 

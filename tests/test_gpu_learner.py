@@ -35,3 +35,23 @@ def test_rollouts_update_the_network(arch, game, n, history):
     if arch == "LSTM":
         assert learner.states.shape == (5, n, 5, 84, 84, 4)
     learner.close(); pool.close()
+
+
+def test_micro_batched_update_equals_the_whole_batch():
+    """The loss is a mean over T x N rows: slices of the batch, weighted by their size, accumulate the same gradient."""
+    import manette_b200 as mb
+    from manette_b200.learner import PAACLearner
+    tab = mb.tab_repetitions(10, 11)
+    got = []
+    for micro in (1 << 20, 48):
+        torch.manual_seed(1)
+        pool = mb.DevicePool([("breakout", rom_bytes("breakout"), 40)], tab_rep=tab)
+        pool.reset_all()
+        learner = PAACLearner(pool, arch="NIPS", seed=9, micro_batch=micro)
+        out = learner.train_rollout()
+        got.append(([p.detach().clone() for p in learner.network.parameters()], float(out["loss"]), float(out["global_norm"])))
+        learner.close(); pool.close()
+    (wa, la, ga), (wb, lb, gb) = got
+    assert abs(la - lb) < 1e-4 * max(1.0, abs(la)) and abs(ga - gb) < 1e-3 * max(1.0, abs(ga))
+    for a, b in zip(wa, wb):
+        assert torch.allclose(a, b, rtol=1e-3, atol=1e-5)
