@@ -18,7 +18,7 @@ class PAACLearner(object):
     def __init__(self, pool, arch="NIPS", gamma=0.99, initial_lr=0.0224, lr_annealing_steps=80000000, alpha=0.99, e=0.1,
                  clip_norm=3.0, clip_norm_type="global", max_local_steps=5, entropy_regularisation_strength=0.02,
                  softmax_temp=1.0, mode="multinomial", epsilon=0.05, seed=0, world_envs=None, network=None, explo_policy=None,
-                 on_step=None, micro_batch=16384):
+                 on_step=None, micro_batch=16384, amp=False):
         self.pool, self.device = pool, pool.device
         self.T, self.gamma = int(max_local_steps), float(gamma)
         self.lstm = arch.upper() == "LSTM"
@@ -26,7 +26,7 @@ class PAACLearner(object):
             raise ValueError("the LSTM architecture needs a pool created with history=5 (paac.py:107-112)")
         if network is None:
             network = PolicyVNetwork(arch, pool.num_actions, pool.nb_choices, pool.depth, softmax_temp,
-                                     entropy_regularisation_strength=entropy_regularisation_strength)
+                                     entropy_regularisation_strength=entropy_regularisation_strength, amp=amp)
         self.network = network.to(self.device)
         self.explo_policy, self.on_step = explo_policy, on_step
         # frames per forward / backward chunk: activations of the PWYX stack are ~1.3 MB per frame in fp32, so pools of

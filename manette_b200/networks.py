@@ -53,7 +53,7 @@ class PolicyVNetwork(nn.Module):
     ARCHS = ("NIPS", "NATURE", "PWYX", "LSTM", "BAYESIAN")
 
     def __init__(self, arch, num_actions, nb_choices, depth=1, softmax_temp=1.0, activation="relu", alpha_leaky_relu=0.1,
-                 entropy_regularisation_strength=0.02, keep_percentage=0.9):
+                 entropy_regularisation_strength=0.02, keep_percentage=0.9, amp=False):
         super().__init__()
         arch = arch.upper()
         assert arch in self.ARCHS, arch
@@ -62,6 +62,7 @@ class PolicyVNetwork(nn.Module):
         self.act = _Act(activation, alpha_leaky_relu)
         c = 4 * depth
         self.keep = float(keep_percentage)
+        self.amp = bool(amp)      # bf16 autocast of the convolution stack (the reference computes in fp32: off by default)
         if arch in ("NIPS", "BAYESIAN"):
             self.convs = nn.ModuleList([_conv(c, 16, 8, 4), _conv(16, 32, 4, 2)])
             self.pool_after, flat, hidden = (), 32 * 9 * 9, 256
@@ -92,11 +93,12 @@ class PolicyVNetwork(nn.Module):
 
     def _features(self, x_u8_nhwc):
         x = x_u8_nhwc.permute(0, 3, 1, 2).float().mul_(1.0 / 255.0)          # networks.py:157
-        for i, conv in enumerate(self.convs):
-            x = self.act(_apply_conv(conv, x))
-            if i in self.pool_after:
-                x = F.max_pool2d(x, 2, 2)
-        return x.permute(0, 2, 3, 1).reshape(x.shape[0], -1)                 # flatten in NHWC order like the reference
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp and x.is_cuda):
+            for i, conv in enumerate(self.convs):
+                x = self.act(_apply_conv(conv, x))
+                if i in self.pool_after:
+                    x = F.max_pool2d(x, 2, 2)
+        return x.float().permute(0, 2, 3, 1).reshape(x.shape[0], -1)         # flatten in NHWC order like the reference
 
     def forward(self, states):
         """states: uint8 (N,84,84,4D), or for LSTM the memory (N,5,84,84,4D) oldest -> newest.

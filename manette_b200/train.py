@@ -54,6 +54,7 @@ _FLAGS = [
 _EXTRA = [
     (("--seed",), "seed", 0, int, "key of the counter-based action sampler"),
     (("--envs_per_warp",), "envs_per_warp", 0, int, "emulation kernel layout override (0 = automatic)"),
+    (("--amp",), "amp", False, None, "bf16 autocast of the convolution stack (the reference computes in fp32)"),
     (("--micro_batch",), "micro_batch", 16384, int, "frames per forward/backward slice of the network (memory bound)"),
 ]
 
@@ -88,7 +89,7 @@ def get_network_and_environment_creator(args, explo_policy, random_seed=3):
             "num_actions": args.num_actions, "nb_choices": args.nb_choices, "depth": 3 if args.rgb else 1,
             "softmax_temp": explo_policy.softmax_temp, "activation": args.activation,
             "alpha_leaky_relu": args.alpha_leaky_relu, "keep_percentage": explo_policy.keep_percentage,
-            "entropy_regularisation_strength": args.entropy_regularisation_strength}
+            "entropy_regularisation_strength": args.entropy_regularisation_strength, "amp": bool(getattr(args, "amp", False))}
 
     def network_creator(name="local_learning"):
         net = PolicyVNetwork(**copy.copy(conf))

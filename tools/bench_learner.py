@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--updates", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--micro-batch", type=int, default=16384)
+    ap.add_argument("--amp", action="store_true", help="bf16 autocast of the convolution stack")
+    ap.add_argument("--tf32", action="store_true", help="TF32 matmuls / convolutions")
     a = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
@@ -40,7 +42,11 @@ def main():
                          device=local, env_id_offset=rank * a.envs, history=5 if a.arch.upper() == "LSTM" else 0)
     pool.reset_all()
     torch.manual_seed(0)
-    learner = PAACLearner(pool, arch=a.arch, seed=rank, micro_batch=a.micro_batch)
+    if a.tf32:
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    learner = PAACLearner(pool, arch=a.arch, seed=rank, micro_batch=a.micro_batch, amp=a.amp)
     for _ in range(a.warmup):
         out = learner.train_rollout()
     torch.cuda.synchronize(dev)
@@ -64,7 +70,7 @@ def main():
                           "unit": "frames/s", "n_gpus": world, "arch": a.arch, "game": a.game, "envs_per_gpu": a.envs,
                           "updates": a.updates, "ms_per_update": float(ms) / a.updates, "macro_steps_per_update": learner.T,
                           "agent_steps_per_s": a.updates * learner.T * a.envs * world / (float(ms) / 1e3),
-                          "parameters": n_par, "micro_batch_frames": a.micro_batch, "loss": float(out["loss"]),
+                          "parameters": n_par, "micro_batch_frames": a.micro_batch, "amp": a.amp, "tf32": a.tf32, "loss": float(out["loss"]),
                           "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}))
     learner.close(); pool.close()
     if world > 1:
