@@ -234,10 +234,13 @@ MN_HD MN_INLINE uint32_t nibbles8(uint32_t b) {
   return b;
 }
 // n bytes of `value` at p (any alignment)
-MN_HD MN_INLINE void fill_px(uint8_t* p, int n, uint32_t value) {
+MN_HD MN_NOINLINE void fill_px(uint8_t* p, int n, uint32_t value) {
   const uint32_t v4 = value * 0x01010101u;
+#pragma unroll 1
   while (n > 0 && (reinterpret_cast<uintptr_t>(p) & 3)) { *p++ = uint8_t(value); --n; }
+#pragma unroll 1
   for (; n >= 4; n -= 4, p += 4) *reinterpret_cast<uint32_t*>(p) = v4;
+#pragma unroll 1
   while (n > 0) { *p++ = uint8_t(value); --n; }
 }
 
@@ -293,7 +296,7 @@ MN_HD MN_NOINLINE void tia_render(Ctx& c, int n, int hpos) {
     }
     const uint32_t bk = span & ~(is0 | is1 | is2);
     const uint32_t plane0 = is1 | bk, plane1 = is2 | bk;
-#pragma unroll
+#pragma unroll 1
     for (int b = 0; b < 4; ++b) {   // 8 pixels per round
       const uint32_t sp = (span >> (8 * b)) & 0xFFu;
       if (sp == 0u) continue;
@@ -343,14 +346,14 @@ MN_HD MN_NOINLINE void tia_advance(Ctx& c, int32_t clock) {
 }
 
 
-MN_HD MN_INLINE void tia_refresh_grp(EnvState& s) {
+MN_HD MN_NOINLINE void tia_refresh_grp(EnvState& s) {
   uint32_t g0 = (s.flags & F_VDELP0) ? s.dgrp0 : s.grp0;
   uint32_t g1 = (s.flags & F_VDELP1) ? s.dgrp1 : s.grp1;
   s.cur_grp0 = uint8_t((s.flags & F_REFP0) ? rev8(g0) : g0);
   s.cur_grp1 = uint8_t((s.flags & F_REFP1) ? rev8(g1) : g1);
   s.enabled = uint8_t((s.enabled & ~(EN_P0 | EN_P1)) | (s.cur_grp0 ? EN_P0 : 0) | (s.cur_grp1 ? EN_P1 : 0));
 }
-MN_HD MN_INLINE void tia_refresh_misc(EnvState& s) {
+MN_HD MN_NOINLINE void tia_refresh_misc(EnvState& s) {
   bool bl = (s.flags & F_VDELBL) ? (s.flags & F_DENABL) != 0 : (s.flags & F_ENABL) != 0;
   bool m0 = (s.flags & F_ENAM0) && !(s.flags & F_RESMP0);
   bool m1 = (s.flags & F_ENAM1) && !(s.flags & F_RESMP1);
@@ -613,7 +616,7 @@ MN_HD MN_NOINLINE void riot_poke(Ctx& c, uint32_t addr, uint32_t v) {
 }
 
 // ------------------------------------------------------------------ bus
-MN_HD MN_INLINE void cart_touch(EnvState& s, uint32_t a) {   // a = addr & 0xFFF, banked carts only
+MN_HD MN_NOINLINE void cart_touch(EnvState& s, uint32_t a) {   // a = addr & 0xFFF, banked carts only
   if (s.cart == CART_F8) { if (a == 0xFF8) s.bank = 0; else if (a == 0xFF9) s.bank = 1; }
   else if (s.cart == CART_F6) { if (a >= 0xFF6 && a <= 0xFF9) s.bank = uint8_t(a - 0xFF6); }
   else if (s.cart == CART_E0) {
@@ -711,7 +714,7 @@ MN_HD MN_INLINE uint32_t cpuSP(const Cpu& r) { return r.axys >> 24; }
 MN_HD MN_INLINE void setA(Cpu& r, uint32_t v) { r.axys = (r.axys & 0xFFFFFF00u) | (v & 0xFFu); }
 MN_HD MN_INLINE void setX(Cpu& r, uint32_t v) { r.axys = (r.axys & 0xFFFF00FFu) | ((v & 0xFFu) << 8); }
 MN_HD MN_INLINE void setSP(Cpu& r, uint32_t v) { r.axys = (r.axys & 0x00FFFFFFu) | (v << 24); }
-MN_HD MN_INLINE uint32_t make_segmap(const EnvState& s) {
+MN_HD MN_NOINLINE uint32_t make_segmap(const EnvState& s) {
   // 4K: pages 0..3; F8 / F6: the four pages of the selected 4K bank; 2K: its two pages twice; E0: three 1K slices + page 7
   const uint32_t banked = uint32_t(s.bank) * 0x04040404u + 0x03020100u;   // bank is 0 for 4K
   const uint32_t sliced = uint32_t(s.slice0) | (uint32_t(s.slice1) << 8) | (uint32_t(s.slice2) << 16) | (7u << 24);
@@ -856,6 +859,28 @@ MN_HD MN_INLINE uint32_t stk_pull(Ctx& c, const Mem& mm, Cpu& r) { r.axys += 0x0
 template <bool TRACK>
 MN_HD MN_NOINLINE_DEV uint32_t cpu_special(Ctx& c, const Mem& mm, Cpu& r, uint32_t ax, uint32_t op, uint32_t m, uint32_t ea) {
   uint32_t w = 0;
+  // Stack traffic of the flow / stack opcodes goes through ONE inlined pull and ONE inlined push (the loop keeps
+  // each byte's bus access and their order; what differs per opcode is only how many bytes and what they mean):
+  // the 14 separate stk_pull / stk_push expansions this replaces were 4 KB of the flat loop's instruction footprint.
+  uint32_t pulled = 0, pushv = 0;
+  int npull = 0, npush = 0;
+  switch (op) {
+    case O_RTS: npull = 2; break;
+    case O_RTI: npull = 3; break;
+    case O_PLA: case O_PLP: npull = 1; break;
+    case O_JSR: { const uint32_t ret = (r.PC - 1) & 0xFFFF; pushv = (ret >> 8) | ((ret & 0xFF) << 8); npush = 2; break; }
+    case O_PHA: pushv = cpuA(r); npush = 1; break;
+    case O_PHP: pushv = pack_ps(r.P, r.nz) | 0x10; npush = 1; break;
+    case O_BRK:
+      rd<TRACK>(c, mm, r, r.PC); r.PC = (r.PC + 1) & 0xFFFF; r.P |= 0x10;
+      pushv = (r.PC >> 8) | ((r.PC & 0xFF) << 8) | (pack_ps(r.P, r.nz) << 16); npush = 3;
+      break;
+    default: break;
+  }
+#pragma unroll 1
+  for (int i = 0; i < npull; ++i) pulled |= stk_pull<TRACK>(c, mm, r) << (8 * i);
+#pragma unroll 1
+  for (int i = 0; i < npush; ++i) stk_push<TRACK>(c, mm, r, (pushv >> (8 * i)) & 0xFFu);
   switch (op) {
     case O_ADC: op_adc(r, m); break;
     case O_SBC: op_sbc(r, m); break;
@@ -884,20 +909,16 @@ MN_HD MN_NOINLINE_DEV uint32_t cpu_special(Ctx& c, const Mem& mm, Cpu& r, uint32
     case O_DCP: w = (m - 1) & 0xFF; op_cmp(r, cpuA(r), w); break;
     case O_ISC: w = (m + 1) & 0xFF; op_sbc(r, w); break;
     case O_JMP: r.PC = ea; break;
-    case O_JSR: { const uint32_t ret = (r.PC - 1) & 0xFFFF; stk_push<TRACK>(c, mm, r, ret >> 8); stk_push<TRACK>(c, mm, r, ret & 0xFF); r.PC = ea; break; }
-    case O_RTS: { const uint32_t lo = stk_pull<TRACK>(c, mm, r); const uint32_t hi = stk_pull<TRACK>(c, mm, r); r.PC = ((lo | (hi << 8)) + 1) & 0xFFFF; break; }
-    case O_RTI: { unpack_ps(r, stk_pull<TRACK>(c, mm, r)); const uint32_t lo = stk_pull<TRACK>(c, mm, r); const uint32_t hi = stk_pull<TRACK>(c, mm, r); r.PC = lo | (hi << 8); break; }
+    case O_JSR: r.PC = ea; break;
+    case O_RTS: r.PC = ((pulled & 0xFFFFu) + 1) & 0xFFFF; break;
+    case O_RTI: unpack_ps(r, pulled & 0xFFu); r.PC = (pulled >> 8) & 0xFFFFu; break;
     case O_BRK: {
-      rd<TRACK>(c, mm, r, r.PC); r.PC = (r.PC + 1) & 0xFFFF; r.P |= 0x10;
-      stk_push<TRACK>(c, mm, r, r.PC >> 8); stk_push<TRACK>(c, mm, r, r.PC & 0xFF); stk_push<TRACK>(c, mm, r, pack_ps(r.P, r.nz));
       r.P |= 0x04;
       const uint32_t lo = rd<TRACK>(c, mm, r, 0xFFFE); r.PC = lo | (rd<TRACK>(c, mm, r, 0xFFFF) << 8);
       break;
     }
-    case O_PHA: stk_push<TRACK>(c, mm, r, cpuA(r)); break;
-    case O_PHP: stk_push<TRACK>(c, mm, r, pack_ps(r.P, r.nz) | 0x10); break;
-    case O_PLA: { const uint32_t v = stk_pull<TRACK>(c, mm, r); setA(r, v); r.nz = v; break; }
-    case O_PLP: unpack_ps(r, stk_pull<TRACK>(c, mm, r)); break;
+    case O_PLA: setA(r, pulled); r.nz = pulled; break;
+    case O_PLP: unpack_ps(r, pulled); break;
     case O_FLAG: { const uint32_t mask = 1u << (ax >> 1); r.P = (ax & 1) ? (r.P | mask) : (r.P & ~mask); break; }
     default: break;   // O_KIL, O_NOP
   }
