@@ -234,7 +234,7 @@ MN_HD MN_INLINE uint32_t nibbles8(uint32_t b) {
   return b;
 }
 // n bytes of `value` at p (any alignment)
-MN_HD MN_NOINLINE void fill_px(uint8_t* p, int n, uint32_t value) {
+MN_HD MN_INLINE void fill_px(uint8_t* p, int n, uint32_t value) {
   const uint32_t v4 = value * 0x01010101u;
 #pragma unroll 1
   while (n > 0 && (reinterpret_cast<uintptr_t>(p) & 3)) { *p++ = uint8_t(value); --n; }
@@ -381,9 +381,11 @@ MN_HD MN_INLINE int resp_zone(int nusiz, int oldx, int newx) {
   const int width = (mode == 5) ? 16 : (mode == 7) ? 32 : 8;
   int res = 0;
   // candidates newx and newx+160 cover the table's 0..236 sweep (later assignments win)
+#pragma unroll 1
   for (int k = 0; k < 2; ++k) {
     const int nx = newx + 160 * k;
     if (nx >= 160 + 72 + 5) break;
+#pragma unroll 1
     for (int cidx = 0; cidx < 3; ++cidx) {
       int off;
       switch (mode) {
@@ -472,7 +474,8 @@ MN_HD MN_NOINLINE void tia_apply(Ctx& c, int32_t rel, uint32_t addr, uint32_t v)
     case 0x2A: {
       const int cyc = hpos / 3;
       if (cyc <= 20 || cyc == 75) s.flags |= F_HMBLANK;
-      for (int k = 0; k < 5; ++k) {
+#pragma unroll 1
+      for (int k = 0; k < 5; ++k) {   // (rolled: five copies of hmove_delta were 2 KB of instruction footprint)
         int p = int(s.pos[k]) + hmove_delta(cyc, s.hm[k]);
         if (p >= 160) p -= 160; else if (p < 0) p += 160;
         s.pos[k] = uint8_t(p);
