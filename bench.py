@@ -44,10 +44,10 @@ DEFAULT_WORKLOAD = "ms_pacman_figar10_n16384"
 # must leave in HBM (2 x 33,600) + machine state in and out (2 x (168 + 128)); K3: 2 raw frames read + one plane
 ROUND_BYTES_PER_NEXT = 2 * 33600 + 2 * (168 + 128)
 # ncu --set full, one k_round launch of 16,384 Ms Pacman next() calls (profiles/r1_k_round_summary.txt):
-# dram__bytes_read.sum + dram__bytes_write.sum = 12.5 MB + 1,059.8 MB -> per next(); warp instructions issued per
+# dram__bytes_read.sum + dram__bytes_write.sum = 11.8 MB + 1,060.4 MB -> per next(); warp instructions issued per
 # next() and the share of the kernel's warp-state samples that wait for an instruction fetch
-NCU_ROUND_DRAM_BYTES_PER_NEXT = (12.480256e6 + 1.059751e9) / 16384
-NCU_ROUND_WARP_INST_PER_NEXT = 4546313415 / 16384
+NCU_ROUND_DRAM_BYTES_PER_NEXT = (11.818496e6 + 1.060357e9) / 16384
+NCU_ROUND_WARP_INST_PER_NEXT = 4768749828 / 16384
 # ncu --set full, one k_push_frames launch over 16,384 gray Ms Pacman envs (profiles/r1_k3_push_frames_summary.txt):
 # 705.2 MB read + 105.8 MB written -> per next(): the 126 source rows the nearest map drops are never read
 NCU_K3_DRAM_BYTES_PER_NEXT = (705.19296e6 + 105.80096e6) / 16384
