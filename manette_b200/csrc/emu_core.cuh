@@ -233,7 +233,9 @@ MN_HD MN_INLINE uint32_t nibbles8(uint32_t b) {
   b = (b | (b << 12)) & 0x000F000Fu; b = (b | (b << 6)) & 0x03030303u; b = (b | (b << 3)) & 0x11111111u;
   return b;
 }
-// n bytes of `value` at p (any alignment)
+// n bytes of `value` at p (any alignment).  Stays inline: as an out-of-line function (tried for its instruction
+// footprint, 3 KB) the kernel faults with an illegal / misaligned address on Seaquest, Breakout and Enduro -- cause
+// not found (nvcc 12.9; the callee and its call sites look right in SASS); the loops are rolled instead.
 MN_HD MN_INLINE void fill_px(uint8_t* p, int n, uint32_t value) {
   const uint32_t v4 = value * 0x01010101u;
 #pragma unroll 1
