@@ -179,7 +179,7 @@ MN_HD MN_INLINE uint32_t copies_word(uint32_t pattern, int pos, int mode, bool s
   if (b >= 0) { int p = pos + b; if (p >= 160) p -= 160; m |= place(pattern, p, w); }
   return m;
 }
-MN_HD MN_INLINE uint32_t player_word(uint32_t grp, int nusiz, int pos, bool suppress, int w) {
+MN_HD MN_NOINLINE uint32_t player_word(uint32_t grp, int nusiz, int pos, bool suppress, int w) {
   int mode = nusiz & 7;
   if (mode == 5 || mode == 7) {        // double / quad sized single copy, drawn one pixel late
     if (suppress) return 0u;
@@ -189,7 +189,7 @@ MN_HD MN_INLINE uint32_t player_word(uint32_t grp, int nusiz, int pos, bool supp
   }
   return copies_word(rev8(grp), pos, mode, suppress, w);
 }
-MN_HD MN_INLINE uint32_t missile_word(int nusiz, int pos, int w) {
+MN_HD MN_NOINLINE uint32_t missile_word(int nusiz, int pos, int w) {
   int mode = nusiz & 7;
   uint32_t pattern = (1u << (1 << ((nusiz >> 4) & 3))) - 1u;
   if (mode == 5 || mode == 7) mode = 0;
@@ -233,9 +233,7 @@ MN_HD MN_INLINE uint32_t nibbles8(uint32_t b) {
   b = (b | (b << 12)) & 0x000F000Fu; b = (b | (b << 6)) & 0x03030303u; b = (b | (b << 3)) & 0x11111111u;
   return b;
 }
-// n bytes of `value` at p (any alignment).  Stays inline: as an out-of-line function (tried for its instruction
-// footprint, 3 KB) the kernel faults with an illegal / misaligned address on Seaquest, Breakout and Enduro -- cause
-// not found (nvcc 12.9; the callee and its call sites look right in SASS); the loops are rolled instead.
+// n bytes of `value` at p (any alignment)
 MN_HD MN_INLINE void fill_px(uint8_t* p, int n, uint32_t value) {
   const uint32_t v4 = value * 0x01010101u;
 #pragma unroll 1
@@ -273,7 +271,9 @@ MN_HD MN_NOINLINE void tia_render(Ctx& c, int n, int hpos) {
     const uint32_t m0 = (en & EN_M0) ? (missile_word(s.nusiz0, s.pos[OB_M0], w) & span) : 0u;
     const uint32_t p1 = (en & EN_P1) ? (player_word(s.cur_grp1, s.nusiz1, s.pos[OB_P1], (s.flags & F_SUP1) != 0, w) & span) : 0u;
     const uint32_t m1 = (en & EN_M1) ? (missile_word(s.nusiz1, s.pos[OB_M1], w) & span) : 0u;
-    // collision latches: any common pixel inside the span
+    // collision latches: any common pixel inside the span.  Every pair has a player, missile or ball in it, and most
+    // 32-pixel words hold none of them (playfield only): skip the fifteen tests there
+    if (p0 | m0 | p1 | m1 | bl) {
     cx |= (m0 & p1) ? 0x0001u : 0u; cx |= (m0 & p0) ? 0x0002u : 0u;
     cx |= (m1 & p0) ? 0x0004u : 0u; cx |= (m1 & p1) ? 0x0008u : 0u;
     cx |= (p0 & pf) ? 0x0010u : 0u; cx |= (p0 & bl) ? 0x0020u : 0u;
@@ -281,6 +281,7 @@ MN_HD MN_NOINLINE void tia_render(Ctx& c, int n, int hpos) {
     cx |= (m0 & pf) ? 0x0100u : 0u; cx |= (m0 & bl) ? 0x0200u : 0u;
     cx |= (m1 & pf) ? 0x0400u : 0u; cx |= (m1 & bl) ? 0x0800u : 0u;
     cx |= (bl & pf) ? 0x1000u : 0u; cx |= (p0 & p1) ? 0x2000u : 0u; cx |= (m0 & m1) ? 0x4000u : 0u;
+    }
     if (!pixels) continue;
     const uint32_t g0 = p0 | m0, g1 = p1 | m1, gf = pf | bl;
     uint8_t* o = out + (base - x0);
@@ -407,6 +408,9 @@ MN_HD MN_INLINE int resp_zone(int nusiz, int oldx, int newx) {
   return res;
 }
 
+static_assert(OB_P0 == 0 && OB_M0 == 1 && OB_P1 == 2 && OB_M1 == 3 && OB_BL == 4, "tia_apply's packed object-index tables");
+static_assert(F_REFP1 == F_REFP0 << 1 && F_ENAM1 == F_ENAM0 << 1 && F_ENABL == F_ENAM0 << 2 && F_VDELP1 == F_VDELP0 << 1,
+              "tia_apply shifts these flag bits by the register offset");
 // ---- picture side: apply one queued register write (colour clock `rel` since the start of the frame)
 MN_HD MN_NOINLINE void tia_apply(Ctx& c, int32_t rel, uint32_t addr, uint32_t v) {
   EnvState& s = *c.s;
@@ -428,11 +432,15 @@ MN_HD MN_NOINLINE void tia_apply(Ctx& c, int32_t rel, uint32_t addr, uint32_t v)
       s.ctrlpf = uint8_t(v);
       if (hpos < (68 + 79)) set_flag(s, F_PFREFL, (v & 1) != 0);
       break;
-    case 0x0B: set_flag(s, F_REFP0, (v & 0x08) != 0); tia_refresh_grp(s); break;
-    case 0x0C: set_flag(s, F_REFP1, (v & 0x08) != 0); tia_refresh_grp(s); break;
-    case 0x0D: s.pf = (s.pf & 0x000FFFF0u) | ((v >> 4) & 0x0Fu); tia_refresh_misc(s); break;
-    case 0x0E: s.pf = (s.pf & 0x000FF00Fu) | (v << 4); tia_refresh_misc(s); break;
-    case 0x0F: s.pf = (s.pf & 0x00000FFFu) | (v << 12); tia_refresh_misc(s); break;
+    // (register groups that differ only in a bit position share one body: the 45-case switch was 9 KB of footprint)
+    case 0x0B: case 0x0C: set_flag(s, F_REFP0 << (addr - 0x0B), (v & 0x08) != 0); tia_refresh_grp(s); break;   // REFP0, REFP1
+    case 0x0D: case 0x0E: case 0x0F: {   // PF0 (high nibble), PF1, PF2 -> bits 0..3, 4..11, 12..19
+      const uint32_t field = (addr == 0x0D) ? 0x0000Fu : (addr == 0x0E) ? 0x00FF0u : 0xFF000u;
+      const uint32_t val = (addr == 0x0D) ? ((v >> 4) & 0x0Fu) : (addr == 0x0E) ? (v << 4) : (v << 12);
+      s.pf = (s.pf & 0x000FFFFFu & ~field) | val;
+      tia_refresh_misc(s);
+      break;
+    }
     case 0x10: case 0x11: {
       const int p = (addr == 0x10) ? OB_P0 : OB_P1;
       const int newx = (hpos < MN_HBLANK) ? 3 : ((hpos - MN_HBLANK + 5) % 160);
@@ -442,24 +450,19 @@ MN_HD MN_NOINLINE void tia_apply(Ctx& c, int32_t rel, uint32_t addr, uint32_t v)
       set_flag(s, (p == OB_P0) ? F_SUP0 : F_SUP1, zone >= 0);
       break;
     }
-    case 0x12: s.pos[OB_M0] = uint8_t((hpos < MN_HBLANK) ? 2 : ((hpos - MN_HBLANK + 4) % 160)); break;
-    case 0x13: s.pos[OB_M1] = uint8_t((hpos < MN_HBLANK) ? 2 : ((hpos - MN_HBLANK + 4) % 160)); break;
-    case 0x14: s.pos[OB_BL] = uint8_t((hpos < MN_HBLANK) ? 2 : ((hpos - MN_HBLANK + 4) % 160)); break;
+    case 0x12: case 0x13: case 0x14:   // RESM0, RESM1, RESBL -> OB_M0 (1), OB_M1 (3), OB_BL (4)
+      s.pos[(0x431u >> (4u * (addr - 0x12))) & 7u] = uint8_t((hpos < MN_HBLANK) ? 2 : ((hpos - MN_HBLANK + 4) % 160));
+      break;
     case 0x1B: s.grp0 = uint8_t(v); s.dgrp1 = s.grp1; tia_refresh_grp(s); break;
     case 0x1C:
       s.grp1 = uint8_t(v); s.dgrp0 = s.grp0; set_flag(s, F_DENABL, (s.flags & F_ENABL) != 0);
       tia_refresh_grp(s); tia_refresh_misc(s);
       break;
-    case 0x1D: set_flag(s, F_ENAM0, (v & 2) != 0); tia_refresh_misc(s); break;
-    case 0x1E: set_flag(s, F_ENAM1, (v & 2) != 0); tia_refresh_misc(s); break;
-    case 0x1F: set_flag(s, F_ENABL, (v & 2) != 0); tia_refresh_misc(s); break;
-    case 0x20: s.hm[OB_P0] = uint8_t(v >> 4); break;
-    case 0x21: s.hm[OB_P1] = uint8_t(v >> 4); break;
-    case 0x22: s.hm[OB_M0] = uint8_t(v >> 4); break;
-    case 0x23: s.hm[OB_M1] = uint8_t(v >> 4); break;
-    case 0x24: s.hm[OB_BL] = uint8_t(v >> 4); break;
-    case 0x25: set_flag(s, F_VDELP0, (v & 1) != 0); tia_refresh_grp(s); break;
-    case 0x26: set_flag(s, F_VDELP1, (v & 1) != 0); tia_refresh_grp(s); break;
+    case 0x1D: case 0x1E: case 0x1F: set_flag(s, F_ENAM0 << (addr - 0x1D), (v & 2) != 0); tia_refresh_misc(s); break;   // ENAM0, ENAM1, ENABL
+    case 0x20: case 0x21: case 0x22: case 0x23: case 0x24:   // HMP0, HMP1, HMM0, HMM1, HMBL -> OB_P0 (0), OB_P1 (2), OB_M0 (1), OB_M1 (3), OB_BL (4)
+      s.hm[(0x43120u >> (4u * (addr - 0x20))) & 7u] = uint8_t(v >> 4);
+      break;
+    case 0x25: case 0x26: set_flag(s, F_VDELP0 << (addr - 0x25), (v & 1) != 0); tia_refresh_grp(s); break;   // VDELP0, VDELP1
     case 0x27: set_flag(s, F_VDELBL, (v & 1) != 0); tia_refresh_misc(s); break;
     case 0x28: case 0x29: {
       const bool one = (addr == 0x29);
@@ -940,8 +943,12 @@ MN_HD MN_INLINE void cpu_exec(Ctx& c, const Mem& mm, Cpu& r, const uint32_t pc, 
   const uint32_t len1 = (k >> K_LEN) & 3u;   // length - 1
   // the whole base cycle count is charged right after the opcode fetch (operand fetches from the RIOT see it)
   r.cycles += int32_t((d >> 12) & 15u);
-  if (!fast_code) { if (len1 >= 1) b1 = rd<TRACK>(c, mm, r, (pc + 1) & 0xFFFFu); if (len1 == 2) b2 = rd<TRACK>(c, mm, r, (pc + 2) & 0xFFFFu); }
-  else r.dbus = byte_of(ir | (b1 << 8) | (b2 << 16), len1);
+  if (!fast_code) {   // operand bytes over the bus, one inlined read (rolled: footprint)
+    uint32_t ops = 0;
+#pragma unroll 1
+    for (uint32_t i = 1; i <= len1; ++i) ops |= rd<TRACK>(c, mm, r, (pc + i) & 0xFFFFu) << (8u * i);
+    b1 = (ops >> 8) & 0xFFu; b2 = (ops >> 16) & 0xFFu;
+  } else r.dbus = byte_of(ir | (b1 << 8) | (b2 << 16), len1);
   r.PC = (pc + len1 + 1u) & 0xFFFFu;
   // ---- address phase: zero-page / absolute, optionally indexed, from the operand mask of the entry
   const uint32_t xm = t.x & 0xFFFFu;
@@ -953,8 +960,9 @@ MN_HD MN_INLINE void cpu_exec(Ctx& c, const Mem& mm, Cpu& r, const uint32_t pc, 
     uint32_t p0, p1;
     if (mode == AM_IND) { p0 = b1 | (b2 << 8); p1 = ((p0 & 0xFF) == 0xFF) ? (p0 & 0xFF00u) : ((p0 + 1) & 0xFFFFu); }
     else { p0 = (mode == AM_IZX) ? ((b1 + cpuX(r)) & 0xFFu) : b1; p1 = (p0 + 1) & 0xFFu; }
-    const uint32_t lo = rd<TRACK>(c, mm, r, p0);
-    base = lo | (rd<TRACK>(c, mm, r, p1) << 8);
+    base = 0;
+#pragma unroll 1
+    for (int i = 0; i < 2; ++i) base |= rd<TRACK>(c, mm, r, i ? p1 : p0) << (8 * i);   // pointer low, then high
     ea = (mode == AM_IZY) ? ((base + cpuY(r)) & 0xFFFFu) : base;
   }
   if ((d & D_PAGEPEN) && ((base ^ ea) & 0xFF00u)) r.cycles += 1;
