@@ -47,9 +47,27 @@ enum : uint32_t {
   D_WRITE = 1u << 27    /* write phase: write class, or read-modify-write on memory */,
   D_PAGEPEN = 1u << 28  /* read class, indexed: +1 cycle when the index crosses a page */,
   D_BRANCH = 1u << 29 };
+// Decode entry of the FAST TICK (cpu_fast in emu_core.cuh): the same four words (for the opcodes the fast tick covers
+// that the general datapath does not -- flag ops, JMP, BIT, JSR/RTS, PHA/PLA/PHP/PLP -- k/x/dm are programmed so that
+// the datapath does the right thing, or nothing) plus `f`:
+//   [7:0]  bits of P a flag op rewrites   [15:8] their new value   [18:16] stack pointer change + 2
+//   [20:19] next PC: 0 sequential / branch, 1 effective address (JMP, JSR), 2 pulled pair + 1 (RTS)
+//   FX_* bits below; pad0: branch test (mask over the flag word | invert << 16), zero for everything else
+struct alignas(16) FastEnt { uint32_t k, d, x, dm, f, pad0, pad1, pad2; };
+enum : uint32_t {
+  FX_SPD = 16, FX_PCS = 19,
+  FX_PULL = 1u << 21    /* the read phase reads 0x100 | (SP + 1) */,
+  FX_PUSH = 1u << 22    /* the write phase writes 0x100 | SP */,
+  FX_PAIR_STACK = 1u << 23 /* the byte pair is pulled from the stack (RTS) instead of read through a zero-page pointer */,
+  FX_BIT = 1u << 24, FX_W_RET = 1u << 25 /* write value = return address (JSR: high byte, then low) */,
+  FX_W_PS = 1u << 26    /* write value = packed status | B (PHP) */,
+  FX_PLP = 1u << 27, FX_VALID = 1u << 28, FX_PAIR = 1u << 29 /* reads a byte pair from RIOT RAM: (zp,X) (zp),Y RTS */,
+  FX_PAIR_X = 1u << 30  /* pointer address = operand + X (zp,X) */, FX_PUSH2 = 1u << 31 /* second push (JSR) */ };
 struct Tables {          // read-only, staged in shared memory by the kernels
   TabEnt e[256];
+  FastEnt f[256];
 };
+static_assert(sizeof(TabEnt) == 16 && sizeof(FastEnt) == 32, "fast_entry() addresses Tables::f at byte 4096 + 32 * opcode");
 
 // Control word of the table-driven datapath (TabEnt::k), see cpu_exec.  Operand selectors are byte-permute
 // selectors over the 8 bytes {A, X, Y, SP | M, 0x01, 0xFF, 0x00}, the function selector one over the bytes
@@ -220,6 +238,57 @@ constexpr TabEnt decode_entry(int opc) {
   if (op == O_BRANCH) d |= D_BRANCH;
   const Datapath dp = datapath_control(op, mode);
   TabEnt t = {dp.k, d, (has_ea ? (wide ? 0xFFFFu : 0xFFu) : 0u) | (dp.binv << 16) | (dp.pmask << 24), dp.dm};
+  return t;
+}
+
+// the fast-tick entry of one opcode (FX_VALID clear: the opcode always takes the general path)
+constexpr FastEnt fast_decode_entry(int opc) {
+  const TabEnt g = decode_entry(opc);
+  const uint32_t mode = g.d & 15u, op = (g.d >> 6) & 63u;
+  const uint32_t len1 = (g.k >> K_LEN) & 3u;
+  FastEnt t = {g.k, g.d, g.x, g.dm, 2u << FX_SPD, 0u, 0u, 0u};
+  const uint32_t lenbits = len1 << K_LEN;
+  // what the datapath does for a plain register store / load, borrowed for the stack forms
+  const Datapath sta = datapath_control(O_STA, AM_IMP), lda = datapath_control(O_LDA, AM_IMP);
+  if (g.k & K_GENERIC) {
+    if (mode == AM_IND) return t;
+    t.f |= FX_VALID;
+    if (g.d & D_INDIRECT) {
+      t.f |= FX_PAIR | (mode == AM_IZX ? uint32_t(FX_PAIR_X) : 0u);
+      // (zp),Y: the index is added to the pointer that was read, not to the operand
+      t.k = (t.k & ~(7u << K_ISEL)) | (uint32_t(mode == AM_IZY ? SEL_Y : SEL_ZERO) << K_ISEL);
+      t.x = (t.x & 0xFFFF0000u) | 0xFFFFu;
+    }
+    return t;
+  }
+  if (g.d & D_BRANCH) {
+    // taken <=> ((flag word & mask) != 0) ^ invert; flag word = nz[8:0] | C << 9 | V << 15 (cpu_fast)
+    const uint32_t ax = (g.d >> 16) & 0xFFu, sel = ax >> 6, wanted = ax & 1u;
+    const uint32_t mask = sel == 0u ? 0x180u : sel == 1u ? 0x8000u : sel == 2u ? 0x200u : 0xFFu;
+    // N, V, C: the test reads the flag itself; Z: the test reads "not zero"
+    t.pad0 = mask | ((sel == 3u ? wanted : (wanted ^ 1u)) << 16);
+    t.f |= FX_VALID;
+    return t;
+  }
+  // the rest: neutral datapath unless set below
+  t.k = lenbits | (uint32_t(SEL_ZERO) << K_ISEL) | (uint32_t(SEL_ZERO) << K_ASEL) | (uint32_t(SEL_ZERO) << K_BSEL);
+  t.x = g.x & 0xFFFFu; t.dm = 0u;
+  switch (op) {
+    case O_FLAG: {
+      const uint32_t ax = (g.d >> 16) & 0xFFu, mask = 1u << (ax >> 1);
+      t.f |= FX_VALID | mask | ((ax & 1u) ? (mask << 8) : 0u);
+      break;
+    }
+    case O_JMP: if (mode == AM_ABS) t.f |= FX_VALID | (1u << FX_PCS); break;
+    case O_BIT: t.f |= FX_VALID | FX_BIT; break;
+    case O_JSR: t.f = (0u << FX_SPD) | FX_VALID | (1u << FX_PCS) | FX_PUSH | FX_PUSH2 | FX_W_RET; t.d |= D_WRITE; break;
+    case O_RTS: t.f = (4u << FX_SPD) | FX_VALID | (2u << FX_PCS) | FX_PAIR | FX_PAIR_STACK; break;
+    case O_PHA: t.f = (1u << FX_SPD) | FX_VALID | FX_PUSH; t.d |= D_WRITE; t.k = sta.k | lenbits | (uint32_t(SEL_ZERO) << K_ISEL); break;
+    case O_PHP: t.f = (1u << FX_SPD) | FX_VALID | FX_PUSH | FX_W_PS; t.d |= D_WRITE; break;
+    case O_PLA: t.f = (3u << FX_SPD) | FX_VALID | FX_PULL; t.d |= D_READ; t.k = lda.k | lenbits | (uint32_t(SEL_ZERO) << K_ISEL); t.dm = lda.dm; break;
+    case O_PLP: t.f = (3u << FX_SPD) | FX_VALID | FX_PULL | FX_PLP; t.d |= D_READ; break;
+    default: break;
+  }
   return t;
 }
 

@@ -8,7 +8,7 @@ namespace mn {
 
 inline void build_tables(Tables* t) {
   memset(t, 0, sizeof(*t));
-  for (int opc = 0; opc < 256; ++opc) t->e[opc] = decode_entry(opc);
+  for (int opc = 0; opc < 256; ++opc) { t->e[opc] = decode_entry(opc); t->f[opc] = fast_decode_entry(opc); }
 }
 inline int desc_cycles(uint32_t d) { return int((d >> 12) & 15); }
 

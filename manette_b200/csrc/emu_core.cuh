@@ -25,6 +25,12 @@
 // The product never runs the host build.
 #pragma once
 #include <stdint.h>
+#include <stddef.h>
+#if !defined(__CUDACC__)
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#endif
 #include "cpu_defs.h"
 
 
@@ -107,8 +113,8 @@ struct EnvState {
 struct Ctx {
   EnvState* s;          // working copy (local / shared memory)
   const uint8_t* rom;   // cartridge image (shared memory)
-  uint8_t* ram;         // 128 bytes, byte j at ram[(j >> 2) * ram_stride + (j & 3)]
-  int ram_stride;       // bytes between consecutive 4-byte RAM words of this lane
+  uint8_t* ram;         // the 128 bytes of RIOT RAM (shared memory; lanes are MN_RAM_PITCH bytes apart: an odd
+                        // number of words, so the lanes of a warp that touch the same byte hit 32 different banks)
   uint8_t* fb;          // this env's two frame buffers (global memory), 2 * MN_FRAME_BYTES
   const Tables* tab;
   uint32_t* fifo;       // MN_FIFO_CAP pending TIA writes of this env (shared memory)
@@ -122,7 +128,8 @@ struct Ctx {
 // start of a new frame (bit 0 then says whether that frame keeps its pixels)
 #define MN_FIFO_FRAME 0x80000000u
 
-MN_HD MN_INLINE uint8_t& ram_at(const Ctx& c, int j) { return c.ram[(j >> 2) * c.ram_stride + (j & 3)]; }
+#define MN_RAM_PITCH 132
+MN_HD MN_INLINE uint8_t& ram_at(const Ctx& c, int j) { return c.ram[j]; }
 
 // ------------------------------------------------------------------ small bit helpers
 MN_HD MN_INLINE uint32_t brev32(uint32_t v) {
@@ -681,6 +688,26 @@ MN_HD MN_INLINE TabEnt tab_entry(maddr tab, uint32_t ir) {
   return reinterpret_cast<const TabEnt*>(tab)[ir];
 #endif
 }
+MN_HD MN_INLINE FastEnt fast_entry(maddr tab, uint32_t ir) {   // Tables::f follows Tables::e
+#if defined(__CUDA_ARCH__)
+  const uint4 q = *reinterpret_cast<const uint4*>(mn_smem + tab + 4096u + ir * 32u);
+  const uint2 q2 = *reinterpret_cast<const uint2*>(mn_smem + tab + 4096u + ir * 32u + 16u);
+  FastEnt t; t.k = q.x; t.d = q.y; t.x = q.z; t.dm = q.w; t.f = q2.x; t.pad0 = q2.y; t.pad1 = t.pad2 = 0u; return t;
+#elif defined(__CUDACC__)
+  (void)tab; (void)ir; FastEnt t; t.k = t.d = t.x = t.dm = t.f = t.pad0 = t.pad1 = t.pad2 = 0u; return t;
+#else
+  return reinterpret_cast<const Tables*>(tab)->f[ir];
+#endif
+}
+MN_HD MN_INLINE uint32_t m32(maddr a) {
+#if defined(__CUDA_ARCH__)
+  return *reinterpret_cast<const uint32_t*>(mn_smem + a);
+#elif defined(__CUDACC__)
+  (void)a; return 0u;
+#else
+  return *reinterpret_cast<const uint32_t*>(a);
+#endif
+}
 MN_HD MN_INLINE maddr maddr_of(const void* p) {
 #if defined(__CUDA_ARCH__)
   return maddr(reinterpret_cast<const uint8_t*>(p) - mn_smem);
@@ -702,6 +729,7 @@ struct Cpu {
   uint32_t hot_lo;   // first cartridge offset that may be a bank-switch hot spot ($1000 = none)
   int32_t cycles;
   int32_t clk0;      // EnvState::clk_frame_start (changes only between frames)
+  int32_t cyc0;      // clk0 / 3: the CPU cycle the frame's first scan line began at (WSYNC)
   int32_t fifo_n;    // pending TIA writes; Ctx::fifo_n is brought up to date around every out-of-line call
   bool stop;
   // RAM-dependence probe (TRACK instantiations only): which RIOT RAM bytes the program has written since
@@ -710,10 +738,10 @@ struct Cpu {
   bool tainted;
 };
 // the read-mostly addresses of the fast paths, passed by value so they stay in registers
-struct Mem { maddr rom, ram, tab, fifo; uint32_t ram_stride; };
+struct Mem { maddr rom, ram, tab, fifo, core; };
 MN_HD MN_INLINE Mem mem_of(const Ctx& c) {
   Mem m; m.rom = maddr_of(c.rom); m.ram = maddr_of(c.ram); m.tab = maddr_of(c.tab); m.fifo = maddr_of(c.fifo);
-  m.ram_stride = uint32_t(c.ram_stride); return m;
+  m.core = maddr_of(c.s); return m;
 }
 MN_HD MN_INLINE uint32_t cpuA(const Cpu& r) { return r.axys & 0xFFu; }
 MN_HD MN_INLINE uint32_t cpuX(const Cpu& r) { return (r.axys >> 8) & 0xFFu; }
@@ -731,7 +759,7 @@ MN_HD MN_NOINLINE uint32_t make_segmap(const EnvState& s) {
 // does not touch fifo_n: that one is carried by the flat loop across frames
 MN_HD MN_INLINE void cpu_load(const EnvState& s, Cpu& r) {
   r.axys = uint32_t(s.A) | (uint32_t(s.X) << 8) | (uint32_t(s.Y) << 16) | (uint32_t(s.SP) << 24); r.PC = s.PC; r.P = s.P; r.nz = s.nz; r.dbus = s.dbus;
-  r.cycles = s.cycles; r.clk0 = s.clk_frame_start; r.segmap = make_segmap(s); r.hot_lo = (s.cart > CART_4K) ? 0xFE0u : 0x1000u;
+  r.cycles = s.cycles; r.clk0 = s.clk_frame_start; r.cyc0 = s.clk_frame_start / 3; r.segmap = make_segmap(s); r.hot_lo = (s.cart > CART_4K) ? 0xFE0u : 0x1000u;
   r.stop = (s.flags & F_STOP) != 0;
   r.def_lo = r.def_hi = r.dep_lo = r.dep_hi = 0; r.tainted = false;
 }
@@ -746,8 +774,7 @@ MN_HD MN_INLINE maddr rom_addr(const Mem& mm, uint32_t segmap, uint32_t addr) {
   return mm.rom + ((page << 10) | (addr & 0x3FFu));
 }
 MN_HD MN_INLINE maddr ram_addr(const Mem& mm, uint32_t addr) {
-  const uint32_t j = addr & 0x7Fu;
-  return mm.ram + (j >> 2) * mm.ram_stride + (j & 3u);
+  return mm.ram + (addr & 0x7Fu);
 }
 // the uncommon reads: bank-switch hot spots (the switch happens before the read), TIA, RIOT
 MN_HD MN_NOINLINE uint32_t rd_slow(Ctx& c, uint32_t addr, int32_t cycles, uint32_t dbus) {
@@ -1032,6 +1059,136 @@ MN_HD MN_INLINE void cpu_step(Ctx& c, const Mem& mm, Cpu& r) {
   cpu_exec<TRACK>(c, mm, r, pc, ir, b1, b2, fast_code, tab_entry(mm.tab, ir));
 }
 
+// ------------------------------------------------------------------ the fast tick
+// One 6502 instruction WITHOUT A BRANCH IN IT.  ncu on the general path above (profiles/r1_k_round_*): with one warp
+// per SM sub-partition every conditional branch of the instruction stream costs 14-40 cycles (predicate -> branch
+// latency, refetch at the target, reconvergence), and cpu_step / cpu_exec carry ~14 of them per instruction even
+// when no lane takes any -- 930 of the 2,370 cycles of an average tick.  cpu_fast computes the whole instruction
+// speculatively, in straight-line code, for the cases tools/warp_sim.cpp found to matter (code in cartridge ROM; the
+// table-driven datapath; branches; flag ops; JMP; BIT; (zp,X) / (zp),Y through pointers in RIOT RAM; JSR / RTS / PHA /
+// PLA / PHP / PLP on a stack in RIOT RAM; operands in ROM or RAM; RIOT timer reads that have not underflowed; writes to
+// RAM, to the TIA write FIFO, and the WSYNC strobe), decides at the end whether every assumption held, and only then
+// commits.  Loads are always issued (their addresses are safe whatever the lane's state), stores are predicated.
+// A lane for which an assumption failed changes nothing and takes cpu_step: the general path is the definition, and
+// tests/ check on the host build that both agree on every instruction of every game (he_set_fast_mode(2)).
+template <bool TRACK>
+MN_HD MN_INLINE bool cpu_fast(const Mem& mm, Cpu& r, const bool go) {
+  if (TRACK) return false;   // the RAM-dependence probe instruments the general path only
+  // (conditions are 0 / 1 words combined with & and |: `&&` / `||` invite the compiler to branch)
+  const uint32_t pc = r.PC;
+  const uint32_t code_ok = uint32_t((pc & 0x1000u) != 0u) & uint32_t((pc & 0xFFFu) < 0xFDEu) & uint32_t((pc & 0x3FFu) < 0x3FEu);
+  const maddr ca = rom_addr(mm, r.segmap, pc);
+  const uint32_t ir = m8(ca), b1 = m8(ca + 1u), b2 = m8(ca + 2u);
+  const FastEnt t = fast_entry(mm.tab, ir);
+  const uint32_t k = t.k, d = t.d, f = t.f;
+  const uint32_t len1 = (k >> K_LEN) & 3u;
+  int32_t cyc = r.cycles + int32_t((d >> 12) & 15u);
+  const uint32_t seq = (pc + len1 + 1u) & 0xFFFFu;
+  const uint32_t sp = r.axys >> 24;
+  // ---- a byte pair from RIOT RAM: the pointer of (zp,X) / (zp),Y, or the return address RTS pulls
+  const uint32_t p0 = (f & FX_PAIR_STACK) ? ((sp + 1u) & 0xFFu) : ((b1 + ((f & FX_PAIR_X) ? cpuX(r) : 0u)) & 0xFFu);
+  const uint32_t p1 = (p0 + 1u) & 0xFFu;
+  const uint32_t pair_ok = uint32_t((f & FX_PAIR) == 0u) | ((p0 & p1) >> 7);
+  const uint32_t phi = m8(ram_addr(mm, p1));
+  const uint32_t pair = m8(ram_addr(mm, p0)) | (phi << 8);
+  // ---- address phase
+  const uint32_t xm = t.x & 0xFFFFu;
+  const uint32_t idx = perm8(r.axys, 0u, ((k >> K_ISEL) & 7u) | 0x7770u);
+  const bool through_ptr = (f & (FX_PAIR | FX_PAIR_STACK)) == FX_PAIR;
+  const uint32_t base = through_ptr ? pair : ((b1 | (b2 << 8)) & xm);
+  const uint32_t ea = (base + idx) & xm;
+  cyc += int32_t(uint32_t((d & D_PAGEPEN) != 0u) & uint32_t(((base ^ ea) & 0xFF00u) != 0u));
+  // ---- read phase: cartridge ROM away from the hot spots, RIOT RAM, or the RIOT timer before it underflows
+  const uint32_t ra = (f & FX_PULL) ? (0x100u | ((sp + 1u) & 0xFFu)) : ea;
+  const bool r_rom = (ra & 0x1000u) != 0u;
+  const uint32_t r_mem = r_rom ? uint32_t((ra & 0xFFFu) < r.hot_lo) : uint32_t((ra & 0x0280u) == 0x0080u);
+  const bool r_tim = (ra & 0x1285u) == 0x0284u;
+  const uint32_t mv = m8(r_rom ? rom_addr(mm, r.segmap, ra) : ram_addr(mm, ra));
+  const uint32_t tw = m32(mm.core + uint32_t(offsetof(EnvState, timer)));   // timer | tshift << 8 (riot_peek)
+  const int32_t tsc = int32_t(m32(mm.core + uint32_t(offsetof(EnvState, timer_set_cycle))));
+  const uint32_t delta = uint32_t((cyc - 1) - tsc);
+  const int32_t tv = int32_t(tw & 0xFFu) - int32_t(delta >> ((tw >> 8) & 0xFFu)) - 1;
+  const bool has_read = (d & D_READ) != 0u;
+  const uint32_t r_ok = uint32_t(!has_read) | r_mem | (uint32_t(r_tim) & uint32_t(tv >= 0));
+  const uint32_t m = has_read ? (r_tim ? (uint32_t(tv) & 0xFFu) : mv) : b1;
+  // ---- operate phase: the datapath of cpu_exec (nothing is masked off here: the entries of opcodes it does not
+  // serve have empty commit masks)
+  const uint32_t s2 = m | 0x00FF0100u;
+  const uint32_t a = perm8(r.axys, s2, (k & 7u) | 0x7770u);
+  const uint32_t b = perm8(r.axys, s2, ((k >> K_BSEL) & 7u) | 0x7770u) ^ ((t.x >> 16) & 0xFFu);
+  const uint32_t carry = r.P & 1u;
+  const uint32_t cin = ((k >> K_CSEL) & 1u) | ((k >> (K_CSEL + 1)) & carry);
+  const uint32_t sum = a + b + cin;
+  const uint32_t rot = (k >> 11) & carry;
+  const uint32_t left = (a << 1) | rot;
+  const uint32_t right = ((a | (rot << 8)) >> 1) | ((a & 1u) << 8);
+  const uint32_t lo_sum_or = perm8(sum, a | b, 0x7740u), lo_and_xor = perm8(a & b, a ^ b, 0x7740u);
+  const uint32_t fn_pool0 = perm8(lo_sum_or, lo_and_xor, 0x5410u);
+  const uint32_t fn_pool1 = perm8(left, right, 0x7740u);
+  const uint32_t res = perm8(fn_pool0, fn_pool1, ((k >> K_FN) & 7u) | 0x7770u);
+  const uint32_t c_pool = perm8(perm8(sum, left, 0x7751u), right, 0x7510u);
+  const uint32_t cout = perm8(c_pool, 0u, ((k >> K_CSRC) & 3u) | 0x4440u);
+  const uint32_t vbit = ((~(a ^ b)) & (a ^ sum) & 0x80u) >> 1;
+  const uint32_t pm = t.x >> 24;
+  uint32_t P = (r.P & ~pm) | ((cout | vbit) & pm);
+  uint32_t nz = (k & K_NZ) ? res : r.nz;
+  // BIT, PLP, flag ops (mutually exclusive, each a couple of selects)
+  const uint32_t nz_hi = (m & 0x80u) << 1;
+  nz = (f & FX_BIT) ? (nz_hi | uint32_t((cpuA(r) & m) != 0u)) : nz;
+  P = (f & FX_BIT) ? ((P & ~0x40u) | (m & 0x40u)) : P;
+  nz = (f & FX_PLP) ? (nz_hi | (((m >> 1) & 1u) ^ 1u)) : nz;
+  P = (f & FX_PLP) ? (m & 0x5Du) : P;
+  P = (P & ~(f & 0xFFu)) | ((f >> 8) & 0xFFu);
+  uint32_t axys = (r.axys & ~t.dm) | ((res * 0x01010101u) & t.dm);
+  axys += (((f >> FX_SPD) & 7u) - 2u) << 24;
+  // ---- branches: one mask test over {Z: nz[7:0], N: nz[8:7], C: bit 9, V: bit 15} (FastEnt::pad0: mask | invert << 16)
+  const uint32_t flagw = (r.nz & 0x1FFu) | ((r.P & 0x41u) << 9);
+  const uint32_t taken = uint32_t((flagw & t.pad0 & 0xFFFFu) != 0u) ^ (t.pad0 >> 16);
+  const uint32_t target = (seq + uint32_t(int32_t(int8_t(b1)))) & 0xFFFFu;
+  // ---- write phase: RIOT RAM, the TIA write FIFO (registers $04-$2C before the scan-line overflow point), WSYNC
+  const uint32_t wa = (f & FX_PUSH) ? (0x100u | sp) : ea;
+  const uint32_t ret = (seq - 1u) & 0xFFFFu;
+  const uint32_t ps = 0x30u | (r.P & 0x5Du) | ((r.nz & 0x180u) ? 0x80u : 0u) | ((r.nz & 0xFFu) ? 0u : 0x02u);   // pack_ps | B
+  uint32_t wv = res & 0xFFu;
+  wv = (f & FX_W_RET) ? (ret >> 8) : wv;
+  wv = (f & FX_W_PS) ? ps : wv;
+  const bool has_write = (d & D_WRITE) != 0u;
+  const uint32_t w_ram = uint32_t((wa & 0x1280u) == 0x0080u);
+  const uint32_t w_tia = uint32_t((wa & 0x1080u) == 0u);
+  const uint32_t a6 = wa & 0x3Fu;
+  const int32_t rel = cyc * 3 - r.clk0;
+  const uint32_t rel_ok = uint32_t(rel < 228 * (MN_MAX_SCANLINES + 1));
+  const uint32_t w_fifo = w_tia & uint32_t(a6 >= 0x04u) & rel_ok & uint32_t(r.fifo_n < MN_FIFO_CAP);
+  const uint32_t w_sync = w_tia & uint32_t(a6 == 0x02u) & rel_ok;
+  const uint32_t w_ok = uint32_t(!has_write) | w_ram | w_fifo | w_sync;
+  const uint32_t w2_ok = uint32_t((f & FX_PUSH2) == 0u) | ((sp - 1u) >> 7 & 1u);
+  const int32_t rest = 76 - ((cyc - r.cyc0) % 76);   // tia_poke: WSYNC holds the 6502 until the end of the scan line
+  // ---- all assumptions held?
+  const uint32_t dec_ok = uint32_t((k & K_DECIMAL) == 0u) | uint32_t((r.P & 0x08u) == 0u);
+  const bool fast = (uint32_t(go) & code_ok & (f >> 28) & dec_ok & pair_ok & r_ok & w_ok & w2_ok & 1u) != 0u;
+  // ---- commit (the stores are predicated; the rest is register moves)
+  const bool do_write = fast & has_write;
+  if (do_write & (w_ram != 0u)) m8w(ram_addr(mm, wa), wv);
+  if (do_write & ((f & FX_PUSH2) != 0u)) m8w(ram_addr(mm, 0x100u | ((sp - 1u) & 0xFFu)), ret & 0xFFu);
+  const bool queued = do_write & (w_ram == 0u) & (w_fifo != 0u) & (a6 <= 0x2Cu) & !((a6 >= 0x15u) & (a6 <= 0x1Au));
+  if (queued) m32w(mm.fifo + uint32_t(r.fifo_n) * 4u, uint32_t(rel) | (a6 << 17) | (wv << 23));
+  if (fast) {
+    uint32_t dbus = byte_of(ir | (b1 << 8) | (b2 << 16), len1);
+    dbus = (f & FX_PAIR) ? phi : dbus;
+    dbus = has_read ? m : dbus;
+    dbus = has_write ? ((f & FX_PUSH2) ? (ret & 0xFFu) : wv) : dbus;
+    cyc += (has_write & (w_ram == 0u) & (w_sync != 0u) & (rest < 76)) ? rest : 0;
+    cyc += taken ? (((seq ^ target) & 0xFF00u) ? 2 : 1) : 0;
+    const uint32_t pcs = (f >> FX_PCS) & 3u;
+    uint32_t npc = taken ? target : seq;
+    npc = (pcs == 1u) ? ea : npc;
+    npc = (pcs == 2u) ? ((pair + 1u) & 0xFFFFu) : npc;
+    r.PC = npc; r.cycles = cyc; r.P = P; r.nz = nz; r.axys = axys; r.dbus = dbus;
+    r.fifo_n += queued ? 1 : 0;
+  }
+  return fast;
+}
+
 
 // ------------------------------------------------------------------ frame
 // program side of the emulated TIA's frame start: rebase every cycle-stamped quantity, tell the picture
@@ -1307,8 +1464,52 @@ MN_HD MN_INLINE bool hot_has_work(const Hot& h) { return h.in_frame || h.more; }
 // are scan-line structured (WSYNC), so lanes kept together in time mostly sit at the same program counter.
 MN_HD MN_INLINE int32_t hot_time(const Hot& h) { return h.in_frame ? ((h.jobs << 16) + h.cpu.cycles) : ((h.jobs + 1) << 16); }
 // one tick: start the next job, or run one instruction of the frame in progress
+#if !defined(__CUDACC__)
+// host test build only: 0 = general path only, 1 = fast tick first (what the kernels do), 2 = run both on every
+// instruction the fast tick accepts and abort on the first difference
+static int g_fast_mode = 1;
+static unsigned long long g_fast_taken = 0, g_fast_refused = 0;
+// one instruction the way the kernels run it (mode 1), or with the fast tick checked against the general path (mode 2);
+// returns false if the general path has to run it
+static inline bool cpu_fast_host(Ctx& c, const Mem& mm, Cpu& r) {
+  if (g_fast_mode == 0) return false;
+  if (g_fast_mode == 1) return cpu_fast<false>(mm, r, true);
+  const Cpu before = r;
+  const EnvState s_before = *c.s;
+  uint8_t ram0[128], ram1[128]; uint32_t fifo0[MN_FIFO_CAP], fifo1[MN_FIFO_CAP];
+  for (int j = 0; j < 128; ++j) ram0[j] = ram_at(c, j);
+  for (int j = 0; j < MN_FIFO_CAP; ++j) fifo0[j] = c.fifo[j];
+  if (!cpu_fast<false>(mm, r, true)) { ++g_fast_refused; return false; }
+  const Cpu fast = r;
+  for (int j = 0; j < 128; ++j) { ram1[j] = ram_at(c, j); ram_at(c, j) = ram0[j]; }
+  for (int j = 0; j < MN_FIFO_CAP; ++j) { fifo1[j] = c.fifo[j]; c.fifo[j] = fifo0[j]; }
+  r = before;
+  cpu_step<false>(c, mm, r);
+  const Cpu& g = r;
+  bool same = g.axys == fast.axys && g.PC == fast.PC && g.P == fast.P && g.nz == fast.nz && g.dbus == fast.dbus && g.cycles == fast.cycles &&
+              g.fifo_n == fast.fifo_n && g.segmap == fast.segmap && g.stop == before.stop;
+  for (int j = 0; j < 128; ++j) same = same && ram_at(c, j) == ram1[j];
+  for (int j = 0; j < g.fifo_n && j < MN_FIFO_CAP; ++j) same = same && c.fifo[j] == fifo1[j];
+  EnvState sa = *c.s, sb = s_before;
+  sa.cycles = sb.cycles = 0; sa.dbus = sb.dbus = 0;   // scratch copies the slow bus functions leave behind
+  same = same && memcmp(&sa, &sb, sizeof(EnvState)) == 0;
+  if (!same) {
+    fprintf(stderr, "cpu_fast != cpu_step at PC %04x: axys %08x/%08x PC %04x/%04x P %02x/%02x nz %03x/%03x dbus %02x/%02x cycles %d/%d fifo %d/%d\n",
+            before.PC, fast.axys, g.axys, fast.PC, g.PC, fast.P, g.P, fast.nz, g.nz, fast.dbus, g.dbus, fast.cycles, g.cycles, fast.fifo_n, g.fifo_n);
+    abort();
+  }
+  ++g_fast_taken;
+  return true;
+}
+#endif
 template <bool TRACK>
-MN_HD MN_INLINE void unit_tick(Ctx& c, const Mem& mm, Unit& u, Hot& h) {
+MN_HD MN_INLINE void unit_tick(Ctx& c, const Mem& mm, Unit& u, Hot& h, const bool elig = true) {
+#if !defined(__CUDACC__)
+  if (!TRACK && elig && h.in_frame && h.budget > 1 && cpu_fast_host(c, mm, h.cpu)) { --h.budget; return; }
+#else
+  if (cpu_fast<TRACK>(mm, h.cpu, elig && h.in_frame && h.budget > 1)) { --h.budget; return; }
+#endif
+  if (!elig) return;
   if (!h.in_frame) {
     c.fifo_n = h.cpu.fifo_n;
     unit_job_begin(c, u);

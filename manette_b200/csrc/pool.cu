@@ -199,8 +199,8 @@ __global__ void k_single_list(PoolDev p, int which, int env, int ale_action) {
 }
 
 // One round of emulation for the envs on list `in`.  Dynamic shared memory:
-//   [rom | tables | core slots (8 warps x slots x 43 words) | ram (8 warps x slots x 128 B, word-interleaved)
-//    | TIA write FIFOs (8 warps x slots x 17 words)]
+//   [rom | tables | core slots (4 warps x slots x 43 words) | ram (4 warps x slots x 132 B: 128 used, odd word pitch)
+//    | TIA write FIFOs (4 warps x slots x 17 words)]
 template <bool TRACK>
 __global__ void __launch_bounds__(MN_THREADS, 2) k_round(PoolDev p, int mode, int in, int out) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(MN_THREADS, 2) k_round(PoolDev p, int mode, in
   Tables* s_tab = reinterpret_cast<Tables*>(smem + rom_bytes);
   uint32_t* s_core = reinterpret_cast<uint32_t*>(smem + rom_bytes + sizeof(Tables));
   uint8_t* s_ram = reinterpret_cast<uint8_t*>(s_core + nslots * MN_CORE_WORDS);
-  uint32_t* s_fifo = reinterpret_cast<uint32_t*>(s_ram + nslots * 128);
+  uint32_t* s_fifo = reinterpret_cast<uint32_t*>(s_ram + nslots * MN_RAM_PITCH);
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.roms + G.rom_off);
     uint4* dst = reinterpret_cast<uint4*>(s_rom);
@@ -240,8 +240,7 @@ __global__ void __launch_bounds__(MN_THREADS, 2) k_round(PoolDev p, int mode, in
   EnvState* s = reinterpret_cast<EnvState*>(s_core + slot * MN_CORE_WORDS);
   Ctx c;
   c.s = s; c.rom = s_rom; c.tab = s_tab;
-  c.ram = s_ram + warp * p.slots * 128 + lane * 4;
-  c.ram_stride = p.slots * 4;
+  c.ram = s_ram + slot * MN_RAM_PITCH;
   c.fb = p.frames + size_t(e) * (2 * MN_FRAME_BYTES);
   c.fifo = s_fifo + slot * (MN_FIFO_CAP + 1);
   c.fifo_n = 0;
@@ -274,7 +273,7 @@ __global__ void __launch_bounds__(MN_THREADS, 2) k_round(PoolDev p, int mode, in
 #pragma unroll 6
       for (int i = 0; i < int(sizeof(EnvState) / 4); ++i) dst[i] = src[i];
       const uint32_t* rsrc = reinterpret_cast<const uint32_t*>(p.ram + size_t(e) * 128);
-      for (int i = 0; i < 32; ++i) *reinterpret_cast<uint32_t*>(c.ram + i * c.ram_stride) = rsrc[i];
+      for (int i = 0; i < 32; ++i) *reinterpret_cast<uint32_t*>(c.ram + i * 4) = rsrc[i];
       if (mode == ROUND_POWER_ON) { s->game = uint8_t(G.game_id); s->cart = uint8_t(G.cart); s->ctrl = uint8_t(G.ctrl); s->host_lives = 0; }
       c.all_pixels = (attempt == 1) || (p.draw_all_frames != 0);
       unit_init(c, u, kind, action, ucount, seed);
@@ -287,13 +286,17 @@ __global__ void __launch_bounds__(MN_THREADS, 2) k_round(PoolDev p, int mode, in
       hot.tainted = (t[4] & 1ull) != 0; hot.obs_bad = (t[4] & 2ull) != 0;
     }
     const Mem mm = mem_of(c);
+    // One warp-wide reduction per tick carries all three decisions: the emulated time of the lane furthest behind
+    // (lanes within sync_slack of it run), "some lane's TIA write FIFO is nearly full" (-1: every lane drains; the
+    // rendering path is entered by all lanes together) and "no lane has work left" (INT_MAX).
     for (;;) {
       const bool work = hot_has_work(hot);
-      const int now = work ? hot_time(hot) : 0x7FFFFFFF;
+      int now = work ? hot_time(hot) : 0x7FFFFFFF;
+      if (hot.cpu.fifo_n >= MN_FIFO_HIGH) now = -1;
       const int first = __reduce_min_sync(wmask, now);
+      if (first < 0) { hot_drain(c, hot); continue; }
       if (first == 0x7FFFFFFF) break;
-      if (work && now - first <= p.sync_slack) unit_tick<TRACK>(c, mm, u, hot);
-      if (__any_sync(wmask, hot.cpu.fifo_n >= MN_FIFO_HIGH)) hot_drain(c, hot);
+      unit_tick<TRACK>(c, mm, u, hot, work && now - first <= p.sync_slack);
     }
     if (mine) {
       bad = unit_finish(c, hot); res = u; atomicAdd(p.total_instr, (unsigned long long)hot.instr);
@@ -345,7 +348,7 @@ __global__ void __launch_bounds__(MN_THREADS, 2) k_round(PoolDev p, int mode, in
 #pragma unroll 6
     for (int i = 0; i < int(sizeof(EnvState) / 4); ++i) dst[i] = src[i];
     uint32_t* rd = reinterpret_cast<uint32_t*>(p.ram + size_t(e) * 128);
-    for (int i = 0; i < 32; ++i) rd[i] = *reinterpret_cast<uint32_t*>(c.ram + i * c.ram_stride);
+    for (int i = 0; i < 32; ++i) rd[i] = *reinterpret_cast<uint32_t*>(c.ram + i * 4);
   }
 }
 
@@ -973,7 +976,7 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
   }
   h->round_grid = blk;
   h->round_smem = ((max_rom + 15) & ~size_t(15)) + sizeof(Tables) +
-                  size_t(MN_WARPS_PER_BLOCK) * slots * (MN_CORE_WORDS * 4 + 128 + (MN_FIFO_CAP + 1) * 4);
+                  size_t(MN_WARPS_PER_BLOCK) * slots * (MN_CORE_WORDS * 4 + MN_RAM_PITCH + (MN_FIFO_CAP + 1) * 4);
   if (h->round_smem > size_t(prop.sharedMemPerBlockOptin)) { delete h; return fail("mn_create: shared memory budget exceeded"); }
   // the attribute belongs to the function, not to this pool: several pools with different needs may coexist
   CU(cudaFuncSetAttribute(k_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(prop.sharedMemPerBlockOptin)));

@@ -31,8 +31,9 @@ static void run_unit(HostEnv* e, int kind, int action, int count, uint32_t seed,
     Hot hot;
     hot_init(u, hot);
     const Mem mm = mem_of(e->c);
+    // resets run the RAM-dependence probe (k_round<true>, general path only); everything else the kernels' flow
     while (hot_has_work(hot)) {
-      unit_tick<true>(e->c, mm, u, hot);
+      if (kind == U_ACTS) unit_tick<false>(e->c, mm, u, hot); else unit_tick<true>(e->c, mm, u, hot);
       if (hot.cpu.fifo_n >= e->drain_at) hot_drain(e->c, hot);
     }
     const bool bad = unit_finish(e->c, hot);
@@ -51,10 +52,11 @@ void* he_create(const uint8_t* rom, int n, const char* game, uint32_t seed, int 
   memset(&e->s, 0, sizeof(e->s));
   build_tables(&e->tab);
   e->rom.assign(rom, rom + n);
+  e->rom.resize(size_t(n) + 16, 0);   // the fast tick fetches operand bytes speculatively (up to 2 bytes past the image)
   e->fb.assign(2 * MN_FRAME_BYTES, 0);
   int g = game_id_from_name(game);
   e->s.game = (uint8_t)g; e->s.cart = (uint8_t)detect_cart(rom, n); e->s.ctrl = (uint8_t)game_db(g).ctrl;
-  e->c.s = &e->s; e->c.rom = e->rom.data(); e->c.ram = e->ram; e->c.ram_stride = 4; e->c.fb = e->fb.data(); e->c.tab = &e->tab;
+  e->c.s = &e->s; e->c.rom = e->rom.data(); e->c.ram = e->ram; e->c.fb = e->fb.data(); e->c.tab = &e->tab;
   e->c.fifo = e->fifo; e->c.fifo_n = 0;
   e->drain_at = MN_FIFO_HIGH; e->redo_count = 0;
   run_unit(e, U_POWER_ON, 0, 0, seed, !skip_frames);
@@ -91,9 +93,10 @@ void* he_console_create(const uint8_t* rom, int n) {
   memset(e->ram, 0, 128);
   build_tables(&e->tab);
   e->rom.assign(rom, rom + n);
+  e->rom.resize(size_t(n) + 16, 0);   // the fast tick fetches operand bytes speculatively (up to 2 bytes past the image)
   e->fb.assign(2 * MN_FRAME_BYTES, 0);
   e->s.game = 0; e->s.cart = (uint8_t)detect_cart(rom, n); e->s.ctrl = 0;
-  e->c.s = &e->s; e->c.rom = e->rom.data(); e->c.ram = e->ram; e->c.ram_stride = 4; e->c.fb = e->fb.data(); e->c.tab = &e->tab;
+  e->c.s = &e->s; e->c.rom = e->rom.data(); e->c.ram = e->ram; e->c.fb = e->fb.data(); e->c.tab = &e->tab;
   e->c.fifo = e->fifo; e->c.fifo_n = 0; e->c.all_pixels = true;
   e->drain_at = MN_FIFO_HIGH; e->redo_count = 0;
   e->s.swcha = 0xFF; e->s.swchb = 0x3F; e->s.flags = F_INPT4 | F_INPT5;
@@ -111,13 +114,16 @@ void he_console_step(void* h, int n_instr) {
   r.fifo_n = e->c.fifo_n;
   const Mem mm = mem_of(e->c);
   for (int i = 0; i < n_instr; ++i) {
-    cpu_step<false>(e->c, mm, r);
+    if (!cpu_fast_host(e->c, mm, r)) cpu_step<false>(e->c, mm, r);
     if (r.fifo_n >= e->drain_at) { e->c.fifo_n = r.fifo_n; tia_drain(e->c); r.fifo_n = 0; }
   }
   e->c.fifo_n = r.fifo_n;
   tia_drain(e->c);
   cpu_store(e->s, r);
 }
+// 0 = general path only, 1 = fast tick first (the kernels' flow), 2 = both on every instruction, abort on a difference
+void he_set_fast_mode(int mode) { g_fast_mode = mode; }
+void he_fast_stats(uint64_t* out2) { out2[0] = g_fast_taken; out2[1] = g_fast_refused; }
 int he_state_size() { return (int)sizeof(EnvState); }
 void he_get_state(void* h, uint8_t* out) { memcpy(out, &((HostEnv*)h)->s, sizeof(EnvState)); }
 // 1 if the last reset never read a RAM byte before writing it and had written all 128 before the settings reset

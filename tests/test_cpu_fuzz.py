@@ -28,9 +28,13 @@ def _mk_rom(seed, size, bias):
     return rom
 
 
+@pytest.mark.parametrize("fast_mode", [1, 2, 0])
 @pytest.mark.parametrize("size,bias", [(2048, True), (4096, True), (4096, False), (8192, True), (16384, True)])
-def test_random_cartridges(libs, size, bias):
+def test_random_cartridges(libs, size, bias, fast_mode):
+    """fast_mode: 1 = the kernels' flow (fast tick first), 2 = fast tick checked against the general path on every
+    instruction it accepts, 0 = general path only."""
     L, H = libs
+    H.he_set_fast_mode(fast_mode)
     L.orc_console_create.restype = C.c_void_p
     H.he_console_create.restype = C.c_void_p
     H.he_console_create.argtypes = [C.c_char_p, C.c_int]
@@ -57,3 +61,4 @@ def test_random_cartridges(libs, size, bias):
         L.orc_get_screen(o, so.ctypes.data); H.he_get_screen(h, sh.ctypes.data)
         assert np.array_equal(so, sh), (size, seed, "screen")
         L.orc_destroy(o); H.he_destroy(h)
+    H.he_set_fast_mode(1)

@@ -123,3 +123,58 @@ def test_next_with_pixel_less_frames_matches_oracle(libs, game):
             L.orc_get_both_screens(o, oboth.ctypes.data)
             assert np.array_equal(both, oboth), (game, i, "both frame buffers after reset")
     L.orc_destroy(o); H.he_destroy(h)
+
+
+@pytest.mark.parametrize("game", GAMES12)
+def test_fast_tick_equals_general_path(libs, game):
+    """cpu_fast (the branch-free tick the kernels try first) against cpu_step (the general path, the definition) on
+    EVERY instruction the fast tick accepts: registers, status, cycles, data bus, RIOT RAM, the TIA write FIFO and the
+    untouched rest of the machine.  The host build aborts on the first difference (he_set_fast_mode(2))."""
+    L, H = libs
+    H.he_fast_stats.argtypes = [C.c_void_p]
+    rom = rom_bytes(game)
+    H.he_set_fast_mode(2)
+    try:
+        h = H.he_create(rom, len(rom), game.encode(), 11, 1)
+        n = L.orc_num_actions(L.orc_create(rom, len(rom), game.encode(), 11))
+        acts = np.zeros(18, np.int32)
+        o = L.orc_create(rom, len(rom), game.encode(), 11)
+        L.orc_minimal_actions(o, acts.ctypes.data)
+        L.orc_destroy(o)
+        rng = np.random.RandomState(5)
+        s0 = np.zeros(2, np.uint64); H.he_fast_stats(s0.ctypes.data)
+        for i in range(120):
+            H.he_next(h, int(acts[rng.randint(n)]), 1, None)
+            if H.he_game_over(h):
+                H.he_reset_game(h, int(rng.randint(0, 31)), 1)
+        s1 = np.zeros(2, np.uint64); H.he_fast_stats(s1.ctypes.data)
+        taken, refused = int(s1[0] - s0[0]), int(s1[1] - s0[1])
+        assert taken > 1000000 and refused < 0.08 * taken, (game, taken, refused)   # the fast tick is the common case
+        H.he_destroy(h)
+    finally:
+        H.he_set_fast_mode(1)
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_general_path_alone_and_checked_fast_tick_match_oracle(libs, mode):
+    """The oracle comparison of test_every_frame_matches_oracle with the fast tick switched off (mode 0: the general
+    path must stay exact on its own -- it is what refused instructions and the reset probe run) and in checked mode."""
+    L, H = libs
+    H.he_set_fast_mode(mode)
+    try:
+        for game in ("breakout", "ms_pacman", "montezuma_revenge"):
+            rom = rom_bytes(game)
+            o = L.orc_create(rom, len(rom), game.encode(), 4)
+            h = H.he_create(rom, len(rom), game.encode(), 4, 0)
+            n = L.orc_num_actions(o)
+            acts = np.zeros(18, np.int32)
+            L.orc_minimal_actions(o, acts.ctypes.data)
+            rng = np.random.RandomState(3)
+            for i in range(160):
+                a = int(acts[rng.randint(n)])
+                assert L.orc_act(o, a) == H.he_act(h, a), (game, i)
+                (ro, so, co), (rh, sh, ch) = _taps(L, H, o, h)
+                assert np.array_equal(ro, rh) and np.array_equal(so, sh) and np.array_equal(co, ch), (game, i, mode)
+            L.orc_destroy(o); H.he_destroy(h)
+    finally:
+        H.he_set_fast_mode(1)
