@@ -1456,6 +1456,11 @@ MN_HD MN_NOINLINE void unit_job_begin(Ctx& c, Unit& u) {
 }
 MN_HD MN_INLINE void hot_init(const Unit& u, Hot& h) {
   h.in_frame = false; h.more = u.idx < u.total; h.budget = 0; h.cpu.stop = false; h.cpu.fifo_n = 0; h.instr = 0; h.jobs = 0;
+  // cpu_fast issues its loads before it knows whether the lane runs at all: the registers they are addressed from
+  // must be valid (any cartridge page, any PC) from the first tick on, not only after the first cpu_load
+  h.cpu.axys = 0; h.cpu.PC = 0x1000u; h.cpu.P = 0; h.cpu.nz = 0; h.cpu.dbus = 0; h.cpu.segmap = 0; h.cpu.hot_lo = 0x1000u;
+  h.cpu.cycles = 0; h.cpu.clk0 = 0; h.cpu.cyc0 = 0;
+  h.cpu.def_lo = h.cpu.def_hi = h.cpu.dep_lo = h.cpu.dep_hi = 0; h.cpu.tainted = false;
   h.def_lo = h.def_hi = h.dep_lo = h.dep_hi = 0; h.tainted = false; h.obs_bad = false;
 }
 MN_HD MN_INLINE bool hot_has_work(const Hot& h) { return h.in_frame || h.more; }

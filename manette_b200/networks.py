@@ -17,9 +17,10 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
-def _torch_init(module, fan_in):
+def _torch_init(module, fan_in, weight_fan=None):
     d = 1.0 / math.sqrt(fan_in)                       # networks.py:47-50,83-85: uniform(-d, d) for weights and biases
-    nn.init.uniform_(module.weight, -d, d)
+    dw = d if weight_fan is None else 1.0 / math.sqrt(weight_fan)
+    nn.init.uniform_(module.weight, -dw, dw)
     nn.init.uniform_(module.bias, -d, d)
     return module
 
@@ -27,7 +28,10 @@ def _torch_init(module, fan_in):
 def _conv(cin, cout, size, stride, same=False):
     m = nn.Conv2d(cin, cout, size, stride, padding=(size // 2 if same else 0) if size % 2 else 0)
     m._same_even = bool(same and size % 2 == 0)       # TF 'SAME' with an even kernel pads (1, 2): done in forward
-    return _torch_init(m, cin * size * size)
+    # The reference's conv_weight_variable reads `input_channels = shape[3]` of an [h, w, cin, cout] kernel
+    # (networks.py:41-46): its weights are U(+-1/sqrt(COUT*h*w)); only the bias (networks.py:52-60) uses cin.
+    # Restated as it behaves, not as it reads.
+    return _torch_init(m, cin * size * size, weight_fan=cout * size * size)
 
 
 def _fc(cin, cout):

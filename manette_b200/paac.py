@@ -8,6 +8,7 @@ This class adds what surrounds the loop: environment construction through the cr
 checkpoint folders (checkpoints.py), learning-rate annealing on `global_step`, periodic progress lines, and -- under
 torchrun -- one process per GPU with the gradient and episode-statistics all-reduce (not in the reference).
 TensorBoard summaries are out of scope."""
+import collections
 import logging
 import os
 import time
@@ -51,7 +52,14 @@ class PAACLearner(object):
         if self.world > 1:                                             # every replica starts from rank 0's variables
             for p in self.network.parameters():
                 dist.broadcast(p.data, 0)
-        self.total_rewards, self.total_steps = [], []
+        # finished episodes: logged on the device per local step (no host sync inside the rollout), drained once per
+        # rollout; only a bounded window is kept (the reference's lists grow for the whole 80 M-step run, paac.py:143-144,
+        # and only their last ten entries are ever read, paac.py:268)
+        self.total_rewards, self.total_steps = collections.deque(maxlen=1000), collections.deque(maxlen=1000)
+        T, n, dev = int(args.max_local_steps), self.emulator_counts, self.pool.device
+        self._fin_count = torch.zeros(T, dtype=self.core.rollout.finished_count.dtype, device=dev)
+        self._fin_reward = torch.zeros((T, n), dtype=self.core.rollout.finished_reward.dtype, device=dev)
+        self._fin_steps = torch.zeros((T, n), dtype=self.core.rollout.finished_steps.dtype, device=dev)
         self.runners = None
 
     # -- actor_learner.py:102-136
@@ -92,9 +100,21 @@ class PAACLearner(object):
 
     # -- paac.py:86-297
     def _after_step(self, t):
-        rewards, lengths = self.core.rollout.finished()                # episodes that ended in this step, env order
-        self.total_rewards.extend(float(r) for r in rewards)
-        self.total_steps.extend(int(s) for s in lengths)
+        ro = self.core.rollout                                         # device-to-device, stream ordered: no host sync
+        self._fin_count[t].copy_(ro.finished_count.reshape(()))
+        self._fin_reward[t].copy_(ro.finished_reward)
+        self._fin_steps[t].copy_(ro.finished_steps)
+
+    def _after_rollout(self):
+        """The episodes that ended in the rollout, in (local step, environment) order -- the order of the reference's
+        appends (paac.py:186-193).  One host synchronisation per rollout."""
+        counts = self._fin_count.cpu().numpy()
+        if not counts.any():
+            return
+        rewards, steps = self._fin_reward.cpu().numpy(), self._fin_steps.cpu().numpy()
+        for t, k in enumerate(counts):
+            self.total_rewards.extend(float(r) for r in rewards[t, :int(k)])
+            self.total_steps.extend(int(x) for x in steps[t, :int(k)])
 
     def train(self):
         self.core.global_step = self.init_network()
@@ -111,11 +131,12 @@ class PAACLearner(object):
         while self.global_step < self.max_global_steps:
             loop_start_time = time.time()
             out = self.core.train_rollout()
+            self._after_rollout()
             counter += 1
             if counter % every == 0:
                 torch.cuda.synchronize(self.pool.device)
                 now = time.time()
-                last_ten = 0.0 if not self.total_rewards else float(np.mean(self.total_rewards[-10:]))
+                last_ten = 0.0 if not self.total_rewards else float(np.mean(list(self.total_rewards)[-10:]))
                 steps_per_sec = self.max_local_steps * self.emulator_counts * self.world / (now - loop_start_time)
                 average_steps_per_sec = (self.global_step - global_step_start) / (now - start_time)
                 if self.rank == 0:

@@ -104,9 +104,16 @@ class DevicePool(object):
 
     def history_ordered(self, out=None, stream=None):
         """The reference's `memory` array (paac.py:107-112): (N, H, 84, 84, 4D), oldest -> newest."""
-        if out is None:
-            out = torch.empty_like(self.history)
-        _native.check(self._L.mn_history_gather(self._h, C.c_void_p(out.data_ptr()), self._stream_ptr(stream)), "mn_history_gather")
+        # The gather runs on the CALLER's stream (torch's current one unless told otherwise), ordered after whatever
+        # the pool's own stream still has in flight: `out` is allocated, read and freed on that same stream, so neither
+        # the consumer nor the caching allocator can get ahead of the copy.
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        stream.wait_stream(self.stream)
+        with torch.cuda.stream(stream):
+            if out is None:
+                out = torch.empty_like(self.history)
+            _native.check(self._L.mn_history_gather(self._h, C.c_void_p(out.data_ptr()), self._stream_ptr(stream)), "mn_history_gather")
         return out
 
     def set_tab_rep(self, tab_rep):

@@ -101,8 +101,10 @@ def evaluate(args, network=None, per_env=None, noop_counts=None, max_macro_steps
     if network is None:
         network = network_creator()
         path = checkpoints.latest_checkpoint(os.path.join(args.folder, "checkpoints"))
-        if path is not None:
-            network.load_state_dict(checkpoints.load(path, pool.device))
+        if path is None:      # the reference's saver.restore fails loudly on a folder without a loadable checkpoint
+            raise FileNotFoundError("no loadable checkpoint (checkpoints/-<step>.pt) under %r: refusing to evaluate a "
+                                    "randomly initialised network" % (args.folder,))
+        network.load_state_dict(checkpoints.load(path, pool.device))
     network = network.to(pool.device)
     if noop_counts is None:
         noop_counts = [random.randint(0, args.noops) if args.noops != 0 else 0 for _ in range(n)]

@@ -94,3 +94,25 @@ def test_history_ring_equals_update_memory_through_real_episodes():
         assert np.array_equal(pool.history[:, pool.history_head].cpu().numpy(), port.memory[:, -1])
     assert wipes > 0, "the schedule was meant to end some episodes"
     pool.close()
+
+
+def test_history_gather_is_ordered_with_its_consumer():
+    """A large gather (0.3 GB) consumed straight away on torch's current stream must equal a gather taken after a
+    full device synchronisation: history_ordered() runs on the caller's stream, after the pool's stream."""
+    import manette_b200 as mb
+    game, n, k, H = "breakout", 2048, 11, 5
+    tab = mb.tab_repetitions(10, k)
+    pool = mb.DevicePool([(game, rom_bytes(game), n)], tab_rep=tab, history=H)
+    pool.reset_all()
+    g = torch.Generator().manual_seed(3)
+    for step in range(3):
+        pool.action_idx.copy_(torch.randint(0, pool.num_actions, (n,), generator=g, dtype=torch.int32))
+        pool.repetition_idx.copy_(torch.randint(0, 3, (n,), generator=g, dtype=torch.int32))
+        pool.step_async(use_indices=True)               # no wait: the gather has to order itself after the step
+        early = pool.history_ordered().clone()
+        torch.cuda.synchronize()
+        late = pool.history_ordered()
+        torch.cuda.synchronize()
+        assert torch.equal(early, late), step
+        assert torch.equal(late[:, -1], pool.states)
+    pool.close()
