@@ -37,21 +37,38 @@ WORKLOADS = {
     "seaquest_figar10_rgb_n4096": dict(games=["seaquest"], n=4096, rgb=True, nb_choices=11, max_rep=10),
     # C4 is the LSTM configuration: the learner's 5-deep observation history (paac.py:107-112) is kept by the pool
     "ms_pacman_figar10_n16384": dict(games=["ms_pacman"], n=16384, rgb=False, nb_choices=11, max_rep=10, history=5),
-    "mixed12_figar10_n16384": dict(games=GAMES12, n=16384, rgb=False, nb_choices=11, max_rep=10, allreduce=3400000),
+    "mixed12_figar10_n16384": dict(games=GAMES12, n=16384, rgb=False, nb_choices=11, max_rep=10),
 }
 DEFAULT_WORKLOAD = "ms_pacman_figar10_n16384"
 # algorithmic HBM bytes of one next() for the emulation kernel: the two pooled raw frames it
 # must leave in HBM (2 x 33,600) + machine state in and out (2 x (168 + 128)); K3: 2 raw frames read + one plane
 ROUND_BYTES_PER_NEXT = 2 * 33600 + 2 * (168 + 128)
-# ncu --set full, one k_round launch of 16,384 Ms Pacman next() calls (profiles/r1_k_round_summary.txt):
-# dram__bytes_read.sum + dram__bytes_write.sum = 11.8 MB + 1,060.4 MB -> per next(); warp instructions issued per
-# next() and the share of the kernel's warp-state samples that wait for an instruction fetch
-NCU_ROUND_DRAM_BYTES_PER_NEXT = (11.818496e6 + 1.060357e9) / 16384
-NCU_ROUND_WARP_INST_PER_NEXT = 4768749828 / 16384
-# ncu --set full, one k_push_frames launch over 16,384 gray Ms Pacman envs (profiles/r1_k3_push_frames_summary.txt):
-# 705.2 MB read + 105.8 MB written -> per next(): the 126 source rows the nearest map drops are never read
-NCU_K3_DRAM_BYTES_PER_NEXT = (705.19296e6 + 105.80096e6) / 16384
 PEAK_WARP_INST_PER_S = 148 * 4 * 1.965e9   # 148 SMs x 4 sub-partitions x 1 warp instruction per clock
+# ncu-derived per-next() counters (warp instructions issued, DRAM bytes moved) are NOT literals here: they are read
+# from profiles/*_counters.json, which tools/ncu_counters.py writes from an ncu report and stamps with the hash of the
+# CUDA sources the profiled library was built from.  A stamp that does not match the sources of the library this run
+# loads makes the dependent figures null ("stale") instead of silently quoting numbers of another kernel.
+ROUND_COUNTERS = os.path.join(ROOT, "profiles", "r2_k_round_counters.json")
+K3_COUNTERS = os.path.join(ROOT, "profiles", "r2_k3_counters.json")
+# networks whose flat fp32 gradient the synchronous-PAAC all-reduce carries (paac.py:233-256), per workload
+ARCH = {"pong_paac_n32": "NIPS", "breakout_figar10_n256": "NIPS", "seaquest_figar10_rgb_n4096": "PWYX",
+        "ms_pacman_figar10_n16384": "LSTM", "mixed12_figar10_n16384": "PWYX"}
+REAL_ALE_RAW_FPS_PER_CORE = 6000.0   # commonly quoted, NOT verifiable here (ALE is not installable offline)
+
+
+def load_counters(path):
+    """(counters dict, None) if the file exists and was taken from the sources this run is built from, else
+    (None, reason)."""
+    from manette_b200 import build as mb_build
+    if not os.path.exists(path):
+        return None, "no %s" % os.path.relpath(path, ROOT)
+    with open(path) as f:
+        doc = json.load(f)
+    have = mb_build.source_hash()
+    if doc.get("source_hash") != have:
+        return None, "stale: %s was profiled on sources %s, this run is built from %s" % (
+            os.path.relpath(path, ROOT), doc.get("source_hash"), have)
+    return doc, None
 
 
 def k3_bytes(depth):
@@ -127,34 +144,60 @@ class ClockSampler(object):
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle = the checker, timed)
-def cpu_pool_run(cfg, steps, warmup, budget_s=None, envs_per_core=4):
-    """The reference's worker pool restated on the CPU oracle (oracle/host_path.py PortRunners: W forked workers,
-    emulator_runner.py:19-42 loop, atari_emulator.py preprocessing), W = all host cores.  Returns a dict."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    sys.path.insert(0, os.path.join(ROOT, "oracle", "shims"))
+def _oracle_imports():
+    for d in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "oracle", "shims")):
+        if d not in sys.path:
+            sys.path.insert(0, d)
     import host_path
     import orc_loader
     import ref_harness
     orc_loader.build()
+    return host_path, orc_loader, ref_harness
+
+
+def cpu_pool_run(cfg, steps, warmup, budget_s=None, envs_per_core=4, kind="auto"):
+    """The reference's worker pool on the box's host cores, W = all of them, 4 envs per worker (the reference's own
+    default shape, train.py:102-103), same game / FiGAR configuration, uniform random policy.
+      kind "reference": the reference's UNMODIFIED runners.py / emulator_runner.py / atari_emulator.py /
+                        environment.py imported from /root/reference (oracle/ref_harness.py) over the CPU oracle
+                        emulator standing in for ALE -- only where the reference tree exists (not on the GPU box);
+      kind "port":      oracle/host_path.py PortRunners, the restatement of the same loop (fixtures prove it equal).
+    Returns a dict."""
+    host_path, orc_loader, ref_harness = _oracle_imports()
+    if kind == "auto":
+        kind = "reference" if ref_harness.available() else "port"
     cores = os.cpu_count() or 1
     n = cores * envs_per_core
     groups = split_games(cfg["games"], n)
     tab_rep = tab_repetitions(cfg["max_rep"], cfg["nb_choices"])
+    act_counter = None
+    if kind == "reference":
+        ref = ref_harness.load()
+        import ale_python_interface as shim
+        act_counter = shim.enable_act_counter(n)
+        emu_cls = ref.atari_emulator.AtariEmulator
+    else:
+        emu_cls = host_path.PortAtariEmulator
     emus, eid = [], 0
     for g, k in groups:
         a = ref_harness.Args(g, ROMS, rgb=cfg["rgb"], max_repetition=cfg["max_rep"], nb_choices=cfg["nb_choices"])
         for _ in range(k):
-            emus.append(host_path.PortAtariEmulator(eid, a))
+            emus.append(emu_cls(eid, a))
             eid += 1
     num_actions = max(len(e.get_legal_actions()) for e in emus)
     acts_per_env = np.array([len(e.get_legal_actions()) for e in emus])
-    states = np.stack([e.get_initial_state() for e in emus])
+    states = np.asarray([e.get_initial_state() for e in emus], dtype=np.uint8)
     variables = [states, np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros((n, num_actions), np.float32),
                  np.zeros((n, cfg["nb_choices"]), np.float32)]
-    runners = host_path.PortRunners(tab_rep, emus, cores, variables)
+    if kind == "reference":
+        runners = ref.runners.Runners(tab_rep, ref.emulator_runner.EmulatorRunner, np.asarray(emus, dtype=object), cores,
+                                      variables)   # paac.py:104 (self.emulators is an ndarray there, actor_learner.py:35)
+    else:
+        runners = host_path.PortRunners(tab_rep, emus, cores, variables)
     runners.start()
     sv = runners.get_shared_variables()
     rng = np.random.RandomState(1234)
+    seen = [int(np.sum(np.frombuffer(act_counter, dtype=np.int64)))] if act_counter is not None else None
 
     def one_step():
         a = (rng.randint(0, 1 << 30, size=n) % acts_per_env)
@@ -165,7 +208,13 @@ def cpu_pool_run(cfg, steps, warmup, budget_s=None, envs_per_core=4):
         sv[4][np.arange(n), r] = 1
         runners.update_environments()
         runners.wait_updated()
-        return int(runners.next_counts().sum())
+        if act_counter is None:
+            return int(runners.next_counts().sum())
+        # next() = 4 act() calls; an episode that ended inside the step cost 16 more (get_initial_state,
+        # atari_emulator.py:102-107), which are not next() calls of the step
+        now = int(np.sum(np.frombuffer(act_counter, dtype=np.int64)))
+        acts, seen[0] = now - seen[0], now
+        return (acts - 16 * int(np.sum(sv[2] != 0))) // 4
 
     try:
         for _ in range(warmup):
@@ -180,9 +229,66 @@ def cpu_pool_run(cfg, steps, warmup, budget_s=None, envs_per_core=4):
         dt = time.perf_counter() - t0
     finally:
         runners.stop()
-    return {"value": frames / dt, "frames": frames, "seconds": dt, "steps": done, "cores": cores, "n_envs": n,
-            "sample": "%d envs (%d per core) x %d macro steps of the same game/FiGAR config on %d worker processes"
-                      % (n, envs_per_core, done, cores)}
+        for r in getattr(runners, "runners", []):
+            r.join(timeout=5)
+    return {"value": frames / dt, "frames": frames, "seconds": dt, "steps": done, "cores": cores, "n_envs": n, "kind": kind,
+            "sample": "%d envs (%d per core) x %d macro steps of the same game/FiGAR config on %d worker processes (%s)"
+                      % (n, envs_per_core, done, cores,
+                         "the reference's unmodified Runners/EmulatorRunner/AtariEmulator over the oracle emulator"
+                         if kind == "reference" else "oracle port of the reference's worker pool")}
+
+
+def cpp_pool_run(cfg, budget_s=4.0, envs_per_core=4):
+    """Best-case CPU line: the oracle emulators stepped by one C++ thread per host core through the
+    FiGAR loop, no Python, no preprocessing (oracle_capi.cpp orc_pool_step)."""
+    import ctypes as C
+    host_path, orc_loader, ref_harness = _oracle_imports()
+    L = orc_loader.lib()
+    L.orc_pool_step.restype = C.c_long
+    L.orc_pool_step.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_create.restype = C.c_void_p
+    cores = os.cpu_count() or 1
+    n = cores * envs_per_core
+    tab_rep = np.array(tab_repetitions(cfg["max_rep"], cfg["nb_choices"]), np.int32)
+    handles, nact = [], []
+    for gi, (g, k) in enumerate(split_games(cfg["games"], n)):
+        rom = rom_bytes(g)
+        for j in range(k):
+            h = L.orc_create(rom, len(rom), g.encode(), C.c_uint32(3 * (len(handles) + 1)))
+            L.orc_reset_game(C.c_void_p(h))
+            handles.append(h)
+            nact.append(L.orc_num_actions(C.c_void_p(h)))
+    envs = (C.c_void_p * n)(*handles)
+    nact = np.array(nact)
+    rng = np.random.RandomState(4321)
+    rewards, terms = np.zeros(n, np.float32), np.zeros(n, np.uint8)
+    frames, t0 = 0, time.perf_counter()
+    steps = 0
+    while time.perf_counter() - t0 < budget_s:
+        a = (rng.randint(0, 1 << 30, size=n) % nact).astype(np.int32)
+        r = tab_rep[rng.randint(0, cfg["nb_choices"], size=n)].astype(np.int32)
+        frames += int(L.orc_pool_step(envs, n, a.ctypes.data, r.ctypes.data, cores, rewards.ctypes.data, terms.ctypes.data))
+        steps += 1
+    dt = time.perf_counter() - t0
+    for h in handles:
+        L.orc_destroy(C.c_void_p(h))
+    return {"value": frames / dt, "unit": "frames/s", "cores": cores, "raw_frames_per_s_per_core": 4.0 * frames / dt / cores,
+            "sample": "%d envs x %d macro steps, %d C++ threads, emulation + FiGAR loop only (no preprocessing, no Python)"
+                      % (n, steps, cores)}
+
+
+def cpu_baseline_block(cfg, r, cpp):
+    """The `cpu_baseline` object of the JSON line from a cpu_pool_run() result and a cpp_pool_run() result."""
+    raw_per_core = cpp["raw_frames_per_s_per_core"] if cpp else None
+    return {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+            "cpu_sample_envs": r["n_envs"], "cpp_pool": cpp,
+            "real_ale_caveat": {
+                "oracle_raw_frames_per_s_per_core": raw_per_core, "real_ale_raw_frames_per_s_per_core": REAL_ALE_RAW_FPS_PER_CORE,
+                "factor": (REAL_ALE_RAW_FPS_PER_CORE / raw_per_core) if raw_per_core else None,
+                "note": "the CPU emulator under this arm is the oracle (a deliberately simple restatement), not ALE: "
+                        "ALE is not installable offline.  Real ALE is commonly quoted at ~6 k raw frames/s/core "
+                        "(unverified here); divide a GPU/CPU ratio against this arm by `factor` to estimate the ratio "
+                        "against an ALE pool on the same cores"}}
 
 
 # ----------------------------------------------------------------------------- main
@@ -230,22 +336,28 @@ def main():
     config = {"workload": args.workload, "games": cfg["games"], "envs_per_gpu": cfg["n"], "rgb": cfg["rgb"],
               "nb_choices": cfg["nb_choices"], "max_repetition": cfg["max_rep"], "policy": "uniform random (counter-based)",
               "decorrelate_steps": args.decorrelate, "observation_history": cfg.get("history", 0),
-              "frame_unit": "1 preprocessed frame = 1 next() = 4 emulated frames + one 84x84xD plane"}
+              "frame_unit": "1 preprocessed frame = 1 next() = 4 emulated frames + one 84x84xD plane",
+              "l2": "per-step working set (frame buffers %d MB + states/ring) exceeds the 126 MB L2; no flush needed"
+                    % (cfg["n"] * 67200 // (1 << 20)),
+              "collective": "none at 1 GPU; at N > 1 every 5 macro steps: flat fp32 gradient all-reduce of the %s net + "
+                            "episode-statistics reduction (paac.py:233-256)" % ARCH[args.workload]}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        # one reference "step" = REF_MACRO macro steps of the bounded CPU sample (4 envs per host core), so that the
-        # default K = 20 times ~10 s of CPU work instead of well under a second
+        # one reference "step" = REF_MACRO macro steps of the bounded CPU sample (4 envs per host core -- the
+        # reference's own pool shape, train.py:102-103 -- NOT the envs_per_gpu of `config`, which names the workload
+        # both arms are quoted on; the rate is per core, see cpu_baseline.cpu_sample_envs), so that the default K = 20
+        # times ~10 s of CPU work instead of well under a second
         REF_MACRO = 16
         r = cpu_pool_run(cfg, args.steps * REF_MACRO, args.warmup * REF_MACRO)
         r["sample"] += " (= %d bench steps of %d macro steps)" % (args.steps, REF_MACRO)
+        cpp = cpp_pool_run(cfg, budget_s=4.0)
         line = {"impl": "reference", "metric": "preprocessed env frames/sec (FiGAR10)", "value": r["value"],
                 "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1000.0 * r["seconds"] / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
-                                 "sample": r["sample"]},
+                "cpu_sample_envs": r["n_envs"], "cpu_baseline": cpu_baseline_block(cfg, r, cpp),
                 "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         emit_line(line)
@@ -284,8 +396,33 @@ def main():
     total = args.warmup + args.steps
     acts = (torch.randint(0, 1 << 30, (2 * total, n), device=dev, generator=gen) % n_act).to(torch.int32)
     reps = torch.randint(0, cfg["nb_choices"], (2 * total, n), device=dev, generator=gen, dtype=torch.int32)
-    grad = torch.zeros(cfg.get("allreduce", 0) or 1, device=dev) if world > 1 and cfg.get("allreduce") else None
+    # Synchronous PAAC across GPUs (north star; paac.py:233-256 is the single-process update it extends): every
+    # T = max_local_steps macro steps the flat fp32 gradient of the workload's network is all-reduced, and the K6
+    # episode statistics (count, sum of returns, sum of lengths: SUM; min / max return: MAX on (-min, max)) are reduced.
+    # Both run on the pool's stream inside the timed region; CUDA events bracket them.
+    grad, coll_events, n_params = None, [], 0
+    if world > 1:
+        from manette_b200.networks import PolicyVNetwork
+        with torch.device("meta"):
+            net = PolicyVNetwork(ARCH[args.workload], pool.num_actions, cfg["nb_choices"], depth=pool.depth)
+        n_params = sum(p.numel() for p in net.parameters())
+        grad = torch.randn(n_params, device=dev) * 1e-3
+        stat_sum = torch.zeros(4, dtype=torch.float64, device=dev)
+        stat_max = torch.zeros(2, dtype=torch.float64, device=dev)
     stream = pool.stream
+
+    def collective_step():
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record(stream)
+        dist.all_reduce(grad)
+        grad.div_(world)
+        st = rollout.stats                                   # count, sum reward, sum length, min, max, global_step
+        stat_sum.copy_(torch.stack([st[0], st[1], st[2], st[5]]))
+        stat_max.copy_(torch.stack([-st[3], st[4]]))
+        dist.all_reduce(stat_sum)
+        dist.all_reduce(stat_max, op=dist.ReduceOp.MAX)
+        eb.record(stream)
+        coll_events.append((ea, eb))
 
     def device_step(t):
         with torch.cuda.stream(stream):
@@ -299,8 +436,8 @@ def main():
             if (t + 1) % T_LOCAL == 0:
                 rollout.returns(boot, 0.99, stream)
                 extra_launches[0] += 2                      # mask flip + K5
-            if grad is not None and (t + 1) % 5 == 0:      # synchronous-PAAC gradient allreduce every T=5 macro steps
-                dist.all_reduce(grad)
+            if grad is not None and (t + 1) % T_LOCAL == 0:
+                collective_step()
 
     # ---- device-resident leg
     for t in range(args.decorrelate):   # spread the envs over game states (they all start identical)
@@ -315,6 +452,7 @@ def main():
     barrier()
     f0, l0, i0 = pool.total_next_calls(), pool.launch_count(), pool.total_instructions()
     extra_launches[0] = 0
+    del coll_events[:]
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -356,6 +494,19 @@ def main():
     else:
         ms_max, frames_all, launches_all = ms, float(frames), int(launches)
     value = frames_all / (ms_max / 1000.0)
+    collective = None
+    if grad is not None:
+        us = [1000.0 * a.elapsed_time(b) for a, b in coll_events]
+        cstat = torch.tensor([float(np.mean(us)) if us else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(cstat, op=dist.ReduceOp.MAX)
+        collective = {"what": "NCCL all-reduce of the flat fp32 gradient (%s net, %d parameters) + episode statistics "
+                              "(4 doubles SUM, 2 doubles MAX), on the pool's stream inside the timed region"
+                              % (ARCH[args.workload], n_params),
+                      "bytes": int(4 * n_params + 48), "every_steps": T_LOCAL, "count": len(us),
+                      "us_per_allreduce": float(cstat[0]),
+                      "share_of_step": float(cstat[0]) * 1e-3 * len(us) / ms_max if ms_max > 0 else None,
+                      "episodes_all_ranks": float(stat_sum[0]), "global_steps_all_ranks": float(stat_sum[3])}
+        del coll_events[:]
 
     # ---- end-to-end leg through Runners with host arrays
     e2e = None
@@ -376,6 +527,9 @@ def main():
             sv[4][...] = 0
             sv[4][ar, h_reps[t]] = 1
             runners.update_environments()
+            if grad is not None and (t + 1) % T_LOCAL == 0:
+                with torch.cuda.stream(stream):
+                    collective_step()
             runners.wait_updated()
             return float(sv[1].sum()) + float(sv[2].sum()) + float(sv[0][0, 0, 0, 0])
 
@@ -403,6 +557,25 @@ def main():
                "api": "Runners.update_environments()/wait_updated() with pinned host arrays"}
         runners.stop()
 
+    # ---- second end-to-end figure: mn_step_host, the single C call INTEGRATION.md shows a maintainer, with PAGEABLE
+    # numpy arrays (actions/repetitions up, states/rewards/terminals down, all inside the call)
+    e2e_host = None
+    if not args.no_e2e and world == 1:
+        pa = np.zeros((n, pool.num_actions), np.float32); pr = np.zeros((n, pool.nb_choices), np.float32)
+        ps = np.zeros(tuple(pool.states.shape), np.uint8); prw = np.zeros(n, np.float32); pt = np.zeros(n, np.float32)
+        k_host = max(3, min(args.steps, 6))
+        f0 = pool.total_next_calls()
+        t0 = None
+        for t in range(1 + k_host):
+            if t == 1:
+                f0, t0 = pool.total_next_calls(), time.perf_counter()
+            pa[...] = 0; pa[ar, h_acts[t]] = 1
+            pr[...] = 0; pr[ar, h_reps[t]] = 1
+            pool.step_host(pa, pr, ps, prw, pt)
+        dt = time.perf_counter() - t0
+        e2e_host = {"value": (pool.total_next_calls() - f0) / dt, "unit": "frames/s", "steps": k_host,
+                    "ms_per_step": 1000.0 * dt / k_host, "api": "mn_step_host() with pageable numpy arrays"}
+
     # ---- roofline of the dominant kernel (k_round), CUDA events around every launch on its stream
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -413,30 +586,44 @@ def main():
     round_ms, round_launches = prof["round"]
     push_ms, push_launches = prof["push"]
     emit_ms, emit_launches = prof["emit"]
-    achieved = frames * ROUND_BYTES_PER_NEXT / (round_ms / 1000.0) / 1e9 if round_ms > 0 else 0.0
+    round_s = round_ms / 1000.0
+    hbm_achieved = frames * ROUND_BYTES_PER_NEXT / round_s / 1e9 if round_ms > 0 else 0.0
     k3_achieved = (frames * k3_bytes(pool.depth)) / (push_ms / 1000.0) / 1e9 if push_ms > 0 else 0.0
-    roofline = {"kernel": "k_round (6502+TIA emulation, one next() per listed env)", "bound": "hbm", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_ROUND_DRAM_BYTES_PER_NEXT * frames / max(round_launches, 1),
-                "traffic_source": "ncu dram bytes per next() of one k_round launch (profiles/r1_k_round_summary.txt) x next() calls "
-                                  "per launch of this run; algorithmic bytes per next() = %d" % ROUND_BYTES_PER_NEXT,
-                "peak_source": peak_src,
+    rc, rc_why = load_counters(ROUND_COUNTERS)
+    k3c, k3_why = load_counters(K3_COUNTERS)
+    next_per_launch = frames / max(round_launches, 1)
+    # K1 is an integer / control-flow kernel: its roofline is the SM issue rate, HBM is secondary.
+    # achieved = warp instructions per next() (ncu smsp__inst_executed.sum of profiled launches of THESE sources)
+    #            x next() calls of this run / k_round's CUDA-event time of this run
+    inst_rate = rc["warp_inst_per_next"] * frames / round_s if rc and round_ms > 0 else None
+    roofline = {"kernel": "k_round (6502+TIA emulation, one next() per listed env)", "bound": "sm_issue",
+                "achieved": inst_rate, "peak": PEAK_WARP_INST_PER_S, "unit": "warp-inst/s",
+                "frac": inst_rate / PEAK_WARP_INST_PER_S if inst_rate else None,
+                "traffic": rc["dram_bytes_per_next"] * next_per_launch if rc else None,
+                "counters": ({"file": os.path.relpath(ROUND_COUNTERS, ROOT), "source_hash": rc["source_hash"],
+                              "warp_inst_per_next": rc["warp_inst_per_next"], "dram_bytes_per_next": rc["dram_bytes_per_next"],
+                              "profiled_issue_active_pct": [l["issue_active_pct"] for l in rc["launches"]],
+                              "profiled_lanes_per_warp_inst": [l["thread_inst_per_warp_inst"] for l in rc["launches"]]}
+                             if rc else {"stale": rc_why}),
+                "peak_source": "148 SMs x 4 sub-partitions x 1 warp instruction per clock x 1.965 GHz (SURVEY.md 8(d))",
                 "avg_launch_ms": round_ms / max(round_launches, 1), "launches": int(round_launches),
-                "share_of_step": round_ms / ms if ms > 0 else None,
-                "note": "emulation is bound by the latency of one warp's instruction stream (SM issue / instruction fetch), "
-                        "not by HBM: the HBM fraction is reported as the contract asks; see sm_issue and profiles/",
-                "sm_issue": {"warp_inst_per_s": NCU_ROUND_WARP_INST_PER_NEXT * frames / (round_ms / 1000.0) if round_ms > 0 else 0.0,
-                             "peak_warp_inst_per_s": PEAK_WARP_INST_PER_S,
-                             "frac": (NCU_ROUND_WARP_INST_PER_NEXT * frames / (round_ms / 1000.0) / PEAK_WARP_INST_PER_S) if round_ms > 0 else 0.0,
-                             "source": "warp instructions per next() from ncu (smsp__inst_executed.sum of one launch) x next() "
-                                       "calls of this run / k_round CUDA-event time"}}
+                "next_calls_per_launch": next_per_launch, "share_of_step": round_ms / ms if ms > 0 else None,
+                "note": "one warp per SM sub-partition runs a serial emulated-6502 instruction stream: the limiter is the "
+                        "latency of that stream (dependent issue, branches), not HBM and not tensor cores (no contraction)",
+                "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak,
+                        "algorithmic_bytes_per_next": ROUND_BYTES_PER_NEXT, "peak_source": peak_src,
+                        "traffic_per_next": rc["dram_bytes_per_next"] if rc else None}}
+    k3_moved = k3c["dram_bytes_per_next"] if (k3c and pool.depth == 1) else None
     extra = {"k3_push_frames": {"bound": "hbm", "achieved": k3_achieved, "peak": peak, "unit": "GB/s",
                                 "frac": k3_achieved / peak, "ms": push_ms, "launches": int(push_launches),
                                 "share_of_step": push_ms / ms if ms > 0 else None,
                                 "algorithmic_bytes_per_next": k3_bytes(pool.depth),
-                                "traffic_per_next": NCU_K3_DRAM_BYTES_PER_NEXT if pool.depth == 1 else None,
-                                "traffic_source": "ncu dram bytes of one launch over 16,384 gray envs "
-                                                  "(profiles/r1_k3_push_frames_summary.txt)"},
+                                "traffic_per_next": k3_moved,
+                                # the nearest map never reads 126 of the 210 source rows: on the bytes that actually
+                                # move the kernel runs at a lower fraction than on the algorithmic ones
+                                "achieved_moved": k3_achieved * k3_moved / k3_bytes(pool.depth) if k3_moved else None,
+                                "frac_moved": k3_achieved * k3_moved / k3_bytes(pool.depth) / peak if k3_moved else None,
+                                "counters": os.path.relpath(K3_COUNTERS, ROOT) if k3c else {"stale": k3_why}},
              "k_emit": {"ms": emit_ms, "launches": int(emit_launches), "share_of_step": emit_ms / ms if ms > 0 else None,
                         "history_depth": int(cfg.get("history", 0))},
              "k6_rollout_record": {"us_per_launch": k6_us, "bound": "launch latency", "envs": n}}
@@ -444,19 +631,18 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_pool_run(cfg, steps=10 ** 9, warmup=1, budget_s=12.0)
-        cpu = {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        cpu = cpu_baseline_block(cfg, r, cpp_pool_run(cfg, budget_s=4.0))
 
     if rank == 0:
         line = {"metric": "preprocessed env frames/sec (FiGAR10)", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
                 "raw_emulated_frames_per_s": 4.0 * value, "macro_steps_per_s": world * n * args.steps / (ms_max / 1000.0),
-                "step_latency": step_latency, "clocks": clocks, "e2e": e2e, "gpu_launches": launches_all, "roofline": roofline, "kernels": extra,
+                "step_latency": step_latency, "clocks": clocks, "e2e": e2e, "e2e_step_host": e2e_host, "collective": collective,
+                "gpu_launches": launches_all, "roofline": roofline, "kernels": extra,
                 "cpu_baseline": cpu, "envs_per_warp": int(args.envs_per_warp),
                 "reset_memo": dict(zip(("restored", "emulated", "stored"), pool.memo_stats())), "exact_reruns": pool.redo_count(),
                 "emulated_6502_instr_per_s": world * ins_timed / (ms_max / 1000.0)}
-        config["l2"] = "per-step working set (frame buffers %d MB + states/ring) exceeds the 126 MB L2; no flush needed" \
-            % (n * 67200 // (1 << 20))
         emit_line(line)
     pool.close()
     if world > 1:

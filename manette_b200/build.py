@@ -36,3 +36,14 @@ def build(force=False, verbose=False):
 
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
+
+
+def source_hash():
+    """sha256 (first 16 hex digits) over the CUDA sources and headers the library is built from: stamps ncu-derived
+    counters under profiles/ so that bench.py can tell whether they describe the kernels it is running."""
+    import hashlib
+    h = hashlib.sha256()
+    for path in sorted(SOURCES + HEADERS):
+        with open(path, "rb") as f:
+            h.update(os.path.basename(path).encode() + b"\0" + f.read() + b"\0")
+    return h.hexdigest()[:16]

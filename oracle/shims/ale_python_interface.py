@@ -15,9 +15,28 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import orc_loader as liborc  # noqa: E402
 
 
+# act() counters for the bench's reference arm: one int64 slot per ALEInterface, in memory shared with forked
+# workers (the reference keeps its own per-emulator step count, but inside the worker processes where the parent
+# cannot read it).  Off unless enable_act_counter() was called before the emulators were built.
+_ACTS = None
+_NEXT_SLOT = [0]
+
+
+def enable_act_counter(n):
+    global _ACTS
+    from multiprocessing.sharedctypes import RawArray
+    _ACTS = RawArray("q", int(n))
+    _NEXT_SLOT[0] = 0
+    return _ACTS
+
+
 class ALEInterface(object):
     def __init__(self):
         self._L = liborc.lib()
+        self._slot = None
+        if _ACTS is not None and _NEXT_SLOT[0] < len(_ACTS):
+            self._slot = _NEXT_SLOT[0]
+            _NEXT_SLOT[0] += 1
         self._h = None
         self._ints = {b"random_seed": 0, b"frame_skip": 1}
         self._floats = {b"repeat_action_probability": 0.25}
@@ -65,6 +84,8 @@ class ALEInterface(object):
         self._L.orc_reset_game(self._h)
 
     def act(self, action):
+        if self._slot is not None:
+            _ACTS[self._slot] += 1
         return self._L.orc_act(self._h, int(action))
 
     def game_over(self):
