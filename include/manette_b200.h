@@ -44,7 +44,7 @@ typedef struct {
   int env_id_offset;         /* global id of local env 0 when the pool is one shard of a multi-GPU job */
   int nb_choices;            /* K = len(tab_rep), 1..32; 0 with tab_rep NULL = plain PAAC ([0]) until mn_set_tab_rep */
   const int* tab_rep;        /* ExplorationPolicy.get_tab_repetitions() (exploration_policy.py:56-62) */
-  int envs_per_warp;         /* tuning: 1,2,4,8,16,32 lanes of a warp that own an environment (0 = default) */
+  int envs_per_warp;         /* tuning: 1..32 lanes of a warp that own an environment (0 = automatic: one block per SM) */
   int draw_all_frames;       /* debug: draw the pixels of all four frames of a next(), not only the two pooled ones */
   int no_reset_memo;         /* debug: emulate every get_initial_state() instead of restoring memoised ones */
   int history;               /* H > 0: keep the learner's H-deep observation history (LSTM nets: n_steps = 5, paac.py:107-112) */

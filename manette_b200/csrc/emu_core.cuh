@@ -91,7 +91,9 @@ struct EnvState {
   int32_t clk_last_update, clks_to_eol, fb_pos;
   uint16_t pend_len[2];   // per frame buffer: longest pixel-less frame since the last frame drawn with pixels
   uint32_t pf;
-  uint32_t flags;
+  uint32_t flags;       // program side (the 6502 warp): F_DUMP F_PARTIAL F_STOP F_INPT4/5 F_TIMER_IRQ_READ F_TERMINAL F_STARTED
+  uint32_t pflags;      // picture side (the TIA partner warp): every other F_* bit.  Two words because the two sides
+                        // update their bits concurrently
   uint16_t collision;
   uint8_t vsync, vblank, nusiz0, nusiz1, ctrlpf, enabled;
   uint8_t col[4];       // P0, P1, PF, BK
@@ -107,7 +109,7 @@ struct EnvState {
   int32_t host_lives;   // atari_emulator.py:121 self.lives
   uint8_t ring_head;    // ObservationPool.current_observation_index
   uint8_t game, cart, ctrl;
-};   // 168 bytes; the 128 bytes of RIOT RAM live beside it (Ctx::ram)
+};   // 172 bytes; the 128 bytes of RIOT RAM live beside it (Ctx::ram)
 
 // per-lane working context (pointers to where the pieces live while a kernel runs)
 struct Ctx {
@@ -117,13 +119,24 @@ struct Ctx {
                         // number of words, so the lanes of a warp that touch the same byte hit 32 different banks)
   uint8_t* fb;          // this env's two frame buffers (global memory), 2 * MN_FRAME_BYTES
   const Tables* tab;
-  uint32_t* fifo;       // MN_FIFO_CAP pending TIA writes of this env (shared memory)
-  int fifo_n;
+  uint32_t* fifo;       // this env's TIA write queue (shared memory): two buffers of MN_FIFO_BUF entries + the mailbox
+  int fifo_n;           // write POSITION in the double buffer: bit 4 = buffer being filled, bits 3..0 = entries in it
+  uint32_t hseq;        // hand-offs issued so far (its parity = the buffer being filled)
   bool all_pixels;      // draw every frame with pixels (the exact-fallback mode)
   uint64_t obs_lo, obs_hi;   // RAM bytes the last game_observe() looked at (reset memoisation probe)
+  bool mbox_timeout;    // a hand-off wait gave up (protocol error: reported, never a hang)
 };
-#define MN_FIFO_CAP 16
-#define MN_FIFO_HIGH 12   // a warp drains when one of its envs has this many pending writes
+// The picture side runs on a PARTNER WARP (pool.cu: picture_warp): the 6502 warp fills one buffer while the partner
+// renders the other.  A hand-off (tia_handoff) publishes the filled buffer through a four-word mailbox per env --
+// per LANE, so that a lane inside a divergent slow path (a collision-latch read) can hand off and wait on its own.
+#define MN_FIFO_BUF 16    // entries per buffer (a power of two)
+#define MN_FIFO_CAP 15    // usable entries: the fill count must stay below MN_FIFO_BUF
+#define MN_FIFO_HIGH 12   // a warp hands off when one of its envs has this many pending writes
+#define MN_FIFO_WORDS 37  // 2 x MN_FIFO_BUF entries + mailbox {hand, done, request, sync clock} + 1: an odd stride
+#define MN_MBOX (2 * MN_FIFO_BUF)
+enum { MB_HAND = 0, MB_DONE = 1, MB_REQ = 2, MB_SYNC = 3 };
+enum { PIC_DRAIN = 0, PIC_END = 1 /* + close the frame: the unit is over */, PIC_EXIT = 2 /* the partner lane leaves */ };
+#define MN_FILL(pos) ((pos) & (MN_FIFO_BUF - 1))
 // FIFO entry: [16:0] colour clock since clk_frame_start, [22:17] register, [30:23] value; bit 31 marks the
 // start of a new frame (bit 0 then says whether that frame keeps its pixels)
 #define MN_FIFO_FRAME 0x80000000u
@@ -166,7 +179,7 @@ MN_HD MN_INLINE uint32_t place(uint32_t pattern, int start, int w) {
 // ------------------------------------------------------------------ TIA: line words
 MN_HD MN_INLINE uint32_t pf_word(const EnvState& s, int w) {
   uint32_t left = (s.pf & 0xFu) | (rev8((s.pf >> 4) & 0xFFu) << 4) | (s.pf & 0xFF000u);
-  uint32_t right = (s.flags & F_PFREFL) ? (brev32(left) >> 12) : left;
+  uint32_t right = (s.pflags & F_PFREFL) ? (brev32(left) >> 12) : left;
   uint32_t cells = (w < 4) ? (((left | (right << 20)) >> (w << 3)) & 0xFFu) : (right >> 12);
   return widen4(cells);
 }
@@ -254,8 +267,8 @@ MN_HD MN_INLINE void fill_px(uint8_t* p, int n, uint32_t value) {
 // render `n` visible pixels of the current line starting at pixel `hpos`
 MN_HD MN_NOINLINE void tia_render(Ctx& c, int n, int hpos) {
   EnvState& s = *c.s;
-  const bool pixels = (s.flags & F_PIXELS) != 0;
-  uint8_t* out = c.fb + ((s.flags & F_CURFB) ? MN_FRAME_BYTES : 0) + s.fb_pos;
+  const bool pixels = (s.pflags & F_PIXELS) != 0;
+  uint8_t* out = c.fb + ((s.pflags & F_CURFB) ? MN_FRAME_BYTES : 0) + s.fb_pos;
   s.fb_pos += n;
   const uint32_t en = s.enabled;
   if (s.vblank & 0x02) { if (pixels) fill_px(out, n, 0u); return; }
@@ -274,9 +287,9 @@ MN_HD MN_NOINLINE void tia_render(Ctx& c, int n, int hpos) {
     const uint32_t span = ((hi == 32) ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
     const uint32_t pf = (en & EN_PF) ? (pf_word(s, w) & span) : 0u;
     const uint32_t bl = (en & EN_BL) ? (ball_word(s, w) & span) : 0u;
-    const uint32_t p0 = (en & EN_P0) ? (player_word(s.cur_grp0, s.nusiz0, s.pos[OB_P0], (s.flags & F_SUP0) != 0, w) & span) : 0u;
+    const uint32_t p0 = (en & EN_P0) ? (player_word(s.cur_grp0, s.nusiz0, s.pos[OB_P0], (s.pflags & F_SUP0) != 0, w) & span) : 0u;
     const uint32_t m0 = (en & EN_M0) ? (missile_word(s.nusiz0, s.pos[OB_M0], w) & span) : 0u;
-    const uint32_t p1 = (en & EN_P1) ? (player_word(s.cur_grp1, s.nusiz1, s.pos[OB_P1], (s.flags & F_SUP1) != 0, w) & span) : 0u;
+    const uint32_t p1 = (en & EN_P1) ? (player_word(s.cur_grp1, s.nusiz1, s.pos[OB_P1], (s.pflags & F_SUP1) != 0, w) & span) : 0u;
     const uint32_t m1 = (en & EN_M1) ? (missile_word(s.nusiz1, s.pos[OB_M1], w) & span) : 0u;
     // collision latches: any common pixel inside the span.  Every pair has a player, missile or ball in it, and most
     // 32-pixel words hold none of them (playfield only): skip the fifteen tests there
@@ -343,34 +356,35 @@ MN_HD MN_NOINLINE void tia_advance(Ctx& c, int32_t clock) {
     }
     const int32_t old_pos = s.fb_pos;
     if (n != 0) tia_render(c, n, from_sol - MN_HBLANK);
-    if ((s.flags & F_HMBLANK) && from_sol < MN_HBLANK + 8) {
+    if ((s.pflags & F_HMBLANK) && from_sol < MN_HBLANK + 8) {
       int32_t blanks = (MN_HBLANK + 8) - from_sol;
       const int32_t room = MN_FRAME_BYTES - old_pos; if (blanks > room) blanks = room;
-      if (s.flags & F_PIXELS) fill_px(c.fb + ((s.flags & F_CURFB) ? MN_FRAME_BYTES : 0) + old_pos, blanks, 0u);
-      if (n + from_sol >= MN_HBLANK + 8) s.flags &= ~F_HMBLANK;
+      if (s.pflags & F_PIXELS) fill_px(c.fb + ((s.pflags & F_CURFB) ? MN_FRAME_BYTES : 0) + old_pos, blanks, 0u);
+      if (n + from_sol >= MN_HBLANK + 8) s.pflags &= ~F_HMBLANK;
     }
     if (s.clks_to_eol == 228) {   // line finished: playfield mirror latches, first-copy suppression ends
-      s.flags = (s.flags & ~(F_SUP0 | F_SUP1 | F_PFREFL)) | ((s.ctrlpf & 1) ? F_PFREFL : 0u);
+      s.pflags = (s.pflags & ~(F_SUP0 | F_SUP1 | F_PFREFL)) | ((s.ctrlpf & 1) ? F_PFREFL : 0u);
     }
   } while (s.clk_last_update < clock);
 }
 
 
 MN_HD MN_NOINLINE void tia_refresh_grp(EnvState& s) {
-  uint32_t g0 = (s.flags & F_VDELP0) ? s.dgrp0 : s.grp0;
-  uint32_t g1 = (s.flags & F_VDELP1) ? s.dgrp1 : s.grp1;
-  s.cur_grp0 = uint8_t((s.flags & F_REFP0) ? rev8(g0) : g0);
-  s.cur_grp1 = uint8_t((s.flags & F_REFP1) ? rev8(g1) : g1);
+  uint32_t g0 = (s.pflags & F_VDELP0) ? s.dgrp0 : s.grp0;
+  uint32_t g1 = (s.pflags & F_VDELP1) ? s.dgrp1 : s.grp1;
+  s.cur_grp0 = uint8_t((s.pflags & F_REFP0) ? rev8(g0) : g0);
+  s.cur_grp1 = uint8_t((s.pflags & F_REFP1) ? rev8(g1) : g1);
   s.enabled = uint8_t((s.enabled & ~(EN_P0 | EN_P1)) | (s.cur_grp0 ? EN_P0 : 0) | (s.cur_grp1 ? EN_P1 : 0));
 }
 MN_HD MN_NOINLINE void tia_refresh_misc(EnvState& s) {
-  bool bl = (s.flags & F_VDELBL) ? (s.flags & F_DENABL) != 0 : (s.flags & F_ENABL) != 0;
-  bool m0 = (s.flags & F_ENAM0) && !(s.flags & F_RESMP0);
-  bool m1 = (s.flags & F_ENAM1) && !(s.flags & F_RESMP1);
+  bool bl = (s.pflags & F_VDELBL) ? (s.pflags & F_DENABL) != 0 : (s.pflags & F_ENABL) != 0;
+  bool m0 = (s.pflags & F_ENAM0) && !(s.pflags & F_RESMP0);
+  bool m1 = (s.pflags & F_ENAM1) && !(s.pflags & F_RESMP1);
   s.enabled = uint8_t((s.enabled & ~(EN_BL | EN_M0 | EN_M1 | EN_PF)) | (bl ? EN_BL : 0) | (m0 ? EN_M0 : 0) |
                       (m1 ? EN_M1 : 0) | (s.pf ? EN_PF : 0));
 }
 MN_HD MN_INLINE void set_flag(EnvState& s, uint32_t f, bool on) { s.flags = on ? (s.flags | f) : (s.flags & ~f); }
+MN_HD MN_INLINE void set_pflag(EnvState& s, uint32_t f, bool on) { s.pflags = on ? (s.pflags | f) : (s.pflags & ~f); }
 
 // number of the 15 HMOVE extra clocks that still count, as a movement in pixels (+ = right)
 MN_HD MN_INLINE int hmove_delta(int cyc, int hm) {
@@ -432,15 +446,15 @@ MN_HD MN_NOINLINE void tia_apply(Ctx& c, int32_t rel, uint32_t addr, uint32_t v)
   tia_advance(c, rel + delay);
   switch (addr) {
     case 0x01: s.vblank = uint8_t(v); break;
-    case 0x04: s.nusiz0 = uint8_t(v); s.flags &= ~F_SUP0; break;
-    case 0x05: s.nusiz1 = uint8_t(v); s.flags &= ~F_SUP1; break;
+    case 0x04: s.nusiz0 = uint8_t(v); s.pflags &= ~F_SUP0; break;
+    case 0x05: s.nusiz1 = uint8_t(v); s.pflags &= ~F_SUP1; break;
     case 0x06: case 0x07: case 0x08: case 0x09: s.col[addr - 0x06] = uint8_t(v & 0xFE); break;
     case 0x0A:
       s.ctrlpf = uint8_t(v);
-      if (hpos < (68 + 79)) set_flag(s, F_PFREFL, (v & 1) != 0);
+      if (hpos < (68 + 79)) set_pflag(s, F_PFREFL, (v & 1) != 0);
       break;
     // (register groups that differ only in a bit position share one body: the 45-case switch was 9 KB of footprint)
-    case 0x0B: case 0x0C: set_flag(s, F_REFP0 << (addr - 0x0B), (v & 0x08) != 0); tia_refresh_grp(s); break;   // REFP0, REFP1
+    case 0x0B: case 0x0C: set_pflag(s, F_REFP0 << (addr - 0x0B), (v & 0x08) != 0); tia_refresh_grp(s); break;   // REFP0, REFP1
     case 0x0D: case 0x0E: case 0x0F: {   // PF0 (high nibble), PF1, PF2 -> bits 0..3, 4..11, 12..19
       const uint32_t field = (addr == 0x0D) ? 0x0000Fu : (addr == 0x0E) ? 0x00FF0u : 0xFF000u;
       const uint32_t val = (addr == 0x0D) ? ((v >> 4) & 0x0Fu) : (addr == 0x0E) ? (v << 4) : (v << 12);
@@ -454,7 +468,7 @@ MN_HD MN_NOINLINE void tia_apply(Ctx& c, int32_t rel, uint32_t addr, uint32_t v)
       const int zone = resp_zone((p == OB_P0) ? s.nusiz0 : s.nusiz1, s.pos[p], newx);
       if (zone == 1) tia_advance(c, rel + 11);
       s.pos[p] = uint8_t(newx);
-      set_flag(s, (p == OB_P0) ? F_SUP0 : F_SUP1, zone >= 0);
+      set_pflag(s, (p == OB_P0) ? F_SUP0 : F_SUP1, zone >= 0);
       break;
     }
     case 0x12: case 0x13: case 0x14:   // RESM0, RESM1, RESBL -> OB_M0 (1), OB_M1 (3), OB_BL (4)
@@ -462,37 +476,37 @@ MN_HD MN_NOINLINE void tia_apply(Ctx& c, int32_t rel, uint32_t addr, uint32_t v)
       break;
     case 0x1B: s.grp0 = uint8_t(v); s.dgrp1 = s.grp1; tia_refresh_grp(s); break;
     case 0x1C:
-      s.grp1 = uint8_t(v); s.dgrp0 = s.grp0; set_flag(s, F_DENABL, (s.flags & F_ENABL) != 0);
+      s.grp1 = uint8_t(v); s.dgrp0 = s.grp0; set_pflag(s, F_DENABL, (s.pflags & F_ENABL) != 0);
       tia_refresh_grp(s); tia_refresh_misc(s);
       break;
-    case 0x1D: case 0x1E: case 0x1F: set_flag(s, F_ENAM0 << (addr - 0x1D), (v & 2) != 0); tia_refresh_misc(s); break;   // ENAM0, ENAM1, ENABL
+    case 0x1D: case 0x1E: case 0x1F: set_pflag(s, F_ENAM0 << (addr - 0x1D), (v & 2) != 0); tia_refresh_misc(s); break;   // ENAM0, ENAM1, ENABL
     case 0x20: case 0x21: case 0x22: case 0x23: case 0x24:   // HMP0, HMP1, HMM0, HMM1, HMBL -> OB_P0 (0), OB_P1 (2), OB_M0 (1), OB_M1 (3), OB_BL (4)
       s.hm[(0x43120u >> (4u * (addr - 0x20))) & 7u] = uint8_t(v >> 4);
       break;
-    case 0x25: case 0x26: set_flag(s, F_VDELP0 << (addr - 0x25), (v & 1) != 0); tia_refresh_grp(s); break;   // VDELP0, VDELP1
-    case 0x27: set_flag(s, F_VDELBL, (v & 1) != 0); tia_refresh_misc(s); break;
+    case 0x25: case 0x26: set_pflag(s, F_VDELP0 << (addr - 0x25), (v & 1) != 0); tia_refresh_grp(s); break;   // VDELP0, VDELP1
+    case 0x27: set_pflag(s, F_VDELBL, (v & 1) != 0); tia_refresh_misc(s); break;
     case 0x28: case 0x29: {
       const bool one = (addr == 0x29);
       const uint32_t f = one ? F_RESMP1 : F_RESMP0;
-      if ((s.flags & f) && !(v & 2)) {
+      if ((s.pflags & f) && !(v & 2)) {
         const int ns = (one ? s.nusiz1 : s.nusiz0) & 7;
         const int middle = (ns == 5) ? 8 : (ns == 7) ? 16 : 4;
         s.pos[one ? OB_M1 : OB_M0] = uint8_t((s.pos[one ? OB_P1 : OB_P0] + middle) % 160);
       }
-      set_flag(s, f, (v & 2) != 0);
+      set_pflag(s, f, (v & 2) != 0);
       tia_refresh_misc(s);
       break;
     }
     case 0x2A: {
       const int cyc = hpos / 3;
-      if (cyc <= 20 || cyc == 75) s.flags |= F_HMBLANK;
+      if (cyc <= 20 || cyc == 75) s.pflags |= F_HMBLANK;
 #pragma unroll 1
       for (int k = 0; k < 5; ++k) {   // (rolled: five copies of hmove_delta were 2 KB of instruction footprint)
         int p = int(s.pos[k]) + hmove_delta(cyc, s.hm[k]);
         if (p >= 160) p -= 160; else if (p < 0) p += 160;
         s.pos[k] = uint8_t(p);
       }
-      s.flags &= ~(F_SUP0 | F_SUP1);
+      s.pflags &= ~(F_SUP0 | F_SUP1);
       break;
     }
     case 0x2B: for (int k = 0; k < 5; ++k) s.hm[k] = 0; break;
@@ -503,33 +517,72 @@ MN_HD MN_NOINLINE void tia_apply(Ctx& c, int32_t rel, uint32_t addr, uint32_t v)
 
 // a frame ends on the picture side: account for what it left in its buffer (see F_ANOMALY)
 MN_HD MN_INLINE void picture_close_frame(EnvState& s) {
-  const int b = (s.flags & F_CURFB) ? 1 : 0;
+  const int b = (s.pflags & F_CURFB) ? 1 : 0;
   const uint32_t len = uint32_t(s.fb_pos);
-  if (s.flags & F_PIXELS) { if (s.pend_len[b] > len) s.flags |= F_ANOMALY; s.pend_len[b] = 0; }
+  if (s.pflags & F_PIXELS) { if (s.pend_len[b] > len) s.pflags |= F_ANOMALY; s.pend_len[b] = 0; }
   else if (len > s.pend_len[b]) s.pend_len[b] = uint16_t(len);
 }
 // ... and the next one starts (what the emulated TIA's frame start does to the picture)
 MN_HD MN_INLINE void picture_open_frame(EnvState& s, bool pixels) {
   picture_close_frame(s);
-  s.flags ^= F_CURFB;
-  s.flags = pixels ? (s.flags | F_PIXELS) : (s.flags & ~F_PIXELS);
+  s.pflags ^= F_CURFB;
+  s.pflags = pixels ? (s.pflags | F_PIXELS) : (s.pflags & ~F_PIXELS);
   s.clk_last_update = 228 * MN_YSTART;
   s.clks_to_eol = 228;
   s.fb_pos = 0;
 }
 
-// run every queued write through the picture
-MN_HD MN_NOINLINE void tia_drain(Ctx& c) {
-  const int n = c.fifo_n;
-  for (int i = 0; i < n; ++i) {
-    const uint32_t e = c.fifo[i];
+// ---- picture side proper: what the partner warp does with one hand-off (the host test build runs it inline).
+// `cnt` queued writes of buffer `buf` go through the picture; then the picture is brought up to colour clock
+// `sync_clk` if one was asked for (collision-latch reads), and the frame is closed if the unit is over.
+MN_HD MN_NOINLINE void picture_process(Ctx& c, int buf, int cnt, int32_t sync_clk, int cmd) {
+  const uint32_t* q = c.fifo + buf * MN_FIFO_BUF;
+  for (int i = 0; i < cnt; ++i) {
+    const uint32_t e = q[i];
     if (e & MN_FIFO_FRAME) picture_open_frame(*c.s, (e & 1u) != 0);
     else tia_apply(c, int32_t(e & 0x1FFFFu), (e >> 17) & 0x3Fu, (e >> 23) & 0xFFu);
   }
-  c.fifo_n = 0;
+  if (sync_clk >= 0) tia_advance(c, sync_clk);
+  if (cmd == PIC_END) picture_close_frame(*c.s);
 }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t mbox_load(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ void mbox_store(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
+// bounded spin: a protocol error must end the kernel with garbage and an error code, never hang the GPU
+__device__ __forceinline__ bool mbox_wait(const uint32_t* p, uint32_t want) {
+  for (uint32_t spins = 0; spins < (1u << 24); ++spins) {
+    if (mbox_load(p) == want) return true;
+    __nanosleep(20);
+  }
+  return false;
+}
+#endif
+// ---- program side: hand the buffer being filled to the picture side and go on with the other one.
+// `blocking`: wait until the picture side is through with it (the caller needs its results).
+MN_HD MN_NOINLINE void tia_handoff(Ctx& c, int32_t sync_clk, int cmd, bool blocking) {
+  const int buf = (c.fifo_n >> 4) & 1, cnt = MN_FILL(c.fifo_n);
+#ifdef __CUDA_ARCH__
+  uint32_t* mb = c.fifo + MN_MBOX;
+  const uint32_t h = c.hseq;
+  // every earlier hand-off must have been consumed: the buffer about to be refilled is the one handed off before
+  if (c.mbox_timeout || !mbox_wait(mb + MB_DONE, h)) c.mbox_timeout = true;   // (after one timeout: no more waiting)
+  mbox_store(mb + MB_REQ, uint32_t(cnt) | (uint32_t(cmd) << 8));
+  mbox_store(mb + MB_SYNC, uint32_t(sync_clk));
+  __threadfence_block();
+  mbox_store(mb + MB_HAND, h + 1u);
+  if (blocking) { if (c.mbox_timeout || !mbox_wait(mb + MB_DONE, h + 1u)) c.mbox_timeout = true; __threadfence_block(); }
+#else
+  (void)blocking;
+  picture_process(c, buf, cnt, sync_clk, cmd);
+#endif
+  c.hseq++;
+  c.fifo_n = (buf ^ 1) << 4;
+}
+// every queued write goes to the picture side (which catches up on its own time)
+MN_HD MN_INLINE void tia_drain(Ctx& c) { if (MN_FILL(c.fifo_n) != 0) tia_handoff(c, -1, PIC_DRAIN, false); }
 MN_HD MN_INLINE void fifo_push(Ctx& c, uint32_t e) {
-  if (c.fifo_n >= MN_FIFO_CAP) tia_drain(c);   // safety net; warps drain together well before this (MN_FIFO_HIGH)
+  if (MN_FILL(c.fifo_n) >= MN_FIFO_CAP) tia_drain(c);   // safety net; warps hand off together well before this (MN_FIFO_HIGH)
   c.fifo[c.fifo_n++] = e;
 }
 
@@ -570,9 +623,9 @@ MN_HD MN_NOINLINE uint32_t tia_peek(Ctx& c, uint32_t addr) {
   const uint32_t noise = s.dbus & 0x3Fu;
   const uint32_t reg = addr & 0x0F;
   if (reg < 8) {
-    // collision latches need the picture up to date
-    tia_drain(c);
-    tia_advance(c, s.cycles * 3 - s.clk_frame_start);
+    // collision latches need the picture up to date: hand off what is queued, ask for the picture to be advanced to
+    // now, and wait for it
+    tia_handoff(c, s.cycles * 3 - s.clk_frame_start, PIC_DRAIN, true);
     // latch pairs in read order: CXM0P CXM1P CXP0FB CXP1FB CXM0FB CXM1FB CXBLPF CXPPMM
     const uint32_t hi = (reg == 6) ? 0x1000u : (reg == 7) ? 0x2000u : (1u << (2 * reg));
     const uint32_t lo = (reg == 6) ? 0u : (reg == 7) ? 0x4000u : (2u << (2 * reg));
@@ -821,7 +874,7 @@ MN_HD MN_INLINE void wr(Ctx& c, const Mem& mm, Cpu& r, uint32_t addr, uint32_t v
   // (same arithmetic as tia_poke, which stays the reference for everything else)
   const uint32_t a6 = addr & 0x3Fu;
   const int32_t rel = r.cycles * 3 - r.clk0;
-  if (!(addr & 0x1080u) && a6 >= 0x04u && rel < 228 * (MN_MAX_SCANLINES + 1) && r.fifo_n < MN_FIFO_CAP) {
+  if (!(addr & 0x1080u) && a6 >= 0x04u && rel < 228 * (MN_MAX_SCANLINES + 1) && MN_FILL(r.fifo_n) < MN_FIFO_CAP) {
     if (a6 <= 0x2Cu && !(a6 >= 0x15u && a6 <= 0x1Au)) { m32w(mm.fifo + uint32_t(r.fifo_n) * 4u, uint32_t(rel) | (a6 << 17) | (v << 23)); r.fifo_n++; }
     return;
   }
@@ -1158,7 +1211,7 @@ MN_HD MN_INLINE bool cpu_fast(const Mem& mm, Cpu& r, const bool go) {
   const uint32_t a6 = wa & 0x3Fu;
   const int32_t rel = cyc * 3 - r.clk0;
   const uint32_t rel_ok = uint32_t(rel < 228 * (MN_MAX_SCANLINES + 1));
-  const uint32_t w_fifo = w_tia & uint32_t(a6 >= 0x04u) & rel_ok & uint32_t(r.fifo_n < MN_FIFO_CAP);
+  const uint32_t w_fifo = w_tia & uint32_t(a6 >= 0x04u) & rel_ok & uint32_t(MN_FILL(r.fifo_n) < MN_FIFO_CAP);
   const uint32_t w_sync = w_tia & uint32_t(a6 == 0x02u) & rel_ok;
   const uint32_t w_ok = uint32_t(!has_write) | w_ram | w_fifo | w_sync;
   const uint32_t w2_ok = uint32_t((f & FX_PUSH2) == 0u) | ((sp - 1u) >> 7 & 1u);
@@ -1350,7 +1403,7 @@ MN_HD MN_INLINE void console_reset(Ctx& c, uint32_t rnd) {
   // TIA (the write FIFO is empty here: units always end drained)
   s.clk_frame_start = 0; s.clk_last_update = 0; s.clks_to_eol = 228; s.vsync_finish_clk = MN_NEVER; s.fb_pos = 0;
   s.dump_disabled_cycle = 0; s.pf = 0; s.collision = 0; s.pend_len[0] = s.pend_len[1] = 0;
-  s.flags &= (F_TERMINAL | F_STARTED | F_INPT4 | F_INPT5);
+  s.flags &= (F_TERMINAL | F_STARTED | F_INPT4 | F_INPT5); s.pflags = 0;
   s.vsync = s.vblank = s.vblank_cpu = s.nusiz0 = s.nusiz1 = s.ctrlpf = s.enabled = 0;
   for (int k = 0; k < 4; ++k) s.col[k] = 0;
   s.grp0 = s.grp1 = s.dgrp0 = s.dgrp1 = s.cur_grp0 = s.cur_grp1 = 0;
@@ -1404,13 +1457,13 @@ MN_HD MN_INLINE void unit_init(Ctx& c, Unit& u, int kind, int action, int count,
   EnvState& s = *c.s;
   u.kind = kind; u.idx = 0; u.action = action; u.reward = 0; u.in_frame = false; u.frozen_last = false; u.budget = 0;
   u.job_is_act = false; u.nstart = 0;
-  c.fifo_n = 0;
-  s.flags &= ~F_ANOMALY;
+  // (the write queue is empty here -- units end drained -- and c.fifo_n already points at the buffer to fill)
+  s.pflags &= ~F_ANOMALY;
   if (kind == U_ACTS) { u.total = count; return; }
   if (kind == U_POWER_ON) {
     rng_seed(s.rng, seed);
     for (int i = 0; i < 128; ++i) ram_at(c, i) = uint8_t(rng_next(s.rng));
-    s.flags = 0; s.frame_number = 0; s.ring_head = 0; s.pend_len[0] = s.pend_len[1] = 0;
+    s.flags = 0; s.pflags = 0; s.frame_number = 0; s.ring_head = 0; s.pend_len[0] = s.pend_len[1] = 0;
   }
   s.episode_frame_number = 0;
   s.left_paddle = s.right_paddle = MN_PADDLE_DEFAULT;
@@ -1454,8 +1507,8 @@ MN_HD MN_NOINLINE void unit_job_begin(Ctx& c, Unit& u) {
     u.in_frame = true;
   }
 }
-MN_HD MN_INLINE void hot_init(const Unit& u, Hot& h) {
-  h.in_frame = false; h.more = u.idx < u.total; h.budget = 0; h.cpu.stop = false; h.cpu.fifo_n = 0; h.instr = 0; h.jobs = 0;
+MN_HD MN_INLINE void hot_init(const Ctx& c, const Unit& u, Hot& h) {
+  h.in_frame = false; h.more = u.idx < u.total; h.budget = 0; h.cpu.stop = false; h.cpu.fifo_n = c.fifo_n; h.instr = 0; h.jobs = 0;
   // cpu_fast issues its loads before it knows whether the lane runs at all: the registers they are addressed from
   // must be valid (any cartridge page, any PC) from the first tick on, not only after the first cpu_load
   h.cpu.axys = 0; h.cpu.PC = 0x1000u; h.cpu.P = 0; h.cpu.nz = 0; h.cpu.dbus = 0; h.cpu.segmap = 0; h.cpu.hot_lo = 0x1000u;
@@ -1481,20 +1534,20 @@ static inline bool cpu_fast_host(Ctx& c, const Mem& mm, Cpu& r) {
   if (g_fast_mode == 1) return cpu_fast<false>(mm, r, true);
   const Cpu before = r;
   const EnvState s_before = *c.s;
-  uint8_t ram0[128], ram1[128]; uint32_t fifo0[MN_FIFO_CAP], fifo1[MN_FIFO_CAP];
+  uint8_t ram0[128], ram1[128]; uint32_t fifo0[MN_MBOX], fifo1[MN_MBOX];
   for (int j = 0; j < 128; ++j) ram0[j] = ram_at(c, j);
-  for (int j = 0; j < MN_FIFO_CAP; ++j) fifo0[j] = c.fifo[j];
+  for (int j = 0; j < MN_MBOX; ++j) fifo0[j] = c.fifo[j];
   if (!cpu_fast<false>(mm, r, true)) { ++g_fast_refused; return false; }
   const Cpu fast = r;
   for (int j = 0; j < 128; ++j) { ram1[j] = ram_at(c, j); ram_at(c, j) = ram0[j]; }
-  for (int j = 0; j < MN_FIFO_CAP; ++j) { fifo1[j] = c.fifo[j]; c.fifo[j] = fifo0[j]; }
+  for (int j = 0; j < MN_MBOX; ++j) { fifo1[j] = c.fifo[j]; c.fifo[j] = fifo0[j]; }
   r = before;
   cpu_step<false>(c, mm, r);
   const Cpu& g = r;
   bool same = g.axys == fast.axys && g.PC == fast.PC && g.P == fast.P && g.nz == fast.nz && g.dbus == fast.dbus && g.cycles == fast.cycles &&
               g.fifo_n == fast.fifo_n && g.segmap == fast.segmap && g.stop == before.stop;
   for (int j = 0; j < 128; ++j) same = same && ram_at(c, j) == ram1[j];
-  for (int j = 0; j < g.fifo_n && j < MN_FIFO_CAP; ++j) same = same && c.fifo[j] == fifo1[j];
+  for (int j = 0; j < MN_MBOX; ++j) same = same && c.fifo[j] == fifo1[j];
   EnvState sa = *c.s, sb = s_before;
   sa.cycles = sb.cycles = 0; sa.dbus = sb.dbus = 0;   // scratch copies the slow bus functions leave behind
   same = same && memcmp(&sa, &sb, sizeof(EnvState)) == 0;
@@ -1542,15 +1595,16 @@ MN_HD MN_INLINE void unit_tick(Ctx& c, const Mem& mm, Unit& u, Hot& h, const boo
 }
 
 // the flat loop's drain: every queued write of this env goes through the picture
-MN_HD MN_INLINE void hot_drain(Ctx& c, Hot& h) { c.fifo_n = h.cpu.fifo_n; tia_drain(c); h.cpu.fifo_n = 0; }
+MN_HD MN_INLINE void hot_drain(Ctx& c, Hot& h) { c.fifo_n = h.cpu.fifo_n; tia_drain(c); h.cpu.fifo_n = c.fifo_n; }
 
 // after the unit's last tick: flush the picture and report whether the pixel-less frames were harmless
 MN_HD MN_INLINE bool unit_finish(Ctx& c, Hot& h) {
   EnvState& s = *c.s;
-  hot_drain(c, h);
-  picture_close_frame(s);
-  const bool bad = (s.flags & F_ANOMALY) || s.pend_len[0] != 0 || s.pend_len[1] != 0;
-  s.flags &= ~F_ANOMALY;
+  c.fifo_n = h.cpu.fifo_n;
+  tia_handoff(c, -1, PIC_END, true);   // the rest of the queue, then the frame is closed; wait for the verdict
+  h.cpu.fifo_n = c.fifo_n;
+  const bool bad = (s.pflags & F_ANOMALY) || s.pend_len[0] != 0 || s.pend_len[1] != 0;
+  s.pflags &= ~F_ANOMALY;
   return bad;
 }
 

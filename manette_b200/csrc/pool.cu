@@ -32,12 +32,12 @@
 namespace mn {
 
 #define MN_MAX_GAMES 16
-#define MN_WARPS_PER_BLOCK 4
-#define MN_THREADS (MN_WARPS_PER_BLOCK * 32)
-#define MN_CORE_WORDS 43   // EnvState (42 words) padded to an odd stride: conflict-free across slots
+#define MN_WARPS_PER_BLOCK 4                  // 6502 warps per block, one per SM sub-partition ...
+#define MN_THREADS (2 * MN_WARPS_PER_BLOCK * 32)   // ... each with a picture-side partner warp (warp w + 4)
+#define MN_CORE_WORDS 43   // EnvState is 43 words: an odd stride, conflict-free across slots
 #define MN_PLANE (MN_IMG * MN_IMG)
 
-static_assert(sizeof(EnvState) == 168, "EnvState layout changed: update MN_CORE_WORDS");
+static_assert(sizeof(EnvState) == 172 && MN_CORE_WORDS * 4 == 172, "EnvState layout changed: update MN_CORE_WORDS (odd)");
 
 // PIL Image.resize((84,84), NEAREST) column map for a 160-wide source (atari_emulator.py:84); rows
 // are floor((y + 0.5) * 2.5).  Golden copy: tests/golden/resize_lut.npz.
@@ -198,11 +198,39 @@ __global__ void k_single_list(PoolDev p, int which, int env, int ale_action) {
   }
 }
 
+// The picture side of the envs of one 6502 warp, on its partner warp: lane l serves the env of lane l.  It waits for
+// hand-offs (emu_core.cuh tia_handoff) and renders them while the 6502 warp runs on.  Requests published by one
+// instruction of the 6502 warp (the warp-wide hand-off of k_round's loop) are seen together and rendered by all
+// lanes in step -- the long branchy rendering code is entered by the whole warp, as it was when it ran inline.
+__device__ __forceinline__ void picture_warp(Ctx& c, unsigned wmask) {
+  uint32_t* mb = c.fifo + MN_MBOX;
+  uint32_t pseq = 0;
+  bool fin = false;
+  for (;;) {
+    const bool req = !fin && mbox_load(mb + MB_HAND) != pseq;
+    if (!__any_sync(wmask, req)) {
+      if (__all_sync(wmask, fin)) break;
+      __nanosleep(40);
+      continue;
+    }
+    if (req) {
+      __threadfence_block();
+      const uint32_t rq = mbox_load(mb + MB_REQ);
+      const int32_t sync_clk = int32_t(mbox_load(mb + MB_SYNC));
+      const int cmd = int(rq >> 8);
+      if (cmd == PIC_EXIT) fin = true;
+      else picture_process(c, int(pseq & 1u), int(rq & 0xFFu), sync_clk, cmd);
+      __threadfence_block();
+      mbox_store(mb + MB_DONE, ++pseq);
+    }
+  }
+}
+
 // One round of emulation for the envs on list `in`.  Dynamic shared memory:
 //   [rom | tables | core slots (4 warps x slots x 43 words) | ram (4 warps x slots x 132 B: 128 used, odd word pitch)
-//    | TIA write FIFOs (4 warps x slots x 17 words)]
+//    | TIA write queues (4 warps x slots x 37 words: two buffers of 16 + the hand-off mailbox)]
 template <bool TRACK>
-__global__ void __launch_bounds__(MN_THREADS, 2) k_round(PoolDev p, int mode, int in, int out) {
+__global__ void __launch_bounds__(MN_THREADS, 1) k_round(PoolDev p, int mode, int in, int out) {
   extern __shared__ __align__(16) uint8_t smem[];
   // ---- which game does this block serve
   int gi = 0;
@@ -226,10 +254,15 @@ __global__ void __launch_bounds__(MN_THREADS, 2) k_round(PoolDev p, int mode, in
     const uint32_t* ts = reinterpret_cast<const uint32_t*>(p.tables);
     uint32_t* td = reinterpret_cast<uint32_t*>(s_tab);
     for (int i = threadIdx.x; i < int(sizeof(Tables) / 4); i += blockDim.x) td[i] = ts[i];
+    for (int i = threadIdx.x; i < nslots; i += blockDim.x) {   // mailboxes: nothing handed off, nothing done
+      uint32_t* mb = s_fifo + i * MN_FIFO_WORDS + MN_MBOX;
+      mb[MB_HAND] = 0u; mb[MB_DONE] = 0u; mb[MB_REQ] = 0u; mb[MB_SYNC] = 0u;
+    }
   }
   __syncthreads();
-  // ---- my env
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // ---- my env (the same for a 6502 lane and its picture-side partner)
+  const int warp = (threadIdx.x >> 5) & (MN_WARPS_PER_BLOCK - 1), lane = threadIdx.x & 31;
+  const bool picture_side = threadIdx.x >= MN_WARPS_PER_BLOCK * 32;
   const int m = hi - lo;
   const int wlo = lo + m * warp / MN_WARPS_PER_BLOCK, whi = lo + m * (warp + 1) / MN_WARPS_PER_BLOCK;
   const bool active = lane < whi - wlo;
@@ -242,8 +275,9 @@ __global__ void __launch_bounds__(MN_THREADS, 2) k_round(PoolDev p, int mode, in
   c.s = s; c.rom = s_rom; c.tab = s_tab;
   c.ram = s_ram + slot * MN_RAM_PITCH;
   c.fb = p.frames + size_t(e) * (2 * MN_FRAME_BYTES);
-  c.fifo = s_fifo + slot * (MN_FIFO_CAP + 1);
-  c.fifo_n = 0;
+  c.fifo = s_fifo + slot * MN_FIFO_WORDS;
+  c.fifo_n = 0; c.hseq = 0; c.mbox_timeout = false;
+  if (picture_side) { picture_warp(c, wmask); return; }
   // what this launch asks of the env
   int kind = U_ACTS, action = 0, ucount = MN_ACTION_REPEAT;
   uint32_t seed = 0;
@@ -279,7 +313,7 @@ __global__ void __launch_bounds__(MN_THREADS, 2) k_round(PoolDev p, int mode, in
       unit_init(c, u, kind, action, ucount, seed);
     }
     Hot hot;
-    hot_init(u, hot);
+    hot_init(c, u, hot);
     if (TRACK && mine && mode == ROUND_INITIAL) {   // the probe continues from the reset round
       const unsigned long long* t = p.track + size_t(e) * 5;
       hot.def_lo = t[0]; hot.def_hi = t[1]; hot.dep_lo = t[2]; hot.dep_hi = t[3];
@@ -292,7 +326,7 @@ __global__ void __launch_bounds__(MN_THREADS, 2) k_round(PoolDev p, int mode, in
     for (;;) {
       const bool work = hot_has_work(hot);
       int now = work ? hot_time(hot) : 0x7FFFFFFF;
-      if (hot.cpu.fifo_n >= MN_FIFO_HIGH) now = -1;
+      if (MN_FILL(hot.cpu.fifo_n) >= MN_FIFO_HIGH) now = -1;
       const int first = __reduce_min_sync(wmask, now);
       if (first < 0) { hot_drain(c, hot); continue; }
       if (first == 0x7FFFFFFF) break;
@@ -311,13 +345,15 @@ __global__ void __launch_bounds__(MN_THREADS, 2) k_round(PoolDev p, int mode, in
     if (!__any_sync(wmask, bad)) break;
     if (attempt == 0 && bad) atomicAdd(p.redo_count, 1ull);
   }
+  tia_handoff(c, -1, PIC_EXIT, false);   // the partner lane leaves
+  if (c.mbox_timeout) atomicExch(p.error, 2);
 
   const bool single_life = p.single_life != 0;
   if (mode != ROUND_POWER_ON && mode != ROUND_RESET) {
     const NextOut o = env_next_result(*s, res, single_life);
     const int head = s->ring_head;
     s->ring_head = uint8_t((head + 1) & (MN_STACK - 1));
-    const int pool_mode = o.pool_single ? ((s->flags & F_CURFB) ? 2 : 1) : 0;
+    const int pool_mode = o.pool_single ? ((s->pflags & F_CURFB) ? 2 : 1) : 0;
     p.push_info[e] = uint8_t(head | (pool_mode << 2));
     if (mode == ROUND_INITIAL) {
       if (out == -1 && o.terminal) atomicExch(p.error, 1);   // last of the four start frames: 'This should never happen.'
@@ -956,16 +992,20 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
     if (cfg->tab_rep[i] > h->max_rep) h->max_rep = cfg->tab_rep[i];
   }
   // env slots per warp.  Measured on B200 (profiles/): the emulation loop is bound by the latency of ONE warp's
-  // instruction stream, and lanes kept together in time (hot_time) mostly share their control flow, so a full warp
-  // costs little more than a thin one.  Use the fewest warps that still give every SM sub-partition (4 x SMs) at
-  // most one: thin warps while the pool is small, full ones from 32 x 4 x SMs environments on.
+  // instruction stream, and a second 6502 warp on an SM sub-partition slows the first one down more than it adds.
+  // So: the fewest lanes per warp for which the whole pool still fits one block (4 6502 warps + their 4 picture-side
+  // partners) per SM -- thin warps while the pool is small, and e.g. 28 lanes on 147 of the 148 SMs for 16,384
+  // environments of one game.  Beyond 32 x 4 x SMs environments the warps are full and blocks queue up.
   int slots = cfg->envs_per_warp;
   if (slots <= 0) {
-    const int subparts = 4 * prop.multiProcessorCount;
-    slots = 1;
-    while (slots < 32 && n > subparts * slots) slots *= 2;
+    slots = 32;
+    for (int sl = 1; sl <= 32; ++sl) {
+      int blocks = 0;
+      for (int g = 0; g < d.n_games; ++g) blocks += (d.games[g].n_envs + MN_WARPS_PER_BLOCK * sl - 1) / (MN_WARPS_PER_BLOCK * sl);
+      if (blocks <= prop.multiProcessorCount) { slots = sl; break; }
+    }
   }
-  if (slots != 1 && slots != 2 && slots != 4 && slots != 8 && slots != 16 && slots != 32) { delete h; return fail("mn_create: envs_per_warp must be 1,2,4,8,16 or 32"); }
+  if (slots < 1 || slots > 32) { delete h; return fail("mn_create: envs_per_warp must be 1..32"); }
   d.slots = slots;
   int blk = 0;
   for (int g = 0; g < d.n_games; ++g) {
@@ -976,7 +1016,7 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
   }
   h->round_grid = blk;
   h->round_smem = ((max_rom + 15) & ~size_t(15)) + sizeof(Tables) +
-                  size_t(MN_WARPS_PER_BLOCK) * slots * (MN_CORE_WORDS * 4 + MN_RAM_PITCH + (MN_FIFO_CAP + 1) * 4);
+                  size_t(MN_WARPS_PER_BLOCK) * slots * (MN_CORE_WORDS * 4 + MN_RAM_PITCH + MN_FIFO_WORDS * 4);
   if (h->round_smem > size_t(prop.sharedMemPerBlockOptin)) { delete h; return fail("mn_create: shared memory budget exceeded"); }
   // the attribute belongs to the function, not to this pool: several pools with different needs may coexist
   CU(cudaFuncSetAttribute(k_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(prop.sharedMemPerBlockOptin)));
@@ -1187,6 +1227,7 @@ int mn_wait(mn_handle h) {
   CU(cudaGetLastError());
   int err = 0;
   CU(cudaMemcpy(&err, h->d.error, sizeof(int), cudaMemcpyDeviceToHost));
+  if (err == 2) return fail("internal error: a 6502 lane gave up waiting for its picture-side partner (hand-off protocol)");
   if (err) return fail("episode over right after reset ('This should never happen.', atari_emulator.py:108-109)");
   return 0;
 }
@@ -1254,7 +1295,7 @@ int mn_get_screen(mn_handle h, int env, uint8_t* out) {
   CU(cudaSetDevice(h->device));
   EnvState s;
   CU(cudaMemcpy(&s, h->d.env + env, sizeof(s), cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(out, h->d.frames + size_t(env) * 2 * MN_FRAME_BYTES + ((s.flags & F_CURFB) ? MN_FRAME_BYTES : 0), MN_FRAME_BYTES,
+  CU(cudaMemcpy(out, h->d.frames + size_t(env) * 2 * MN_FRAME_BYTES + ((s.pflags & F_CURFB) ? MN_FRAME_BYTES : 0), MN_FRAME_BYTES,
                 cudaMemcpyDeviceToHost));
   return 0;
 }

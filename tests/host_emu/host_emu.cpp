@@ -11,7 +11,7 @@ using namespace mn;
 
 struct HostEnv {
   EnvState s; Ctx c; Tables tab; std::vector<uint8_t> rom; std::vector<uint8_t> fb; uint8_t ram[128];
-  uint32_t fifo[MN_FIFO_CAP];
+  uint32_t fifo[MN_FIFO_WORDS];
   int drain_at;        // drain when this many writes are pending (tests sweep it)
   int redo_count;      // units that had to be re-run with every frame drawn
   Unit last;
@@ -29,12 +29,12 @@ static void run_unit(HostEnv* e, int kind, int action, int count, uint32_t seed,
     Unit u;
     unit_init(e->c, u, kind, action, count, seed);
     Hot hot;
-    hot_init(u, hot);
+    hot_init(e->c, u, hot);
     const Mem mm = mem_of(e->c);
     // resets run the RAM-dependence probe (k_round<true>, general path only); everything else the kernels' flow
     while (hot_has_work(hot)) {
       if (kind == U_ACTS) unit_tick<false>(e->c, mm, u, hot); else unit_tick<true>(e->c, mm, u, hot);
-      if (hot.cpu.fifo_n >= e->drain_at) hot_drain(e->c, hot);
+      if (MN_FILL(hot.cpu.fifo_n) >= e->drain_at) hot_drain(e->c, hot);
     }
     const bool bad = unit_finish(e->c, hot);
     e->last = u;
@@ -57,7 +57,7 @@ void* he_create(const uint8_t* rom, int n, const char* game, uint32_t seed, int 
   int g = game_id_from_name(game);
   e->s.game = (uint8_t)g; e->s.cart = (uint8_t)detect_cart(rom, n); e->s.ctrl = (uint8_t)game_db(g).ctrl;
   e->c.s = &e->s; e->c.rom = e->rom.data(); e->c.ram = e->ram; e->c.fb = e->fb.data(); e->c.tab = &e->tab;
-  e->c.fifo = e->fifo; e->c.fifo_n = 0;
+  e->c.fifo = e->fifo; e->c.fifo_n = 0; e->c.hseq = 0; e->c.mbox_timeout = false;
   e->drain_at = MN_FIFO_HIGH; e->redo_count = 0;
   run_unit(e, U_POWER_ON, 0, 0, seed, !skip_frames);
   return e;
@@ -97,7 +97,7 @@ void* he_console_create(const uint8_t* rom, int n) {
   e->fb.assign(2 * MN_FRAME_BYTES, 0);
   e->s.game = 0; e->s.cart = (uint8_t)detect_cart(rom, n); e->s.ctrl = 0;
   e->c.s = &e->s; e->c.rom = e->rom.data(); e->c.ram = e->ram; e->c.fb = e->fb.data(); e->c.tab = &e->tab;
-  e->c.fifo = e->fifo; e->c.fifo_n = 0; e->c.all_pixels = true;
+  e->c.fifo = e->fifo; e->c.fifo_n = 0; e->c.hseq = 0; e->c.mbox_timeout = false; e->c.all_pixels = true;
   e->drain_at = MN_FIFO_HIGH; e->redo_count = 0;
   e->s.swcha = 0xFF; e->s.swchb = 0x3F; e->s.flags = F_INPT4 | F_INPT5;
   for (int i = 0; i < 4; ++i) e->s.analog[i] = MN_RES_MAX;
@@ -115,7 +115,7 @@ void he_console_step(void* h, int n_instr) {
   const Mem mm = mem_of(e->c);
   for (int i = 0; i < n_instr; ++i) {
     if (!cpu_fast_host(e->c, mm, r)) cpu_step<false>(e->c, mm, r);
-    if (r.fifo_n >= e->drain_at) { e->c.fifo_n = r.fifo_n; tia_drain(e->c); r.fifo_n = 0; }
+    if (MN_FILL(r.fifo_n) >= e->drain_at) { e->c.fifo_n = r.fifo_n; tia_drain(e->c); r.fifo_n = e->c.fifo_n; }
   }
   e->c.fifo_n = r.fifo_n;
   tia_drain(e->c);
@@ -133,12 +133,12 @@ int he_lives(void* h) { return ((HostEnv*)h)->s.lives; }
 void he_get_ram(void* h, uint8_t* out) { memcpy(out, ((HostEnv*)h)->ram, 128); }
 void he_get_screen(void* h, uint8_t* out) {
   HostEnv* e = (HostEnv*)h;
-  memcpy(out, e->fb.data() + ((e->s.flags & F_CURFB) ? MN_FRAME_BYTES : 0), MN_FRAME_BYTES);
+  memcpy(out, e->fb.data() + ((e->s.pflags & F_CURFB) ? MN_FRAME_BYTES : 0), MN_FRAME_BYTES);
 }
 // [0] the current frame buffer, [1] the other one
 void he_get_both_screens(void* h, uint8_t* out) {
   HostEnv* e = (HostEnv*)h;
-  const int cur = (e->s.flags & F_CURFB) ? 1 : 0;
+  const int cur = (e->s.pflags & F_CURFB) ? 1 : 0;
   memcpy(out, e->fb.data() + cur * MN_FRAME_BYTES, MN_FRAME_BYTES);
   memcpy(out + MN_FRAME_BYTES, e->fb.data() + (cur ^ 1) * MN_FRAME_BYTES, MN_FRAME_BYTES);
 }

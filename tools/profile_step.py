@@ -41,12 +41,14 @@ def main():
 
     for _ in range(a.decorrelate):
         step()
+    torch.cuda.profiler.start()   # ncu --profile-from-start off captures the measured steps only
     f0 = pool.total_next_calls()
     i0 = pool.total_instructions()
     t0 = time.perf_counter()
     for _ in range(a.steps):
         step()
     dt = time.perf_counter() - t0
+    torch.cuda.profiler.stop()
     fr = pool.total_next_calls() - f0
     ins = pool.total_instructions() - i0
     print("game=%s envs=%d epw=%d steps=%d next_calls=%d seconds=%.3f frames_per_s=%.1f instr_per_next=%.0f Minstr_per_s=%.1f redo=%d"

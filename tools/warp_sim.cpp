@@ -15,7 +15,7 @@
 using namespace mn;
 
 struct Lane {
-  EnvState s; Ctx c; std::vector<uint8_t> fb; uint8_t ram[128]; uint32_t fifo[MN_FIFO_CAP + 1];
+  EnvState s; Ctx c; std::vector<uint8_t> fb; uint8_t ram[128]; uint32_t fifo[MN_FIFO_WORDS];
   Unit u; Hot hot;
 };
 static Tables g_tab;
@@ -24,11 +24,11 @@ static std::vector<uint8_t> g_rom;
 static void run_alone(Lane& l, int kind, int action, int count, uint32_t seed) {
   l.c.all_pixels = true;
   unit_init(l.c, l.u, kind, action, count, seed);
-  hot_init(l.u, l.hot);
+  hot_init(l.c, l.u, l.hot);
   const Mem mm = mem_of(l.c);
   while (hot_has_work(l.hot)) {
     unit_tick<false>(l.c, mm, l.u, l.hot);
-    if (l.hot.cpu.fifo_n >= MN_FIFO_HIGH) hot_drain(l.c, l.hot);
+    if (MN_FILL(l.hot.cpu.fifo_n) >= MN_FIFO_HIGH) hot_drain(l.c, l.hot);
   }
   unit_finish(l.c, l.hot);
 }
@@ -113,7 +113,7 @@ static uint32_t classify(const Lane& l) {
       if (ea & 0x1000u) why |= R_WR_CART;
       else if (ea & 0x80u) why |= R_WR_RIOT;
       else if (a6 < 4) why |= (a6 == 2) ? R_WR_WSYNC : R_WR_TIA_LOW;
-      else if (r.fifo_n >= MN_FIFO_CAP) why |= R_FIFO_FULL;
+      else if (MN_FILL(r.fifo_n) >= MN_FIFO_CAP) why |= R_FIFO_FULL;
     }
   }
   return why;
@@ -144,7 +144,7 @@ int main(int argc, char** argv) {
     l.fb.assign(2 * MN_FRAME_BYTES, 0);
     l.s.game = uint8_t(g); l.s.cart = uint8_t(detect_cart(g_rom.data(), n)); l.s.ctrl = uint8_t(ge.ctrl);
     l.c.s = &l.s; l.c.rom = g_rom.data(); l.c.ram = l.ram; l.c.fb = l.fb.data(); l.c.tab = &g_tab;
-    l.c.fifo = l.fifo; l.c.fifo_n = 0;
+    l.c.fifo = l.fifo; l.c.fifo_n = 0; l.c.hseq = 0; l.c.mbox_timeout = false;
     run_alone(l, U_POWER_ON, 0, 0, 3u * uint32_t(i + 1));
     // decorrelate: random macro actions with FiGAR-like repeats, resets on game over
     int done = 0;
@@ -185,7 +185,7 @@ int main(int argc, char** argv) {
       if (l.s.flags & F_TERMINAL) { run_alone(l, U_RESET, 0, 0, rng_next(l.s.rng)); for (int q = 0; q < 4; ++q) run_alone(l, U_ACTS, 0, 4, 0); }
       l.c.all_pixels = false;
       unit_init(l.c, l.u, U_ACTS, ge.actions[rand() % ge.n_actions], 4, 0);
-      hot_init(l.u, l.hot);
+      hot_init(l.c, l.u, l.hot);
     }
     for (;;) {
       int first = 0x7FFFFFFF;
@@ -226,7 +226,7 @@ int main(int argc, char** argv) {
         const Mem mm = mem_of(l.c);
         unit_tick<false>(l.c, mm, l.u, l.hot);
       }
-      for (int i = 0; i < L; ++i) if (lanes[i].hot.cpu.fifo_n >= MN_FIFO_HIGH) drain = true;
+      for (int i = 0; i < L; ++i) if (MN_FILL(lanes[i].hot.cpu.fifo_n) >= MN_FIFO_HIGH) drain = true;
       if (drain) { ++drains; for (int i = 0; i < L; ++i) hot_drain(lanes[i].c, lanes[i].hot); }
     }
     for (int i = 0; i < L; ++i) unit_finish(lanes[i].c, lanes[i].hot);
