@@ -86,6 +86,7 @@ struct PoolDev {             // kernel argument block (by value)
   int32_t n_games, n_envs, slots /* env slots per warp */, depth, num_actions, nb_choices;
   int32_t single_life, random_start, seed, env_id_offset, draw_all_frames;
   int32_t sync_slack;        // lanes of a warp stay within this many CPU cycles of the slowest one (see hot_time)
+  int32_t fifo_high;         // a warp hands its TIA write queues off when one of them holds this many entries
   int32_t tab_rep[32];
   const uint8_t* roms;
   EnvState* env;
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(MN_THREADS, 1) k_round(PoolDev p, int mode, in
     for (;;) {
       const bool work = hot_has_work(hot);
       int now = work ? hot_time(hot) : 0x7FFFFFFF;
-      if (MN_FILL(hot.cpu.fifo_n) >= MN_FIFO_HIGH) now = -1;
+      if (MN_FILL(hot.cpu.fifo_n) >= p.fifo_high) now = -1;
       const int first = __reduce_min_sync(wmask, now);
       if (first < 0) { hot_drain(c, hot); continue; }
       if (first == 0x7FFFFFFF) break;
@@ -985,6 +986,8 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
   d.draw_all_frames = cfg->draw_all_frames;
   d.sync_slack = 4;
   if (const char* ev = getenv("MN_SYNC_SLACK")) d.sync_slack = atoi(ev) < 0 ? 0x3FFFFFFF : atoi(ev);
+  d.fifo_high = MN_FIFO_HIGH;
+  if (const char* ev = getenv("MN_FIFO_HIGH")) { const int v = atoi(ev); if (v >= 1 && v <= MN_FIFO_HIGH) d.fifo_high = v; }
   h->max_rep = 0;
   for (int i = 0; i < cfg->nb_choices; ++i) {
     if (cfg->tab_rep[i] < 0 || cfg->tab_rep[i] > 1000) { delete h; return fail("mn_create: tab_rep entries must be 0..1000"); }

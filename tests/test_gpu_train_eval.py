@@ -85,6 +85,15 @@ def test_gif_hook_receives_both_pooled_frames(tmp_path, monkeypatch):
     cli.random_seed = 5
     ev = mb_test.prepare_args(cli)
     assert ev.visualize == 1
+    # a folder without a checkpoint is refused (the reference's saver.restore fails loudly too) ...
+    with pytest.raises(FileNotFoundError):
+        mb_test.evaluate(ev, max_macro_steps=1)
+    mb.release_pools()
+    # ... so the run folder gets one: freshly initialised weights stored the way train.py stores them
+    from manette_b200 import checkpoints
+    from manette_b200.networks import PolicyVNetwork
+    net = PolicyVNetwork("NIPS", len(mb.csrc_info.MINIMAL_ACTIONS["breakout"]), 11)
+    checkpoints.save(os.path.join(args.debugging_folder, "checkpoints"), 0, net.state_dict())
     made, orig = [], mb_test.get_save_frame
     monkeypatch.setattr(mb_test, "get_save_frame", lambda name, fps=30: made.append(orig(name, fps)) or made[-1])
     mb_test.evaluate(ev, max_macro_steps=2)

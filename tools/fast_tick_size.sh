@@ -1,0 +1,7 @@
+#!/bin/bash
+# SASS instruction count of the fast tick (tools/fast_probe.cu: cpu_fast in a bare loop; ~25 instructions are the harness)
+set -e
+mkdir -p /tmp/probe
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -cubin -o /tmp/probe/p.cubin "$(dirname "$0")/fast_probe.cu"
+cuobjdump -sass /tmp/probe/p.cubin > /tmp/probe/p.sass
+echo "total SASS instructions: $(grep -cE '^\s+/\*[0-9a-f]{4}\*/' /tmp/probe/p.sass)"
