@@ -53,7 +53,7 @@ enum : uint32_t {
 //   [7:0]  bits of P a flag op rewrites   [15:8] their new value   [18:16] stack pointer change + 2
 //   [20:19] next PC: 0 sequential / branch, 1 effective address (JMP, JSR), 2 pulled pair + 1 (RTS)
 //   FX_* bits below; pad0: branch test (mask over the flag word | invert << 16), zero for everything else
-struct alignas(16) FastEnt { uint32_t k, d, x, dm, f, pad0, pad1, pad2; };
+struct alignas(16) FastCompact { uint32_t k, d, x, dm, f, pad0, pad1, pad2; };
 enum : uint32_t {
   FX_SPD = 16, FX_PCS = 19,
   FX_PULL = 1u << 21    /* the read phase reads 0x100 | (SP + 1) */,
@@ -63,11 +63,29 @@ enum : uint32_t {
   FX_W_PS = 1u << 26    /* write value = packed status | B (PHP) */,
   FX_PLP = 1u << 27, FX_VALID = 1u << 28, FX_PAIR = 1u << 29 /* reads a byte pair from RIOT RAM: (zp,X) (zp),Y RTS */,
   FX_PAIR_X = 1u << 30  /* pointer address = operand + X (zp,X) */, FX_PUSH2 = 1u << 31 /* second push (JSR) */ };
+// What cpu_fast actually loads: the compact entry spread over 24 words (six 16-byte shared-memory loads), every field
+// in the exact form the instruction stream consumes it -- byte-permute selectors ready made, masks as whole words,
+// the stack-pointer change as the word to add to the packed register file -- so that no field costs a shift-and-mask
+// on the serial path of the one warp that runs it (profiles/: that path is bound by its instruction count).
+struct alignas(16) FastEnt {
+  uint32_t sel_a, sel_b, sel_idx, sel_fn;        // operand / index / function selectors (perm8)
+  uint32_t sel_cout, xm, binv, pm;               // carry-out selector, operand mask, inversion of operand b, P bits rewritten
+  uint32_t dm, spd, cyc, seqinc;                 // register-file mask of the result, SP change << 24, base cycles, length
+  uint32_t cmask, cconst, rotmask, nzmask;       // carry in = (C & cmask) | cconst; rotate-in = C & rotmask; nz <- result?
+  uint32_t g, bm_nz, bm_p, pclr;                 // G_* flags; branch test over nz / over P; flag op: bits of P cleared ...
+  uint32_t pset, sel_pb, sel_padd, pad;          // ... and set; the byte pair's address = (byte sel_pb) + (byte sel_padd)
+};
+enum : uint32_t {
+  G_VALID = 1u << 0, G_NEEDPAIR = 1u << 1 /* both bytes of the pair must lie in RIOT RAM */, G_PTR = 1u << 2 /* base = the pair */,
+  G_RA_P0 = 1u << 3 /* read address = 0x100 | pair address (PLA) */, G_READ = 1u << 4, G_WRITE = 1u << 5,
+  G_PUSH = 1u << 6 /* write address = 0x100 | SP */, G_PUSH2 = 1u << 7 /* second push (JSR) */, G_W_RET = 1u << 8,
+  G_BIT = 1u << 9, G_INV = 1u << 10 /* branch test inverted */, G_PC_EA = 1u << 11, G_PC_PAIR = 1u << 12,
+  G_DECIMAL = 1u << 13, G_PAGEPEN = 1u << 14 };
 struct Tables {          // read-only, staged in shared memory by the kernels
   TabEnt e[256];
   FastEnt f[256];
 };
-static_assert(sizeof(TabEnt) == 16 && sizeof(FastEnt) == 32, "fast_entry() addresses Tables::f at byte 4096 + 32 * opcode");
+static_assert(sizeof(TabEnt) == 16 && sizeof(FastEnt) == 96, "fast_entry() addresses Tables::f at byte 4096 + 96 * opcode");
 
 // Control word of the table-driven datapath (TabEnt::k), see cpu_exec.  Operand selectors are byte-permute
 // selectors over the 8 bytes {A, X, Y, SP | M, 0x01, 0xFF, 0x00}, the function selector one over the bytes
@@ -242,11 +260,11 @@ constexpr TabEnt decode_entry(int opc) {
 }
 
 // the fast-tick entry of one opcode (FX_VALID clear: the opcode always takes the general path)
-constexpr FastEnt fast_decode_entry(int opc) {
+constexpr FastCompact fast_compact_entry(int opc) {
   const TabEnt g = decode_entry(opc);
   const uint32_t mode = g.d & 15u, op = (g.d >> 6) & 63u;
   const uint32_t len1 = (g.k >> K_LEN) & 3u;
-  FastEnt t = {g.k, g.d, g.x, g.dm, 2u << FX_SPD, 0u, 0u, 0u};
+  FastCompact t = {g.k, g.d, g.x, g.dm, 2u << FX_SPD, 0u, 0u, 0u};
   const uint32_t lenbits = len1 << K_LEN;
   // what the datapath does for a plain register store / load, borrowed for the stack forms
   const Datapath sta = datapath_control(O_STA, AM_IMP), lda = datapath_control(O_LDA, AM_IMP);
@@ -284,11 +302,46 @@ constexpr FastEnt fast_decode_entry(int opc) {
     case O_JSR: t.f = (0u << FX_SPD) | FX_VALID | (1u << FX_PCS) | FX_PUSH | FX_PUSH2 | FX_W_RET; t.d |= D_WRITE; break;
     case O_RTS: t.f = (4u << FX_SPD) | FX_VALID | (2u << FX_PCS) | FX_PAIR | FX_PAIR_STACK; break;
     case O_PHA: t.f = (1u << FX_SPD) | FX_VALID | FX_PUSH; t.d |= D_WRITE; t.k = sta.k | lenbits | (uint32_t(SEL_ZERO) << K_ISEL); break;
-    case O_PHP: t.f = (1u << FX_SPD) | FX_VALID | FX_PUSH | FX_W_PS; t.d |= D_WRITE; break;
+    // (PHP / PLP take the general path: rare, and serving them cost every tick a dozen instructions)
     case O_PLA: t.f = (3u << FX_SPD) | FX_VALID | FX_PULL; t.d |= D_READ; t.k = lda.k | lenbits | (uint32_t(SEL_ZERO) << K_ISEL); t.dm = lda.dm; break;
-    case O_PLP: t.f = (3u << FX_SPD) | FX_VALID | FX_PULL | FX_PLP; t.d |= D_READ; break;
     default: break;
   }
+  return t;
+}
+
+// the wide entry of one opcode
+constexpr FastEnt fast_decode_entry(int opc) {
+  const FastCompact c = fast_compact_entry(opc);
+  const uint32_t k = c.k, d = c.d, f = c.f;
+  FastEnt t = {};
+  t.sel_a = (k & 7u) | 0x7770u;
+  t.sel_b = ((k >> K_BSEL) & 7u) | 0x7770u;
+  t.sel_idx = ((k >> K_ISEL) & 7u) | 0x7770u;
+  t.sel_fn = ((k >> K_FN) & 7u) | 0x7770u;
+  t.sel_cout = ((k >> K_CSRC) & 3u) | 0x4440u;
+  t.xm = c.x & 0xFFFFu; t.binv = (c.x >> 16) & 0xFFu; t.pm = c.x >> 24;
+  t.dm = c.dm;
+  t.spd = (((f >> FX_SPD) & 7u) - 2u) << 24;
+  t.cyc = (d >> 12) & 15u;
+  t.seqinc = ((k >> K_LEN) & 3u) + 1u;
+  t.cconst = (k >> K_CSEL) & 1u; t.cmask = (k >> (K_CSEL + 1)) & 1u;
+  t.rotmask = (k >> 11) & 1u;
+  t.nzmask = (k & K_NZ) ? 0xFFFFFFFFu : 0u;
+  t.pclr = f & 0xFFu; t.pset = (f >> 8) & 0xFFu;
+  // branch test: flag word of the compact form = nz[8:0] | C << 9 | V << 15; here nz and P are tested where they are
+  t.bm_nz = c.pad0 & 0x1FFu; t.bm_p = (c.pad0 >> 9) & 0x41u;
+  // pair address: (zp,X): operand + X; (zp),Y: operand; RTS / PLA: SP + 1.  perm8 pools {A X Y SP | operand 0 0 0}
+  // and {A X Y SP | 0 1 0 0}
+  const bool from_stack = (f & (FX_PAIR_STACK | FX_PULL)) != 0u;
+  t.sel_pb = from_stack ? 0x5553u : 0x5554u;
+  t.sel_padd = from_stack ? 0x4445u : (f & FX_PAIR_X) ? 0x4441u : 0x4444u;
+  const uint32_t pcs = (f >> FX_PCS) & 3u;
+  t.g = ((f & FX_VALID) ? G_VALID : 0u) | ((f & FX_PAIR) ? G_NEEDPAIR : 0u) |
+        (((f & (FX_PAIR | FX_PAIR_STACK)) == FX_PAIR) ? G_PTR : 0u) | ((f & FX_PULL) ? G_RA_P0 : 0u) |
+        ((d & D_READ) ? G_READ : 0u) | ((d & D_WRITE) ? G_WRITE : 0u) | ((f & FX_PUSH) ? G_PUSH : 0u) |
+        ((f & FX_PUSH2) ? G_PUSH2 : 0u) | ((f & FX_W_RET) ? G_W_RET : 0u) | ((f & FX_BIT) ? G_BIT : 0u) |
+        ((c.pad0 >> 16) ? G_INV : 0u) | (pcs == 1u ? G_PC_EA : 0u) | (pcs == 2u ? G_PC_PAIR : 0u) |
+        ((k & K_DECIMAL) ? G_DECIMAL : 0u) | ((d & D_PAGEPEN) ? G_PAGEPEN : 0u);
   return t;
 }
 

@@ -704,9 +704,13 @@ extern __shared__ __align__(16) uint8_t mn_smem[];
 #else
 typedef uintptr_t maddr;
 #endif
+// (device: `maddr` is an address of the .shared window itself -- __cvta_generic_to_shared -- and the accessors are
+// ld.shared / st.shared with that register as the address: indexing mn_smem[] instead made the compiler rebuild the
+// window base and add it to every offset, ~9 instructions of every tick.  The "memory" clobber keeps their order
+// against the ordinary C++ accesses the slow paths make to the same bytes.)
 MN_HD MN_INLINE uint32_t m8(maddr a) {
 #if defined(__CUDA_ARCH__)
-  return mn_smem[a];
+  uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v;
 #elif defined(__CUDACC__)
   (void)a; return 0u;   // host pass of nvcc: never executed
 #else
@@ -715,7 +719,7 @@ MN_HD MN_INLINE uint32_t m8(maddr a) {
 }
 MN_HD MN_INLINE void m8w(maddr a, uint32_t v) {
 #if defined(__CUDA_ARCH__)
-  mn_smem[a] = uint8_t(v);
+  asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory");
 #elif defined(__CUDACC__)
   (void)a; (void)v;
 #else
@@ -724,7 +728,7 @@ MN_HD MN_INLINE void m8w(maddr a, uint32_t v) {
 }
 MN_HD MN_INLINE void m32w(maddr a, uint32_t v) {
 #if defined(__CUDA_ARCH__)
-  *reinterpret_cast<uint32_t*>(mn_smem + a) = v;
+  asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
 #elif defined(__CUDACC__)
   (void)a; (void)v;
 #else
@@ -733,8 +737,9 @@ MN_HD MN_INLINE void m32w(maddr a, uint32_t v) {
 }
 MN_HD MN_INLINE TabEnt tab_entry(maddr tab, uint32_t ir) {
 #if defined(__CUDA_ARCH__)
-  const uint4 q = *reinterpret_cast<const uint4*>(mn_smem + tab + ir * 16u);
-  TabEnt t; t.k = q.x; t.d = q.y; t.x = q.z; t.dm = q.w; return t;
+  TabEnt t;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t.k), "=r"(t.d), "=r"(t.x), "=r"(t.dm) : "r"(tab + ir * 16u) : "memory");
+  return t;
 #elif defined(__CUDACC__)
   (void)tab; (void)ir; TabEnt t; t.k = t.d = t.x = t.dm = 0u; return t;
 #else
@@ -743,18 +748,24 @@ MN_HD MN_INLINE TabEnt tab_entry(maddr tab, uint32_t ir) {
 }
 MN_HD MN_INLINE FastEnt fast_entry(maddr tab, uint32_t ir) {   // Tables::f follows Tables::e
 #if defined(__CUDA_ARCH__)
-  const uint4 q = *reinterpret_cast<const uint4*>(mn_smem + tab + 4096u + ir * 32u);
-  const uint2 q2 = *reinterpret_cast<const uint2*>(mn_smem + tab + 4096u + ir * 32u + 16u);
-  FastEnt t; t.k = q.x; t.d = q.y; t.x = q.z; t.dm = q.w; t.f = q2.x; t.pad0 = q2.y; t.pad1 = t.pad2 = 0u; return t;
+  const uint32_t q = tab + 4096u + ir * 96u;
+  FastEnt t;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t.sel_a), "=r"(t.sel_b), "=r"(t.sel_idx), "=r"(t.sel_fn) : "r"(q) : "memory");
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(t.sel_cout), "=r"(t.xm), "=r"(t.binv), "=r"(t.pm) : "r"(q) : "memory");
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+32];" : "=r"(t.dm), "=r"(t.spd), "=r"(t.cyc), "=r"(t.seqinc) : "r"(q) : "memory");
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+48];" : "=r"(t.cmask), "=r"(t.cconst), "=r"(t.rotmask), "=r"(t.nzmask) : "r"(q) : "memory");
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+64];" : "=r"(t.g), "=r"(t.bm_nz), "=r"(t.bm_p), "=r"(t.pclr) : "r"(q) : "memory");
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+80];" : "=r"(t.pset), "=r"(t.sel_pb), "=r"(t.sel_padd), "=r"(t.pad) : "r"(q) : "memory");
+  return t;
 #elif defined(__CUDACC__)
-  (void)tab; (void)ir; FastEnt t; t.k = t.d = t.x = t.dm = t.f = t.pad0 = t.pad1 = t.pad2 = 0u; return t;
+  (void)tab; (void)ir; FastEnt t = {}; return t;
 #else
   return reinterpret_cast<const Tables*>(tab)->f[ir];
 #endif
 }
 MN_HD MN_INLINE uint32_t m32(maddr a) {
 #if defined(__CUDA_ARCH__)
-  return *reinterpret_cast<const uint32_t*>(mn_smem + a);
+  uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v;
 #elif defined(__CUDACC__)
   (void)a; return 0u;
 #else
@@ -763,7 +774,7 @@ MN_HD MN_INLINE uint32_t m32(maddr a) {
 }
 MN_HD MN_INLINE maddr maddr_of(const void* p) {
 #if defined(__CUDA_ARCH__)
-  return maddr(reinterpret_cast<const uint8_t*>(p) - mn_smem);
+  return maddr(__cvta_generic_to_shared(p));
 #elif defined(__CUDACC__)
   (void)p; return 0u;
 #else
@@ -779,6 +790,7 @@ struct Cpu {
   uint32_t nz;       // Z <=> (nz & 0xFF) == 0 ; N <=> nz & 0x180
   uint32_t dbus;     // last value on the data bus (the undriven bits of TIA reads)
   uint32_t segmap;   // cartridge window: byte k = 1K ROM page visible at $1000 + k * $400
+  uint32_t romw;     // offset of the window in the ROM image when its four pages are consecutive (every cartridge type but E0)
   uint32_t hot_lo;   // first cartridge offset that may be a bank-switch hot spot ($1000 = none)
   int32_t cycles;
   int32_t clk0;      // EnvState::clk_frame_start (changes only between frames)
@@ -812,7 +824,7 @@ MN_HD MN_NOINLINE uint32_t make_segmap(const EnvState& s) {
 // does not touch fifo_n: that one is carried by the flat loop across frames
 MN_HD MN_INLINE void cpu_load(const EnvState& s, Cpu& r) {
   r.axys = uint32_t(s.A) | (uint32_t(s.X) << 8) | (uint32_t(s.Y) << 16) | (uint32_t(s.SP) << 24); r.PC = s.PC; r.P = s.P; r.nz = s.nz; r.dbus = s.dbus;
-  r.cycles = s.cycles; r.clk0 = s.clk_frame_start; r.cyc0 = s.clk_frame_start / 3; r.segmap = make_segmap(s); r.hot_lo = (s.cart > CART_4K) ? 0xFE0u : 0x1000u;
+  r.cycles = s.cycles; r.clk0 = s.clk_frame_start; r.cyc0 = s.clk_frame_start / 3; r.segmap = make_segmap(s); r.romw = (r.segmap & 0xFFu) << 10; r.hot_lo = (s.cart > CART_4K) ? 0xFE0u : 0x1000u;
   r.stop = (s.flags & F_STOP) != 0;
   r.def_lo = r.def_hi = r.dep_lo = r.dep_hi = 0; r.tainted = false;
 }
@@ -847,7 +859,7 @@ MN_HD MN_INLINE uint32_t rd(Ctx& c, const Mem& mm, Cpu& r, uint32_t addr) {
     c.fifo_n = r.fifo_n;
     v = rd_slow(c, addr, r.cycles, r.dbus);
     r.fifo_n = c.fifo_n;
-    if (rom) r.segmap = make_segmap(*c.s);
+    if (rom) { r.segmap = make_segmap(*c.s); r.romw = (r.segmap & 0xFFu) << 10; }
   }
   r.dbus = v;
   return v;
@@ -881,7 +893,7 @@ MN_HD MN_INLINE void wr(Ctx& c, const Mem& mm, Cpu& r, uint32_t addr, uint32_t v
   c.fifo_n = r.fifo_n;
   r.cycles = wr_slow(c, addr, v, r.cycles);
   r.fifo_n = c.fifo_n;
-  if (addr & 0x1000u) r.segmap = make_segmap(*c.s);
+  if (addr & 0x1000u) { r.segmap = make_segmap(*c.s); r.romw = (r.segmap & 0xFFu) << 10; }
   else r.stop = (c.s->flags & F_STOP) != 0;
 }
 
@@ -1124,88 +1136,84 @@ MN_HD MN_INLINE void cpu_step(Ctx& c, const Mem& mm, Cpu& r) {
 // commits.  Loads are always issued (their addresses are safe whatever the lane's state), stores are predicated.
 // A lane for which an assumption failed changes nothing and takes cpu_step: the general path is the definition, and
 // tests/ check on the host build that both agree on every instruction of every game (he_set_fast_mode(2)).
-template <bool TRACK>
+// FLAT: the cartridge window is 4 KB of consecutive ROM (2K images are staged twice, 4K / F8 / F6 banks are contiguous):
+// its address is one add.  E0 cartridges (three switchable 1K slices) go through the page map.
+template <bool FLAT>
+MN_HD MN_INLINE maddr fast_rom_addr(const Mem& mm, const Cpu& r, uint32_t addr) {
+  return FLAT ? (mm.rom + r.romw + (addr & 0xFFFu)) : rom_addr(mm, r.segmap, addr);
+}
+template <bool TRACK, bool FLAT>
 MN_HD MN_INLINE bool cpu_fast(const Mem& mm, Cpu& r, const bool go) {
   if (TRACK) return false;   // the RAM-dependence probe instruments the general path only
-  // (conditions are 0 / 1 words combined with & and |: `&&` / `||` invite the compiler to branch)
+  // (conditions are 0 / 1 words combined with & and |: `&&` / `||` invite the compiler to branch; every field of the
+  // decode entry arrives in the form it is used in, see FastEnt)
   const uint32_t pc = r.PC;
-  const uint32_t code_ok = uint32_t((pc & 0x1000u) != 0u) & uint32_t((pc & 0xFFFu) < 0xFDEu) & uint32_t((pc & 0x3FFu) < 0x3FEu);
-  const maddr ca = rom_addr(mm, r.segmap, pc);
+  // (the three bytes must not straddle a 1K page when pages need not be consecutive)
+  const uint32_t code_ok = uint32_t((pc & 0x1000u) != 0u) & uint32_t((pc & 0xFFFu) < 0xFDEu) & (FLAT ? 1u : uint32_t((pc & 0x3FFu) < 0x3FEu));
+  const maddr ca = fast_rom_addr<FLAT>(mm, r, pc);
   const uint32_t ir = m8(ca), b1 = m8(ca + 1u), b2 = m8(ca + 2u);
   const FastEnt t = fast_entry(mm.tab, ir);
-  const uint32_t k = t.k, d = t.d, f = t.f;
-  const uint32_t len1 = (k >> K_LEN) & 3u;
-  int32_t cyc = r.cycles + int32_t((d >> 12) & 15u);
-  const uint32_t seq = (pc + len1 + 1u) & 0xFFFFu;
+  const uint32_t g = t.g;
+  int32_t cyc = r.cycles + int32_t(t.cyc);
+  const uint32_t seq = (pc + t.seqinc) & 0xFFFFu;
   const uint32_t sp = r.axys >> 24;
-  // ---- a byte pair from RIOT RAM: the pointer of (zp,X) / (zp),Y, or the return address RTS pulls
-  const uint32_t p0 = (f & FX_PAIR_STACK) ? ((sp + 1u) & 0xFFu) : ((b1 + ((f & FX_PAIR_X) ? cpuX(r) : 0u)) & 0xFFu);
+  // ---- a byte pair from RIOT RAM: the pointer of (zp,X) / (zp),Y, or the return address RTS pulls; PLA reads the
+  // first byte of the same address.  address = {operand | SP} + {0 | X | 1}, both picked by table selectors
+  const uint32_t p0 = (perm8(r.axys, b1, t.sel_pb) + perm8(r.axys, 0x00000100u, t.sel_padd)) & 0xFFu;
   const uint32_t p1 = (p0 + 1u) & 0xFFu;
-  const uint32_t pair_ok = uint32_t((f & FX_PAIR) == 0u) | ((p0 & p1) >> 7);
+  const uint32_t pair_ok = uint32_t((g & G_NEEDPAIR) == 0u) | ((p0 & p1) >> 7);
   const uint32_t phi = m8(ram_addr(mm, p1));
   const uint32_t pair = m8(ram_addr(mm, p0)) | (phi << 8);
   // ---- address phase
-  const uint32_t xm = t.x & 0xFFFFu;
-  const uint32_t idx = perm8(r.axys, 0u, ((k >> K_ISEL) & 7u) | 0x7770u);
-  const bool through_ptr = (f & (FX_PAIR | FX_PAIR_STACK)) == FX_PAIR;
-  const uint32_t base = through_ptr ? pair : ((b1 | (b2 << 8)) & xm);
-  const uint32_t ea = (base + idx) & xm;
-  cyc += int32_t(uint32_t((d & D_PAGEPEN) != 0u) & uint32_t(((base ^ ea) & 0xFF00u) != 0u));
+  const uint32_t idx = perm8(r.axys, 0u, t.sel_idx);
+  const uint32_t base = (g & G_PTR) ? pair : ((b1 | (b2 << 8)) & t.xm);
+  const uint32_t ea = (base + idx) & t.xm;
+  cyc += int32_t(uint32_t((g & G_PAGEPEN) != 0u) & uint32_t(((base ^ ea) & 0xFF00u) != 0u));
   // ---- read phase: cartridge ROM away from the hot spots, RIOT RAM, or the RIOT timer before it underflows
-  const uint32_t ra = (f & FX_PULL) ? (0x100u | ((sp + 1u) & 0xFFu)) : ea;
+  const uint32_t ra = (g & G_RA_P0) ? (0x100u | p0) : ea;
   const bool r_rom = (ra & 0x1000u) != 0u;
   const uint32_t r_mem = r_rom ? uint32_t((ra & 0xFFFu) < r.hot_lo) : uint32_t((ra & 0x0280u) == 0x0080u);
   const bool r_tim = (ra & 0x1285u) == 0x0284u;
-  const uint32_t mv = m8(r_rom ? rom_addr(mm, r.segmap, ra) : ram_addr(mm, ra));
+  const uint32_t mv = m8(r_rom ? fast_rom_addr<FLAT>(mm, r, ra) : ram_addr(mm, ra));
   const uint32_t tw = m32(mm.core + uint32_t(offsetof(EnvState, timer)));   // timer | tshift << 8 (riot_peek)
   const int32_t tsc = int32_t(m32(mm.core + uint32_t(offsetof(EnvState, timer_set_cycle))));
   const uint32_t delta = uint32_t((cyc - 1) - tsc);
   const int32_t tv = int32_t(tw & 0xFFu) - int32_t(delta >> ((tw >> 8) & 0xFFu)) - 1;
-  const bool has_read = (d & D_READ) != 0u;
+  const bool has_read = (g & G_READ) != 0u;
   const uint32_t r_ok = uint32_t(!has_read) | r_mem | (uint32_t(r_tim) & uint32_t(tv >= 0));
   const uint32_t m = has_read ? (r_tim ? (uint32_t(tv) & 0xFFu) : mv) : b1;
   // ---- operate phase: the datapath of cpu_exec (nothing is masked off here: the entries of opcodes it does not
   // serve have empty commit masks)
   const uint32_t s2 = m | 0x00FF0100u;
-  const uint32_t a = perm8(r.axys, s2, (k & 7u) | 0x7770u);
-  const uint32_t b = perm8(r.axys, s2, ((k >> K_BSEL) & 7u) | 0x7770u) ^ ((t.x >> 16) & 0xFFu);
-  const uint32_t carry = r.P & 1u;
-  const uint32_t cin = ((k >> K_CSEL) & 1u) | ((k >> (K_CSEL + 1)) & carry);
+  const uint32_t a = perm8(r.axys, s2, t.sel_a);
+  const uint32_t b = perm8(r.axys, s2, t.sel_b) ^ t.binv;
+  const uint32_t cin = (r.P & t.cmask) | t.cconst;
   const uint32_t sum = a + b + cin;
-  const uint32_t rot = (k >> 11) & carry;
+  const uint32_t rot = r.P & t.rotmask;
   const uint32_t left = (a << 1) | rot;
   const uint32_t right = ((a | (rot << 8)) >> 1) | ((a & 1u) << 8);
   const uint32_t lo_sum_or = perm8(sum, a | b, 0x7740u), lo_and_xor = perm8(a & b, a ^ b, 0x7740u);
   const uint32_t fn_pool0 = perm8(lo_sum_or, lo_and_xor, 0x5410u);
   const uint32_t fn_pool1 = perm8(left, right, 0x7740u);
-  const uint32_t res = perm8(fn_pool0, fn_pool1, ((k >> K_FN) & 7u) | 0x7770u);
+  const uint32_t res = perm8(fn_pool0, fn_pool1, t.sel_fn);
   const uint32_t c_pool = perm8(perm8(sum, left, 0x7751u), right, 0x7510u);
-  const uint32_t cout = perm8(c_pool, 0u, ((k >> K_CSRC) & 3u) | 0x4440u);
+  const uint32_t cout = perm8(c_pool, 0u, t.sel_cout);
   const uint32_t vbit = ((~(a ^ b)) & (a ^ sum) & 0x80u) >> 1;
-  const uint32_t pm = t.x >> 24;
-  uint32_t P = (r.P & ~pm) | ((cout | vbit) & pm);
-  uint32_t nz = (k & K_NZ) ? res : r.nz;
-  // BIT, PLP, flag ops (mutually exclusive, each a couple of selects)
-  const uint32_t nz_hi = (m & 0x80u) << 1;
-  nz = (f & FX_BIT) ? (nz_hi | uint32_t((cpuA(r) & m) != 0u)) : nz;
-  P = (f & FX_BIT) ? ((P & ~0x40u) | (m & 0x40u)) : P;
-  nz = (f & FX_PLP) ? (nz_hi | (((m >> 1) & 1u) ^ 1u)) : nz;
-  P = (f & FX_PLP) ? (m & 0x5Du) : P;
-  P = (P & ~(f & 0xFFu)) | ((f >> 8) & 0xFFu);
-  uint32_t axys = (r.axys & ~t.dm) | ((res * 0x01010101u) & t.dm);
-  axys += (((f >> FX_SPD) & 7u) - 2u) << 24;
-  // ---- branches: one mask test over {Z: nz[7:0], N: nz[8:7], C: bit 9, V: bit 15} (FastEnt::pad0: mask | invert << 16)
-  const uint32_t flagw = (r.nz & 0x1FFu) | ((r.P & 0x41u) << 9);
-  const uint32_t taken = uint32_t((flagw & t.pad0 & 0xFFFFu) != 0u) ^ (t.pad0 >> 16);
+  uint32_t P = (r.P & ~t.pm) | ((cout | vbit) & t.pm);
+  uint32_t nz = (res & t.nzmask) | (r.nz & ~t.nzmask);
+  // BIT, flag ops (a couple of selects each)
+  nz = (g & G_BIT) ? (((m & 0x80u) << 1) | uint32_t((cpuA(r) & m) != 0u)) : nz;
+  P = (g & G_BIT) ? ((P & ~0x40u) | (m & 0x40u)) : P;
+  P = (P & ~t.pclr) | t.pset;
+  const uint32_t axys = ((r.axys & ~t.dm) | ((res * 0x01010101u) & t.dm)) + t.spd;
+  // ---- branches: taken <=> ((nz & mask) | (P & mask)) != 0, possibly inverted (Z: nz[7:0], N: nz[8:7], C, V in P)
+  const uint32_t taken = uint32_t(((r.nz & t.bm_nz) | (r.P & t.bm_p)) != 0u) ^ uint32_t((g & G_INV) != 0u);
   const uint32_t target = (seq + uint32_t(int32_t(int8_t(b1)))) & 0xFFFFu;
-  // ---- write phase: RIOT RAM, the TIA write FIFO (registers $04-$2C before the scan-line overflow point), WSYNC
-  const uint32_t wa = (f & FX_PUSH) ? (0x100u | sp) : ea;
+  // ---- write phase: RIOT RAM, the TIA write queue (registers $04-$2C before the scan-line overflow point), WSYNC
+  const uint32_t wa = (g & G_PUSH) ? (0x100u | sp) : ea;
   const uint32_t ret = (seq - 1u) & 0xFFFFu;
-  const uint32_t ps = 0x30u | (r.P & 0x5Du) | ((r.nz & 0x180u) ? 0x80u : 0u) | ((r.nz & 0xFFu) ? 0u : 0x02u);   // pack_ps | B
-  uint32_t wv = res & 0xFFu;
-  wv = (f & FX_W_RET) ? (ret >> 8) : wv;
-  wv = (f & FX_W_PS) ? ps : wv;
-  const bool has_write = (d & D_WRITE) != 0u;
+  const uint32_t wv = (g & G_W_RET) ? (ret >> 8) : (res & 0xFFu);
+  const bool has_write = (g & G_WRITE) != 0u;
   const uint32_t w_ram = uint32_t((wa & 0x1280u) == 0x0080u);
   const uint32_t w_tia = uint32_t((wa & 0x1080u) == 0u);
   const uint32_t a6 = wa & 0x3Fu;
@@ -1214,28 +1222,27 @@ MN_HD MN_INLINE bool cpu_fast(const Mem& mm, Cpu& r, const bool go) {
   const uint32_t w_fifo = w_tia & uint32_t(a6 >= 0x04u) & rel_ok & uint32_t(MN_FILL(r.fifo_n) < MN_FIFO_CAP);
   const uint32_t w_sync = w_tia & uint32_t(a6 == 0x02u) & rel_ok;
   const uint32_t w_ok = uint32_t(!has_write) | w_ram | w_fifo | w_sync;
-  const uint32_t w2_ok = uint32_t((f & FX_PUSH2) == 0u) | ((sp - 1u) >> 7 & 1u);
+  const uint32_t w2_ok = uint32_t((g & G_PUSH2) == 0u) | ((sp - 1u) >> 7 & 1u);
   const int32_t rest = 76 - ((cyc - r.cyc0) % 76);   // tia_poke: WSYNC holds the 6502 until the end of the scan line
   // ---- all assumptions held?
-  const uint32_t dec_ok = uint32_t((k & K_DECIMAL) == 0u) | uint32_t((r.P & 0x08u) == 0u);
-  const bool fast = (uint32_t(go) & code_ok & (f >> 28) & dec_ok & pair_ok & r_ok & w_ok & w2_ok & 1u) != 0u;
+  const uint32_t dec_ok = uint32_t((g & G_DECIMAL) == 0u) | uint32_t((r.P & 0x08u) == 0u);
+  const bool fast = (uint32_t(go) & code_ok & g & dec_ok & pair_ok & r_ok & w_ok & w2_ok & 1u) != 0u;   // (g & 1: G_VALID)
   // ---- commit (the stores are predicated; the rest is register moves)
   const bool do_write = fast & has_write;
   if (do_write & (w_ram != 0u)) m8w(ram_addr(mm, wa), wv);
-  if (do_write & ((f & FX_PUSH2) != 0u)) m8w(ram_addr(mm, 0x100u | ((sp - 1u) & 0xFFu)), ret & 0xFFu);
+  if (do_write & ((g & G_PUSH2) != 0u)) m8w(ram_addr(mm, 0x100u | ((sp - 1u) & 0xFFu)), ret & 0xFFu);
   const bool queued = do_write & (w_ram == 0u) & (w_fifo != 0u) & (a6 <= 0x2Cu) & !((a6 >= 0x15u) & (a6 <= 0x1Au));
   if (queued) m32w(mm.fifo + uint32_t(r.fifo_n) * 4u, uint32_t(rel) | (a6 << 17) | (wv << 23));
   if (fast) {
-    uint32_t dbus = byte_of(ir | (b1 << 8) | (b2 << 16), len1);
-    dbus = (f & FX_PAIR) ? phi : dbus;
+    uint32_t dbus = byte_of(ir | (b1 << 8) | (b2 << 16), t.seqinc - 1u);
+    dbus = (g & G_NEEDPAIR) ? phi : dbus;
     dbus = has_read ? m : dbus;
-    dbus = has_write ? ((f & FX_PUSH2) ? (ret & 0xFFu) : wv) : dbus;
+    dbus = has_write ? ((g & G_PUSH2) ? (ret & 0xFFu) : wv) : dbus;
     cyc += (has_write & (w_ram == 0u) & (w_sync != 0u) & (rest < 76)) ? rest : 0;
     cyc += taken ? (((seq ^ target) & 0xFF00u) ? 2 : 1) : 0;
-    const uint32_t pcs = (f >> FX_PCS) & 3u;
     uint32_t npc = taken ? target : seq;
-    npc = (pcs == 1u) ? ea : npc;
-    npc = (pcs == 2u) ? ((pair + 1u) & 0xFFFFu) : npc;
+    npc = (g & G_PC_EA) ? ea : npc;
+    npc = (g & G_PC_PAIR) ? ((pair + 1u) & 0xFFFFu) : npc;
     r.PC = npc; r.cycles = cyc; r.P = P; r.nz = nz; r.axys = axys; r.dbus = dbus;
     r.fifo_n += queued ? 1 : 0;
   }
@@ -1511,7 +1518,7 @@ MN_HD MN_INLINE void hot_init(const Ctx& c, const Unit& u, Hot& h) {
   h.in_frame = false; h.more = u.idx < u.total; h.budget = 0; h.cpu.stop = false; h.cpu.fifo_n = c.fifo_n; h.instr = 0; h.jobs = 0;
   // cpu_fast issues its loads before it knows whether the lane runs at all: the registers they are addressed from
   // must be valid (any cartridge page, any PC) from the first tick on, not only after the first cpu_load
-  h.cpu.axys = 0; h.cpu.PC = 0x1000u; h.cpu.P = 0; h.cpu.nz = 0; h.cpu.dbus = 0; h.cpu.segmap = 0; h.cpu.hot_lo = 0x1000u;
+  h.cpu.axys = 0; h.cpu.PC = 0x1000u; h.cpu.P = 0; h.cpu.nz = 0; h.cpu.dbus = 0; h.cpu.segmap = 0; h.cpu.romw = 0; h.cpu.hot_lo = 0x1000u;
   h.cpu.cycles = 0; h.cpu.clk0 = 0; h.cpu.cyc0 = 0;
   h.cpu.def_lo = h.cpu.def_hi = h.cpu.dep_lo = h.cpu.dep_hi = 0; h.cpu.tainted = false;
   h.def_lo = h.def_hi = h.dep_lo = h.dep_hi = 0; h.tainted = false; h.obs_bad = false;
@@ -1531,13 +1538,13 @@ static unsigned long long g_fast_taken = 0, g_fast_refused = 0;
 // returns false if the general path has to run it
 static inline bool cpu_fast_host(Ctx& c, const Mem& mm, Cpu& r) {
   if (g_fast_mode == 0) return false;
-  if (g_fast_mode == 1) return cpu_fast<false>(mm, r, true);
+  if (g_fast_mode == 1) return cpu_fast<false, false>(mm, r, true);
   const Cpu before = r;
   const EnvState s_before = *c.s;
   uint8_t ram0[128], ram1[128]; uint32_t fifo0[MN_MBOX], fifo1[MN_MBOX];
   for (int j = 0; j < 128; ++j) ram0[j] = ram_at(c, j);
   for (int j = 0; j < MN_MBOX; ++j) fifo0[j] = c.fifo[j];
-  if (!cpu_fast<false>(mm, r, true)) { ++g_fast_refused; return false; }
+  if (!cpu_fast<false, false>(mm, r, true)) { ++g_fast_refused; return false; }
   const Cpu fast = r;
   for (int j = 0; j < 128; ++j) { ram1[j] = ram_at(c, j); ram_at(c, j) = ram0[j]; }
   for (int j = 0; j < MN_MBOX; ++j) { fifo1[j] = c.fifo[j]; c.fifo[j] = fifo0[j]; }
@@ -1560,12 +1567,12 @@ static inline bool cpu_fast_host(Ctx& c, const Mem& mm, Cpu& r) {
   return true;
 }
 #endif
-template <bool TRACK>
+template <bool TRACK, bool FLAT = false>
 MN_HD MN_INLINE void unit_tick(Ctx& c, const Mem& mm, Unit& u, Hot& h, const bool elig = true) {
 #if !defined(__CUDACC__)
   if (!TRACK && elig && h.in_frame && h.budget > 1 && cpu_fast_host(c, mm, h.cpu)) { --h.budget; return; }
 #else
-  if (cpu_fast<TRACK>(mm, h.cpu, elig && h.in_frame && h.budget > 1)) { --h.budget; return; }
+  if (cpu_fast<TRACK, FLAT>(mm, h.cpu, elig && h.in_frame && h.budget > 1)) { --h.budget; return; }
 #endif
   if (!elig) return;
   if (!h.in_frame) {

@@ -33,7 +33,8 @@ namespace mn {
 
 #define MN_MAX_GAMES 16
 #define MN_WARPS_PER_BLOCK 4                  // 6502 warps per block, one per SM sub-partition ...
-#define MN_THREADS (2 * MN_WARPS_PER_BLOCK * 32)   // ... each with a picture-side partner warp (warp w + 4)
+#define MN_PARTNERS 2                         // ... each with this many picture-side partner warps (warps w + 4, w + 8),
+#define MN_THREADS ((1 + MN_PARTNERS) * MN_WARPS_PER_BLOCK * 32)   // which share the 6502 warp's environments evenly
 #define MN_CORE_WORDS 43   // EnvState is 43 words: an odd stride, conflict-free across slots
 #define MN_PLANE (MN_IMG * MN_IMG)
 
@@ -207,13 +208,19 @@ __device__ __forceinline__ void picture_warp(Ctx& c, unsigned wmask) {
   uint32_t* mb = c.fifo + MN_MBOX;
   uint32_t pseq = 0;
   bool fin = false;
+  unsigned idle_ns = 64;
   for (;;) {
     const bool req = !fin && mbox_load(mb + MB_HAND) != pseq;
     if (!__any_sync(wmask, req)) {
       if (__all_sync(wmask, fin)) break;
-      __nanosleep(40);
+      // An idle partner shares its SM sub-partition's issue slots with the 6502 warp it serves: poll rarely.  Hand-offs
+      // come ~60 us apart and only two kinds are waited for (collision-latch reads, the end of a unit), so a back-off
+      // up to ~0.5 us costs nothing that shows, while a tight poll took a third of all issued instructions (ncu).
+      __nanosleep(idle_ns);
+      if (idle_ns < 512) idle_ns += idle_ns;
       continue;
     }
+    idle_ns = 64;
     if (req) {
       __threadfence_block();
       const uint32_t rq = mbox_load(mb + MB_REQ);
@@ -224,6 +231,22 @@ __device__ __forceinline__ void picture_warp(Ctx& c, unsigned wmask) {
       __threadfence_block();
       mbox_store(mb + MB_DONE, ++pseq);
     }
+  }
+}
+
+// The flat warp loop of k_round.  One warp-wide reduction per tick carries all three decisions: the emulated time of
+// the lane furthest behind (lanes within sync_slack of it run), "some lane's TIA write queue is nearly full" (-1: every
+// lane hands off to the picture side) and "no lane has work left" (INT_MAX).
+template <bool TRACK, bool FLAT>
+__device__ __forceinline__ void run_units(Ctx& c, const Mem& mm, Unit& u, Hot& hot, unsigned wmask, int sync_slack, int fifo_high) {
+  for (;;) {
+    const bool work = hot_has_work(hot);
+    int now = work ? hot_time(hot) : 0x7FFFFFFF;
+    if (MN_FILL(hot.cpu.fifo_n) >= fifo_high) now = -1;
+    const int first = __reduce_min_sync(wmask, now);
+    if (first < 0) { hot_drain(c, hot); continue; }
+    if (first == 0x7FFFFFFF) break;
+    unit_tick<TRACK, FLAT>(c, mm, u, hot, work && now - first <= sync_slack);
   }
 }
 
@@ -241,7 +264,7 @@ __global__ void __launch_bounds__(MN_THREADS, 1) k_round(PoolDev p, int mode, in
   const int j = blockIdx.x - G.blk0;
   const int lo = int((long long)count * j / G.n_blks), hi = int((long long)count * (j + 1) / G.n_blks);
   if (hi <= lo) return;   // whole block idle (uniform)
-  const int rom_bytes = (G.rom_size + 15) & ~15;
+  const int rom_bytes = (G.rom_size == 2048) ? 4096 : ((G.rom_size + 15) & ~15);
   const int nslots = MN_WARPS_PER_BLOCK * p.slots;
   uint8_t* s_rom = smem;
   Tables* s_tab = reinterpret_cast<Tables*>(smem + rom_bytes);
@@ -252,6 +275,8 @@ __global__ void __launch_bounds__(MN_THREADS, 1) k_round(PoolDev p, int mode, in
     const uint4* src = reinterpret_cast<const uint4*>(p.roms + G.rom_off);
     uint4* dst = reinterpret_cast<uint4*>(s_rom);
     for (int i = threadIdx.x; i < rom_bytes / 16; i += blockDim.x) dst[i] = src[i];
+    // a 2K image a second time behind itself: the cartridge window is then 4 KB of consecutive bytes like any other
+    if (G.rom_size == 2048) for (int i = threadIdx.x; i < 2048 / 16; i += blockDim.x) dst[2048 / 16 + i] = src[i];
     const uint32_t* ts = reinterpret_cast<const uint32_t*>(p.tables);
     uint32_t* td = reinterpret_cast<uint32_t*>(s_tab);
     for (int i = threadIdx.x; i < int(sizeof(Tables) / 4); i += blockDim.x) td[i] = ts[i];
@@ -262,11 +287,16 @@ __global__ void __launch_bounds__(MN_THREADS, 1) k_round(PoolDev p, int mode, in
   }
   __syncthreads();
   // ---- my env (the same for a 6502 lane and its picture-side partner)
-  const int warp = (threadIdx.x >> 5) & (MN_WARPS_PER_BLOCK - 1), lane = threadIdx.x & 31;
-  const bool picture_side = threadIdx.x >= MN_WARPS_PER_BLOCK * 32;
+  const int warp = (threadIdx.x >> 5) & (MN_WARPS_PER_BLOCK - 1);
+  const int role = threadIdx.x / (MN_WARPS_PER_BLOCK * 32);   // 0: 6502 warp, 1..MN_PARTNERS: picture-side partner
+  const bool picture_side = role != 0;
   const int m = hi - lo;
   const int wlo = lo + m * warp / MN_WARPS_PER_BLOCK, whi = lo + m * (warp + 1) / MN_WARPS_PER_BLOCK;
-  const bool active = lane < whi - wlo;
+  // a partner warp serves a contiguous share of the 6502 warp's lanes with its first lanes (the picture side is the
+  // divergent half of the machine: fewer environments per warp cost it less than they would cost the 6502 side)
+  const int per = (whi - wlo + MN_PARTNERS - 1) / MN_PARTNERS;
+  const int lane = picture_side ? (role - 1) * per + int(threadIdx.x & 31) : int(threadIdx.x & 31);
+  const bool active = lane < whi - wlo && (!picture_side || int(threadIdx.x & 31) < per);
   const unsigned wmask = __ballot_sync(0xFFFFFFFFu, active);   // the lanes that vote in the loops below
   if (!active) return;
   const int e = p.lists[size_t(in) * p.n_envs + G.env0 + wlo + lane];
@@ -321,18 +351,9 @@ __global__ void __launch_bounds__(MN_THREADS, 1) k_round(PoolDev p, int mode, in
       hot.tainted = (t[4] & 1ull) != 0; hot.obs_bad = (t[4] & 2ull) != 0;
     }
     const Mem mm = mem_of(c);
-    // One warp-wide reduction per tick carries all three decisions: the emulated time of the lane furthest behind
-    // (lanes within sync_slack of it run), "some lane's TIA write FIFO is nearly full" (-1: every lane drains; the
-    // rendering path is entered by all lanes together) and "no lane has work left" (INT_MAX).
-    for (;;) {
-      const bool work = hot_has_work(hot);
-      int now = work ? hot_time(hot) : 0x7FFFFFFF;
-      if (MN_FILL(hot.cpu.fifo_n) >= p.fifo_high) now = -1;
-      const int first = __reduce_min_sync(wmask, now);
-      if (first < 0) { hot_drain(c, hot); continue; }
-      if (first == 0x7FFFFFFF) break;
-      unit_tick<TRACK>(c, mm, u, hot, work && now - first <= p.sync_slack);
-    }
+    // (block-uniform: a block serves one cartridge)
+    if (G.cart != CART_E0) run_units<TRACK, true>(c, mm, u, hot, wmask, p.sync_slack, p.fifo_high);
+    else run_units<TRACK, false>(c, mm, u, hot, wmask, p.sync_slack, p.fifo_high);
     if (mine) {
       bad = unit_finish(c, hot); res = u; atomicAdd(p.total_instr, (unsigned long long)hot.instr);
       // an env whose game ended inside this macro step is reset before anyone can look at its frames
@@ -976,6 +997,7 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
     G.rom_off = int(rom_total); G.rom_size = mg.rom_size;
     rom_total += (size_t(mg.rom_size) + 15) & ~size_t(15);
     if (size_t(mg.rom_size) > max_rom) max_rom = mg.rom_size;
+    if (max_rom < 4096) max_rom = 4096;   // 2K images are staged twice (k_round)
     G.env0 = n; G.n_envs = mg.n_envs;
     n += mg.n_envs;
     if (G.n_actions > max_actions) max_actions = G.n_actions;
