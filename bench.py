@@ -38,6 +38,8 @@ WORKLOADS = {
     # C4 is the LSTM configuration: the learner's 5-deep observation history (paac.py:107-112) is kept by the pool
     "ms_pacman_figar10_n16384": dict(games=["ms_pacman"], n=16384, rgb=False, nb_choices=11, max_rep=10, history=5),
     "mixed12_figar10_n16384": dict(games=GAMES12, n=16384, rgb=False, nb_choices=11, max_rep=10),
+    # not a BASELINE config: the game whose resets depend on RAM (steady-state leg, --steady-state)
+    "yars_revenge_figar10_n4096": dict(games=["yars_revenge"], n=4096, rgb=False, nb_choices=11, max_rep=10),
 }
 DEFAULT_WORKLOAD = "ms_pacman_figar10_n16384"
 # algorithmic HBM bytes of one next() for the emulation kernel: the two pooled raw frames it
@@ -52,7 +54,7 @@ ROUND_COUNTERS = os.path.join(ROOT, "profiles", "r2_k_round_counters.json")
 K3_COUNTERS = os.path.join(ROOT, "profiles", "r2_k3_counters.json")
 # networks whose flat fp32 gradient the synchronous-PAAC all-reduce carries (paac.py:233-256), per workload
 ARCH = {"pong_paac_n32": "NIPS", "breakout_figar10_n256": "NIPS", "seaquest_figar10_rgb_n4096": "PWYX",
-        "ms_pacman_figar10_n16384": "LSTM", "mixed12_figar10_n16384": "PWYX"}
+        "ms_pacman_figar10_n16384": "LSTM", "mixed12_figar10_n16384": "PWYX", "yars_revenge_figar10_n4096": "NIPS"}
 REAL_ALE_RAW_FPS_PER_CORE = 6000.0   # commonly quoted, NOT verifiable here (ALE is not installable offline)
 
 
@@ -323,6 +325,10 @@ def main():
     ap.add_argument("--envs-per-warp", type=int, default=0)
     ap.add_argument("--decorrelate", type=int, default=24,
                     help="untimed random-policy macro steps before the warm-up so the envs are spread over game states")
+    ap.add_argument("--steady-state", type=int, default=0,
+                    help="after the timed region: this many more macro steps (episodes end and restart inside them), "
+                         "reported as per-step latency percentiles + reset-memo counters")
+    ap.add_argument("--random-start", action="store_true", help="random_start pools (the reset memo is off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -381,7 +387,7 @@ def main():
     tab_rep = tab_repetitions(cfg["max_rep"], cfg["nb_choices"])
     groups = [(g, rom_bytes(g), k) for g, k in split_games(cfg["games"], n)]
     pool = mb.DevicePool(groups, rgb=cfg["rgb"], tab_rep=tab_rep, device=local_rank, env_id_offset=rank * n,
-                         envs_per_warp=args.envs_per_warp, history=cfg.get("history", 0))
+                         envs_per_warp=args.envs_per_warp, history=cfg.get("history", 0), random_start=args.random_start)
     pool.reset_all()
     # the caller's per-step bookkeeping (paac.py:173-205) and n-step returns (paac.py:226-231) ride along: K6 every
     # macro step, K5 every T = max_local_steps = 5 steps
@@ -507,6 +513,30 @@ def main():
                       "share_of_step": float(cstat[0]) * 1e-3 * len(us) / ms_max if ms_max > 0 else None,
                       "episodes_all_ranks": float(stat_sum[0]), "global_steps_all_ranks": float(stat_sum[3])}
         del coll_events[:]
+
+    # ---- steady state: many more macro steps, so that episodes end and restart inside the steps (reset memo hits,
+    # and misses -- 80 emulated frames on the step's critical path -- where the memo cannot help)
+    steady = None
+    if args.steady_state > 0:
+        m0 = pool.memo_stats()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steady_state + 1)]
+        term = torch.zeros((), device=dev)
+        with torch.cuda.stream(stream):
+            marks[0].record(stream)
+            for i in range(args.steady_state):
+                pool.action_idx.copy_((torch.randint(0, 1 << 30, (n,), device=dev, generator=gen) % n_act).to(torch.int32))
+                pool.repetition_idx.copy_(torch.randint(0, cfg["nb_choices"], (n,), device=dev, generator=gen, dtype=torch.int32))
+                pool.step_async(use_indices=True, stream=stream)
+                term += pool.terminals.sum()
+                marks[i + 1].record(stream)
+        pool.wait()
+        stream.synchronize()
+        lat = np.array([marks[i].elapsed_time(marks[i + 1]) for i in range(args.steady_state)])
+        m1 = pool.memo_stats()
+        steady = {"steps": args.steady_state, "ms_p50": float(np.percentile(lat, 50)), "ms_p99": float(np.percentile(lat, 99)),
+                  "ms_max": float(lat.max()), "p99_over_p50": float(np.percentile(lat, 99) / np.percentile(lat, 50)),
+                  "episodes_ended": float(term), "random_start": bool(args.random_start),
+                  "resets_restored_from_memo": int(m1[0] - m0[0]), "resets_emulated": int(m1[1] - m0[1])}
 
     # ---- end-to-end leg through Runners with host arrays
     e2e = None
@@ -638,7 +668,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
                 "raw_emulated_frames_per_s": 4.0 * value, "macro_steps_per_s": world * n * args.steps / (ms_max / 1000.0),
-                "step_latency": step_latency, "clocks": clocks, "e2e": e2e, "e2e_step_host": e2e_host, "collective": collective,
+                "step_latency": step_latency, "clocks": clocks, "e2e": e2e, "e2e_step_host": e2e_host, "collective": collective, "steady_state": steady,
                 "gpu_launches": launches_all, "roofline": roofline, "kernels": extra,
                 "cpu_baseline": cpu, "envs_per_warp": int(args.envs_per_warp),
                 "reset_memo": dict(zip(("restored", "emulated", "stored"), pool.memo_stats())), "exact_reruns": pool.redo_count(),

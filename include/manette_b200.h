@@ -101,6 +101,11 @@ int mn_memo_stats(mn_handle h, int64_t* out3);          /* get_initial_state() c
 int mn_total_instructions(mn_handle h, int64_t* out);   /* emulated 6502 instructions since creation */
 int mn_redo_count(mn_handle h, int64_t* out);   /* units re-run with every frame drawn (exact fallback), since creation */
 int mn_palette(uint8_t* gray128_host, uint8_t* rgb128x3_host);
+/* diagnostics: a library built with -DMN_CHECK records the first frame-buffer address violation of the picture side
+   {code, value, value}; code 0 = none.  Returns -1 in a normal build (no reference counterpart). */
+int mn_check_report(unsigned int* out3);
+/* diagnostics (pools created with MN_DIAG=2 in the environment): where the 6502 lanes waited for the picture side */
+int mn_diag_counters(mn_handle h, unsigned long long* out4);
 /* start no-ops of episode `episode` of global environment `global_env` when random_start is on.  The
  * reference draws them from unseeded random.randint(0, 30) (atari_emulator.py:75); here they are a
  * reproducible function so a CPU oracle can be fed the same schedule.  Returns 0..30. */

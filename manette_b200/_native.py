@@ -64,6 +64,8 @@ SYMBOLS = {
     "mn_total_instructions": (_I, [_VP, C.POINTER(C.c_int64)]),
     "mn_redo_count": (_I, [_VP, C.POINTER(C.c_int64)]),
     "mn_palette": (_I, [_VP, _VP]),
+    "mn_check_report": (_I, [_VP]),
+    "mn_diag_counters": (_I, [_VP, _VP]),
     "mn_start_noops": (_I, [_U32, _U32, _U32]),
     "mn_preprocess": (_I, [_VP, _VP, _I, _I, _VP]),
     "mn_sample_figar": (_I, [_VP, _VP, _I, _I, _I, _I, _F, _U64, _U32, _VP, _VP, _VP, _VP, _VP]),

@@ -29,7 +29,9 @@ def stale():
 def build(force=False, verbose=False):
     """Compile if the library is missing or older than its sources.  Returns the library path."""
     if force or stale():
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+        # MN_BUILD_DEFS="-DMN_CHECK -DMN_FILL_NOINLINE": diagnostic builds (tools/gpu_check_build.sh)
+        extra = os.environ.get("MN_BUILD_DEFS", "").split()
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
         subprocess.check_call(cmd)
     return LIB_PATH
 

@@ -34,6 +34,18 @@
 #include "cpu_defs.h"
 
 
+// Out-of-line functions receive the env record, its RAM and its write queue through ordinary pointers; without a hint
+// the compiler addresses them generically (64-bit LD / ST through the address-space check) although they always live
+// in shared memory, and the frame buffers likewise although they are global.  ~770 such accesses in k_round.
+#if defined(__CUDA_ARCH__)
+#define MN_IN_SHARED(p) __builtin_assume(__isShared(p))
+#define MN_IN_GLOBAL(p) __builtin_assume(__isGlobal(p))
+#else
+#define MN_IN_SHARED(p) do { } while (0)
+#define MN_IN_GLOBAL(p) do { } while (0)
+#endif
+#define MN_CTX_SPACES(c) do { MN_IN_SHARED((c).s); MN_IN_SHARED((c).ram); MN_IN_SHARED((c).fifo); MN_IN_SHARED((c).rom); MN_IN_GLOBAL((c).fb); } while (0)
+
 namespace mn {
 
 // ------------------------------------------------------------------ constants
@@ -120,21 +132,24 @@ struct Ctx {
   uint8_t* fb;          // this env's two frame buffers (global memory), 2 * MN_FRAME_BYTES
   const Tables* tab;
   uint32_t* fifo;       // this env's TIA write queue (shared memory): two buffers of MN_FIFO_BUF entries + the mailbox
-  int fifo_n;           // write POSITION in the double buffer: bit 4 = buffer being filled, bits 3..0 = entries in it
+  int fifo_n;           // write POSITION in the buffers: bits 5..4 = buffer being filled, bits 3..0 = entries in it
   uint32_t hseq;        // hand-offs issued so far (its parity = the buffer being filled)
   bool all_pixels;      // draw every frame with pixels (the exact-fallback mode)
   uint64_t obs_lo, obs_hi;   // RAM bytes the last game_observe() looked at (reset memoisation probe)
   bool mbox_timeout;    // a hand-off wait gave up (protocol error: reported, never a hang)
+  uint32_t wait_free, wait_done, n_handoff;   // diagnostics: clocks spent waiting for a free buffer / for a blocking hand-off
 };
 // The picture side runs on a PARTNER WARP (pool.cu: picture_warp): the 6502 warp fills one buffer while the partner
 // renders the other.  A hand-off (tia_handoff) publishes the filled buffer through a four-word mailbox per env --
 // per LANE, so that a lane inside a divergent slow path (a collision-latch read) can hand off and wait on its own.
 #define MN_FIFO_BUF 16    // entries per buffer (a power of two)
+#define MN_FIFO_NBUF 4    // buffers per env (a power of two): the 6502 side may run up to NBUF - 1 hand-offs ahead
 #define MN_FIFO_CAP 15    // usable entries: the fill count must stay below MN_FIFO_BUF
 #define MN_FIFO_HIGH 12   // a warp hands off when one of its envs has this many pending writes
-#define MN_FIFO_WORDS 37  // 2 x MN_FIFO_BUF entries + mailbox {hand, done, request, sync clock} + 1: an odd stride
-#define MN_MBOX (2 * MN_FIFO_BUF)
-enum { MB_HAND = 0, MB_DONE = 1, MB_REQ = 2, MB_SYNC = 3 };
+#define MN_MBOX (MN_FIFO_NBUF * MN_FIFO_BUF)
+#define MN_FIFO_WORDS (MN_MBOX + 2 * MN_FIFO_NBUF + 3)   // buffers + per-buffer {request, sync clock} + {hand, done} + 1: an odd stride
+enum { MB_HAND = 0, MB_DONE = 1, MB_REQ = 2 /* + 2 * buffer: request, sync clock */ };
+static_assert((MN_FIFO_WORDS & 1) == 1, "odd stride");
 enum { PIC_DRAIN = 0, PIC_END = 1 /* + close the frame: the unit is over */, PIC_EXIT = 2 /* the partner lane leaves */ };
 #define MN_FILL(pos) ((pos) & (MN_FIFO_BUF - 1))
 // FIFO entry: [16:0] colour clock since clk_frame_start, [22:17] register, [30:23] value; bit 31 marks the
@@ -253,8 +268,29 @@ MN_HD MN_INLINE uint32_t nibbles8(uint32_t b) {
   b = (b | (b << 12)) & 0x000F000Fu; b = (b | (b << 6)) & 0x03030303u; b = (b | (b << 3)) & 0x11111111u;
   return b;
 }
+// ---- -DMN_CHECK: every frame-buffer address the picture side forms is checked (range, alignment of the word stores)
+// and the first violation is recorded for mn_check_report() instead of being left to fault or to scribble.  Built to
+// chase the fault that appeared in round 1 whenever fill_px was compiled out of line (tools/gpu_check_build.sh).
+#if defined(MN_CHECK) && defined(__CUDACC__)
+__device__ unsigned int g_mn_check[8];
+MN_HD MN_INLINE void mn_check_fail(unsigned code, unsigned v0, unsigned v1) {
+#ifdef __CUDA_ARCH__
+  if (atomicCAS(&g_mn_check[0], 0u, code) == 0u) { g_mn_check[1] = v0; g_mn_check[2] = v1; }
+#else
+  (void)code; (void)v0; (void)v1;
+#endif
+}
+#define MN_ASSERT(cond, code, v0, v1) do { if (!(cond)) mn_check_fail((unsigned)(code), (unsigned)(v0), (unsigned)(v1)); } while (0)
+#else
+#define MN_ASSERT(cond, code, v0, v1) do { } while (0)
+#endif
+#ifdef MN_FILL_NOINLINE
+#define MN_FILL_ATTR MN_NOINLINE
+#else
+#define MN_FILL_ATTR MN_INLINE
+#endif
 // n bytes of `value` at p (any alignment)
-MN_HD MN_INLINE void fill_px(uint8_t* p, int n, uint32_t value) {
+MN_HD MN_FILL_ATTR void fill_px(uint8_t* p, int n, uint32_t value) {
   const uint32_t v4 = value * 0x01010101u;
 #pragma unroll 1
   while (n > 0 && (reinterpret_cast<uintptr_t>(p) & 3)) { *p++ = uint8_t(value); --n; }
@@ -266,9 +302,13 @@ MN_HD MN_INLINE void fill_px(uint8_t* p, int n, uint32_t value) {
 
 // render `n` visible pixels of the current line starting at pixel `hpos`
 MN_HD MN_NOINLINE void tia_render(Ctx& c, int n, int hpos) {
+  MN_CTX_SPACES(c);
   EnvState& s = *c.s;
   const bool pixels = (s.pflags & F_PIXELS) != 0;
   uint8_t* out = c.fb + ((s.pflags & F_CURFB) ? MN_FRAME_BYTES : 0) + s.fb_pos;
+  MN_ASSERT(n > 0 && hpos >= 0 && hpos + n <= MN_SCREEN_W, 1, n, hpos);
+  MN_ASSERT(s.fb_pos >= 0 && s.fb_pos + n <= MN_FRAME_BYTES, 2, s.fb_pos, n);
+  MN_ASSERT(((s.fb_pos - hpos) & 3) == 0, 3, s.fb_pos, hpos);        // the 32-bit pixel stores below rely on this
   s.fb_pos += n;
   const uint32_t en = s.enabled;
   if (s.vblank & 0x02) { if (pixels) fill_px(out, n, 0u); return; }
@@ -326,6 +366,7 @@ MN_HD MN_NOINLINE void tia_render(Ctx& c, int n, int hpos) {
       const uint32_t sel = nibbles8((plane0 >> (8 * b)) & 0xFFu) | (nibbles8((plane1 >> (8 * b)) & 0xFFu) << 1);
       const uint32_t lo4 = perm4(colours, sel), hi4 = perm4(colours, sel >> 16);
       uint8_t* q = o + 8 * b;
+      MN_ASSERT((reinterpret_cast<uintptr_t>(q) & 3) == 0 && q >= c.fb && q + 8 <= c.fb + 2 * MN_FRAME_BYTES + 32, 4, q - c.fb, sp);
       if (sp == 0xFFu) { reinterpret_cast<uint32_t*>(q)[0] = lo4; reinterpret_cast<uint32_t*>(q)[1] = hi4; }
       else {
         if ((sp & 0x0Fu) == 0x0Fu) reinterpret_cast<uint32_t*>(q)[0] = lo4;
@@ -340,6 +381,7 @@ MN_HD MN_NOINLINE void tia_render(Ctx& c, int n, int hpos) {
 
 // bring the picture up to colour clock `clock` (relative to the start of the frame)
 MN_HD MN_NOINLINE void tia_advance(Ctx& c, int32_t clock) {
+  MN_CTX_SPACES(c);
   EnvState& s = *c.s;
   const int32_t start = 228 * MN_YSTART;
   const int32_t stop = start + 228 * MN_SCREEN_H;
@@ -359,6 +401,7 @@ MN_HD MN_NOINLINE void tia_advance(Ctx& c, int32_t clock) {
     if ((s.pflags & F_HMBLANK) && from_sol < MN_HBLANK + 8) {
       int32_t blanks = (MN_HBLANK + 8) - from_sol;
       const int32_t room = MN_FRAME_BYTES - old_pos; if (blanks > room) blanks = room;
+      MN_ASSERT(old_pos >= 0 && blanks >= 0 && old_pos + blanks <= MN_FRAME_BYTES, 5, old_pos, blanks);
       if (s.pflags & F_PIXELS) fill_px(c.fb + ((s.pflags & F_CURFB) ? MN_FRAME_BYTES : 0) + old_pos, blanks, 0u);
       if (n + from_sol >= MN_HBLANK + 8) s.pflags &= ~F_HMBLANK;
     }
@@ -370,6 +413,7 @@ MN_HD MN_NOINLINE void tia_advance(Ctx& c, int32_t clock) {
 
 
 MN_HD MN_NOINLINE void tia_refresh_grp(EnvState& s) {
+  MN_IN_SHARED(&s);
   uint32_t g0 = (s.pflags & F_VDELP0) ? s.dgrp0 : s.grp0;
   uint32_t g1 = (s.pflags & F_VDELP1) ? s.dgrp1 : s.grp1;
   s.cur_grp0 = uint8_t((s.pflags & F_REFP0) ? rev8(g0) : g0);
@@ -377,6 +421,7 @@ MN_HD MN_NOINLINE void tia_refresh_grp(EnvState& s) {
   s.enabled = uint8_t((s.enabled & ~(EN_P0 | EN_P1)) | (s.cur_grp0 ? EN_P0 : 0) | (s.cur_grp1 ? EN_P1 : 0));
 }
 MN_HD MN_NOINLINE void tia_refresh_misc(EnvState& s) {
+  MN_IN_SHARED(&s);
   bool bl = (s.pflags & F_VDELBL) ? (s.pflags & F_DENABL) != 0 : (s.pflags & F_ENABL) != 0;
   bool m0 = (s.pflags & F_ENAM0) && !(s.pflags & F_RESMP0);
   bool m1 = (s.pflags & F_ENAM1) && !(s.pflags & F_RESMP1);
@@ -434,6 +479,7 @@ static_assert(F_REFP1 == F_REFP0 << 1 && F_ENAM1 == F_ENAM0 << 1 && F_ENABL == F
               "tia_apply shifts these flag bits by the register offset");
 // ---- picture side: apply one queued register write (colour clock `rel` since the start of the frame)
 MN_HD MN_NOINLINE void tia_apply(Ctx& c, int32_t rel, uint32_t addr, uint32_t v) {
+  MN_CTX_SPACES(c);
   EnvState& s = *c.s;
   const int32_t hpos = rel % 228;
   int32_t delay;
@@ -536,7 +582,9 @@ MN_HD MN_INLINE void picture_open_frame(EnvState& s, bool pixels) {
 // `cnt` queued writes of buffer `buf` go through the picture; then the picture is brought up to colour clock
 // `sync_clk` if one was asked for (collision-latch reads), and the frame is closed if the unit is over.
 MN_HD MN_NOINLINE void picture_process(Ctx& c, int buf, int cnt, int32_t sync_clk, int cmd) {
+  MN_CTX_SPACES(c);
   const uint32_t* q = c.fifo + buf * MN_FIFO_BUF;
+  MN_ASSERT(cnt >= 0 && cnt <= MN_FIFO_CAP && buf >= 0 && buf < MN_FIFO_NBUF, 6, cnt, buf);
   for (int i = 0; i < cnt; ++i) {
     const uint32_t e = q[i];
     if (e & MN_FIFO_FRAME) picture_open_frame(*c.s, (e & 1u) != 0);
@@ -550,9 +598,9 @@ MN_HD MN_NOINLINE void picture_process(Ctx& c, int buf, int cnt, int32_t sync_cl
 __device__ __forceinline__ uint32_t mbox_load(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 __device__ __forceinline__ void mbox_store(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
 // bounded spin: a protocol error must end the kernel with garbage and an error code, never hang the GPU
-__device__ __forceinline__ bool mbox_wait(const uint32_t* p, uint32_t want) {
+__device__ __forceinline__ bool mbox_wait(const uint32_t* p, uint32_t want) {   // until *p has reached `want`
   for (uint32_t spins = 0; spins < (1u << 24); ++spins) {
-    if (mbox_load(p) == want) return true;
+    if (int32_t(mbox_load(p) - want) >= 0) return true;
     __nanosleep(20);
   }
   return false;
@@ -561,23 +609,28 @@ __device__ __forceinline__ bool mbox_wait(const uint32_t* p, uint32_t want) {
 // ---- program side: hand the buffer being filled to the picture side and go on with the other one.
 // `blocking`: wait until the picture side is through with it (the caller needs its results).
 MN_HD MN_NOINLINE void tia_handoff(Ctx& c, int32_t sync_clk, int cmd, bool blocking) {
-  const int buf = (c.fifo_n >> 4) & 1, cnt = MN_FILL(c.fifo_n);
+  MN_CTX_SPACES(c);
+  const int buf = (c.fifo_n >> 4) & (MN_FIFO_NBUF - 1), cnt = MN_FILL(c.fifo_n);
 #ifdef __CUDA_ARCH__
   uint32_t* mb = c.fifo + MN_MBOX;
-  const uint32_t h = c.hseq;
-  // every earlier hand-off must have been consumed: the buffer about to be refilled is the one handed off before
-  if (c.mbox_timeout || !mbox_wait(mb + MB_DONE, h)) c.mbox_timeout = true;   // (after one timeout: no more waiting)
-  mbox_store(mb + MB_REQ, uint32_t(cnt) | (uint32_t(cmd) << 8));
-  mbox_store(mb + MB_SYNC, uint32_t(sync_clk));
+  const uint32_t h = c.hseq;            // this is hand-off number h, of buffer h % NBUF
+  mbox_store(mb + MB_REQ + 2 * buf, uint32_t(cnt) | (uint32_t(cmd) << 8));
+  mbox_store(mb + MB_REQ + 2 * buf + 1, uint32_t(sync_clk));
   __threadfence_block();
   mbox_store(mb + MB_HAND, h + 1u);
-  if (blocking) { if (c.mbox_timeout || !mbox_wait(mb + MB_DONE, h + 1u)) c.mbox_timeout = true; __threadfence_block(); }
+  // the buffer filled next was handed off NBUF - 1 hand-offs ago: it must have been consumed
+  const uint32_t t0 = uint32_t(clock64());
+  const uint32_t need = blocking ? h + 1u : h + 2u - MN_FIFO_NBUF;
+  if (int32_t(need) > 0) { if (c.mbox_timeout || !mbox_wait(mb + MB_DONE, need)) c.mbox_timeout = true; }   // (after one timeout: no more waiting)
+  if (blocking) { __threadfence_block(); c.wait_done += uint32_t(clock64()) - t0; }
+  else c.wait_free += uint32_t(clock64()) - t0;
+  c.n_handoff++;
 #else
   (void)blocking;
   picture_process(c, buf, cnt, sync_clk, cmd);
 #endif
   c.hseq++;
-  c.fifo_n = (buf ^ 1) << 4;
+  c.fifo_n = ((buf + 1) & (MN_FIFO_NBUF - 1)) << 4;
 }
 // every queued write goes to the picture side (which catches up on its own time)
 MN_HD MN_INLINE void tia_drain(Ctx& c) { if (MN_FILL(c.fifo_n) != 0) tia_handoff(c, -1, PIC_DRAIN, false); }
@@ -588,6 +641,7 @@ MN_HD MN_INLINE void fifo_push(Ctx& c, uint32_t e) {
 
 // ---- program side: a TIA register write.  Only what the 6502 can observe happens now.
 MN_HD MN_INLINE void tia_poke(Ctx& c, uint32_t addr, uint32_t v) {
+  MN_CTX_SPACES(c);
   EnvState& s = *c.s;
   addr &= 0x3F;
   const int32_t clock = s.cycles * 3;
@@ -619,6 +673,7 @@ MN_HD MN_INLINE void tia_poke(Ctx& c, uint32_t addr, uint32_t v) {
 }
 
 MN_HD MN_NOINLINE uint32_t tia_peek(Ctx& c, uint32_t addr) {
+  MN_CTX_SPACES(c);
   EnvState& s = *c.s;
   const uint32_t noise = s.dbus & 0x3Fu;
   const uint32_t reg = addr & 0x0F;
@@ -652,6 +707,7 @@ MN_HD MN_NOINLINE uint32_t tia_peek(Ctx& c, uint32_t addr) {
 
 // ------------------------------------------------------------------ RIOT
 MN_HD MN_NOINLINE uint32_t riot_peek(Ctx& c, uint32_t addr) {
+  MN_CTX_SPACES(c);
   EnvState& s = *c.s;
   switch (addr & 7) {
     case 0: return s.swcha;
@@ -673,6 +729,7 @@ MN_HD MN_NOINLINE uint32_t riot_peek(Ctx& c, uint32_t addr) {
   return uint32_t(t) & 0xFFu;
 }
 MN_HD MN_NOINLINE void riot_poke(Ctx& c, uint32_t addr, uint32_t v) {
+  MN_CTX_SPACES(c);
   EnvState& s = *c.s;
   if ((addr & 7) == 1) s.ddra = uint8_t(v);
   else if ((addr & 7) == 3) s.ddrb = uint8_t(v);
@@ -684,7 +741,8 @@ MN_HD MN_NOINLINE void riot_poke(Ctx& c, uint32_t addr, uint32_t v) {
 }
 
 // ------------------------------------------------------------------ bus
-MN_HD MN_NOINLINE void cart_touch(EnvState& s, uint32_t a) {   // a = addr & 0xFFF, banked carts only
+MN_HD MN_NOINLINE void cart_touch(EnvState& s, uint32_t a) {
+  MN_IN_SHARED(&s);   // a = addr & 0xFFF, banked carts only
   if (s.cart == CART_F8) { if (a == 0xFF8) s.bank = 0; else if (a == 0xFF9) s.bank = 1; }
   else if (s.cart == CART_F6) { if (a >= 0xFF6 && a <= 0xFF9) s.bank = uint8_t(a - 0xFF6); }
   else if (s.cart == CART_E0) {
@@ -816,6 +874,7 @@ MN_HD MN_INLINE void setA(Cpu& r, uint32_t v) { r.axys = (r.axys & 0xFFFFFF00u) 
 MN_HD MN_INLINE void setX(Cpu& r, uint32_t v) { r.axys = (r.axys & 0xFFFF00FFu) | ((v & 0xFFu) << 8); }
 MN_HD MN_INLINE void setSP(Cpu& r, uint32_t v) { r.axys = (r.axys & 0x00FFFFFFu) | (v << 24); }
 MN_HD MN_NOINLINE uint32_t make_segmap(const EnvState& s) {
+  MN_IN_SHARED(&s);
   // 4K: pages 0..3; F8 / F6: the four pages of the selected 4K bank; 2K: its two pages twice; E0: three 1K slices + page 7
   const uint32_t banked = uint32_t(s.bank) * 0x04040404u + 0x03020100u;   // bank is 0 for 4K
   const uint32_t sliced = uint32_t(s.slice0) | (uint32_t(s.slice1) << 8) | (uint32_t(s.slice2) << 16) | (7u << 24);
@@ -843,6 +902,7 @@ MN_HD MN_INLINE maddr ram_addr(const Mem& mm, uint32_t addr) {
 }
 // the uncommon reads: bank-switch hot spots (the switch happens before the read), TIA, RIOT
 MN_HD MN_NOINLINE uint32_t rd_slow(Ctx& c, uint32_t addr, int32_t cycles, uint32_t dbus) {
+  MN_CTX_SPACES(c);
   EnvState& s = *c.s;
   if (addr & 0x1000u) { cart_touch(s, addr & 0xFFFu); return m8(rom_addr(mem_of(c), make_segmap(s), addr)); }
   s.cycles = cycles; s.dbus = uint8_t(dbus);
@@ -867,6 +927,7 @@ MN_HD MN_INLINE uint32_t rd(Ctx& c, const Mem& mm, Cpu& r, uint32_t addr) {
 // the writes that land neither in RIOT RAM nor (the common case) in the TIA write FIFO;
 // returns the CPU cycle count (WSYNC / RSYNC stall the 6502)
 MN_HD MN_NOINLINE int32_t wr_slow(Ctx& c, uint32_t addr, uint32_t v, int32_t cycles) {
+  MN_CTX_SPACES(c);
   EnvState& s = *c.s;
   if (addr & 0x1000u) { if (s.cart > CART_4K) cart_touch(s, addr & 0xFFFu); return cycles; }
   s.cycles = cycles;
@@ -1253,6 +1314,7 @@ MN_HD MN_INLINE bool cpu_fast(const Mem& mm, Cpu& r, const bool go) {
 // ------------------------------------------------------------------ frame
 // program side of the emulated TIA's frame start: rebase every cycle-stamped quantity, tell the picture
 MN_HD MN_INLINE void frame_begin(Ctx& c, bool pixels) {
+  MN_CTX_SPACES(c);
   EnvState& s = *c.s;
   const int32_t clocks = ((s.cycles * 3) - s.clk_frame_start) % 228;
   const int32_t cy = s.cycles;
@@ -1297,6 +1359,7 @@ MN_HD MN_INLINE int32_t ram_bcd(Ctx& c, int off) { const uint32_t b = ram_seen(c
 
 // per-game reward / terminal / lives from RAM after every frame
 MN_HD MN_NOINLINE void game_observe(Ctx& c) {
+  MN_CTX_SPACES(c);
   EnvState& s = *c.s;
   int32_t sc = s.score;
   bool term = false;
@@ -1403,6 +1466,7 @@ MN_HD MN_INLINE void latch_inputs(EnvState& s, int action) {
   }
 }
 MN_HD MN_INLINE void console_reset(Ctx& c, uint32_t rnd) {
+  MN_CTX_SPACES(c);
   EnvState& s = *c.s;
   s.cycles = 0;
   // RIOT
@@ -1461,6 +1525,7 @@ MN_HD MN_INLINE void unit_idle(Unit& u) { u.kind = U_ACTS; u.idx = u.total = 0; 
 
 // `seed`: U_POWER_ON: the ALE seed; U_RESET: the RNG draw (already taken) that seeds the RIOT timer
 MN_HD MN_INLINE void unit_init(Ctx& c, Unit& u, int kind, int action, int count, uint32_t seed) {
+  MN_CTX_SPACES(c);
   EnvState& s = *c.s;
   u.kind = kind; u.idx = 0; u.action = action; u.reward = 0; u.in_frame = false; u.frozen_last = false; u.budget = 0;
   u.job_is_act = false; u.nstart = 0;
@@ -1480,6 +1545,7 @@ MN_HD MN_INLINE void unit_init(Ctx& c, Unit& u, int kind, int action, int count,
 }
 
 MN_HD MN_NOINLINE void unit_job_done(Ctx& c, Unit& u) {
+  MN_CTX_SPACES(c);
   EnvState& s = *c.s;
   u.in_frame = false;
   game_observe(c);
@@ -1493,6 +1559,7 @@ MN_HD MN_NOINLINE void unit_job_done(Ctx& c, Unit& u) {
 
 // start the next job of the unit
 MN_HD MN_NOINLINE void unit_job_begin(Ctx& c, Unit& u) {
+  MN_CTX_SPACES(c);
   EnvState& s = *c.s;
   {
     int action;
@@ -1596,8 +1663,14 @@ MN_HD MN_INLINE void unit_tick(Ctx& c, const Mem& mm, Unit& u, Hot& h, const boo
     }
     unit_job_done(c, u);
     h.in_frame = false;
-    // scrapes after RomSettings::reset() (job 64 on) shape the episode: they must only see written bytes
-    if (TRACK && (u.kind == U_ACTS || u.idx > 64) && ((c.obs_lo & ~h.def_lo) | (c.obs_hi & ~h.def_hi))) h.obs_bad = true;
+    // Scrapes after RomSettings::reset() (job 64 on) shape the episode.  A byte they look at before the program has
+    // written it still holds its value from before the reset: the result depends on it exactly as it does on a byte
+    // the program itself reads before writing, so it joins the dependence set (the memo key).  Yars' Revenge is the
+    // README game this matters for: its lives byte is scraped before the program rewrites it.
+    if (TRACK && (u.kind == U_ACTS || u.idx > 64)) {
+      const uint64_t lo = c.obs_lo & ~h.def_lo, hi = c.obs_hi & ~h.def_hi;
+      if (lo | hi) { h.dep_lo |= lo; h.dep_hi |= hi; h.tainted = true; }
+    }
   }
 }
 
@@ -1606,6 +1679,7 @@ MN_HD MN_INLINE void hot_drain(Ctx& c, Hot& h) { c.fifo_n = h.cpu.fifo_n; tia_dr
 
 // after the unit's last tick: flush the picture and report whether the pixel-less frames were harmless
 MN_HD MN_INLINE bool unit_finish(Ctx& c, Hot& h) {
+  MN_CTX_SPACES(c);
   EnvState& s = *c.s;
   c.fifo_n = h.cpu.fifo_n;
   tia_handoff(c, -1, PIC_END, true);   // the rest of the queue, then the frame is closed; wait for the verdict

@@ -33,7 +33,9 @@ namespace mn {
 
 #define MN_MAX_GAMES 16
 #define MN_WARPS_PER_BLOCK 4                  // 6502 warps per block, one per SM sub-partition ...
-#define MN_PARTNERS 2                         // ... each with this many picture-side partner warps (warps w + 4, w + 8),
+#ifndef MN_PARTNERS
+#define MN_PARTNERS 1                         // ... each with this many picture-side partner warps (warps w + 4, w + 8 ...),
+#endif
 #define MN_THREADS ((1 + MN_PARTNERS) * MN_WARPS_PER_BLOCK * 32)   // which share the 6502 warp's environments evenly
 #define MN_CORE_WORDS 43   // EnvState is 43 words: an odd stride, conflict-free across slots
 #define MN_PLANE (MN_IMG * MN_IMG)
@@ -88,6 +90,7 @@ struct PoolDev {             // kernel argument block (by value)
   int32_t single_life, random_start, seed, env_id_offset, draw_all_frames;
   int32_t sync_slack;        // lanes of a warp stay within this many CPU cycles of the slowest one (see hot_time)
   int32_t fifo_high;         // a warp hands its TIA write queues off when one of them holds this many entries
+  int32_t diag;              // MN_DIAG (measurement only, results are wrong): 1 = the picture side acknowledges without rendering
   int32_t tab_rep[32];
   const uint8_t* roms;
   EnvState* env;
@@ -119,6 +122,7 @@ struct PoolDev {             // kernel argument block (by value)
   unsigned long long* track; // (N,5) def_lo def_hi dep_lo dep_hi flags : RAM-dependence probe of the reset in flight
   unsigned long long* memo_stats;   // hits, misses, inserts
   unsigned long long* total_instr;  // emulated 6502 instructions
+  unsigned long long* diag_out;     // MN_DIAG=2 counters
   unsigned long long* redo_count;   // units re-run with every frame drawn (exact fallback of the pixel-less frames)
   uint8_t* history;          // (N, H, 84, 84, 4D) ring of the last H published states (paac.py:79-83,107-112), or null
   int32_t history_depth;
@@ -204,7 +208,7 @@ __global__ void k_single_list(PoolDev p, int which, int env, int ale_action) {
 // hand-offs (emu_core.cuh tia_handoff) and renders them while the 6502 warp runs on.  Requests published by one
 // instruction of the 6502 warp (the warp-wide hand-off of k_round's loop) are seen together and rendered by all
 // lanes in step -- the long branchy rendering code is entered by the whole warp, as it was when it ran inline.
-__device__ __forceinline__ void picture_warp(Ctx& c, unsigned wmask) {
+__device__ __forceinline__ void picture_warp(Ctx& c, unsigned wmask, int diag) {
   uint32_t* mb = c.fifo + MN_MBOX;
   uint32_t pseq = 0;
   bool fin = false;
@@ -223,11 +227,12 @@ __device__ __forceinline__ void picture_warp(Ctx& c, unsigned wmask) {
     idle_ns = 64;
     if (req) {
       __threadfence_block();
-      const uint32_t rq = mbox_load(mb + MB_REQ);
-      const int32_t sync_clk = int32_t(mbox_load(mb + MB_SYNC));
+      const int buf = int(pseq & (MN_FIFO_NBUF - 1));
+      const uint32_t rq = mbox_load(mb + MB_REQ + 2 * buf);
+      const int32_t sync_clk = int32_t(mbox_load(mb + MB_REQ + 2 * buf + 1));
       const int cmd = int(rq >> 8);
       if (cmd == PIC_EXIT) fin = true;
-      else picture_process(c, int(pseq & 1u), int(rq & 0xFFu), sync_clk, cmd);
+      else if (!(diag & 1)) picture_process(c, buf, int(rq & 0xFFu), sync_clk, cmd);
       __threadfence_block();
       mbox_store(mb + MB_DONE, ++pseq);
     }
@@ -252,7 +257,7 @@ __device__ __forceinline__ void run_units(Ctx& c, const Mem& mm, Unit& u, Hot& h
 
 // One round of emulation for the envs on list `in`.  Dynamic shared memory:
 //   [rom | tables | core slots (4 warps x slots x 43 words) | ram (4 warps x slots x 132 B: 128 used, odd word pitch)
-//    | TIA write queues (4 warps x slots x 37 words: two buffers of 16 + the hand-off mailbox)]
+//    | TIA write queues (4 warps x slots x MN_FIFO_WORDS: NBUF buffers of 16 + the hand-off mailbox)]
 template <bool TRACK>
 __global__ void __launch_bounds__(MN_THREADS, 1) k_round(PoolDev p, int mode, int in, int out) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -282,7 +287,7 @@ __global__ void __launch_bounds__(MN_THREADS, 1) k_round(PoolDev p, int mode, in
     for (int i = threadIdx.x; i < int(sizeof(Tables) / 4); i += blockDim.x) td[i] = ts[i];
     for (int i = threadIdx.x; i < nslots; i += blockDim.x) {   // mailboxes: nothing handed off, nothing done
       uint32_t* mb = s_fifo + i * MN_FIFO_WORDS + MN_MBOX;
-      mb[MB_HAND] = 0u; mb[MB_DONE] = 0u; mb[MB_REQ] = 0u; mb[MB_SYNC] = 0u;
+      mb[MB_HAND] = 0u; mb[MB_DONE] = 0u;
     }
   }
   __syncthreads();
@@ -307,8 +312,9 @@ __global__ void __launch_bounds__(MN_THREADS, 1) k_round(PoolDev p, int mode, in
   c.ram = s_ram + slot * MN_RAM_PITCH;
   c.fb = p.frames + size_t(e) * (2 * MN_FRAME_BYTES);
   c.fifo = s_fifo + slot * MN_FIFO_WORDS;
-  c.fifo_n = 0; c.hseq = 0; c.mbox_timeout = false;
-  if (picture_side) { picture_warp(c, wmask); return; }
+  c.fifo_n = 0; c.hseq = 0; c.mbox_timeout = false; c.wait_free = c.wait_done = c.n_handoff = 0;
+  const long long t_begin = clock64();
+  if (picture_side) { picture_warp(c, wmask, p.diag); return; }
   // what this launch asks of the env
   int kind = U_ACTS, action = 0, ucount = MN_ACTION_REPEAT;
   uint32_t seed = 0;
@@ -369,6 +375,10 @@ __global__ void __launch_bounds__(MN_THREADS, 1) k_round(PoolDev p, int mode, in
   }
   tia_handoff(c, -1, PIC_EXIT, false);   // the partner lane leaves
   if (c.mbox_timeout) atomicExch(p.error, 2);
+  if (p.diag & 2) {   // MN_DIAG=2: where the 6502 lanes waited (lane-clocks, summed over the launches)
+    atomicAdd(p.diag_out + 0, (unsigned long long)c.wait_free); atomicAdd(p.diag_out + 1, (unsigned long long)c.wait_done);
+    atomicAdd(p.diag_out + 2, (unsigned long long)(clock64() - t_begin)); atomicAdd(p.diag_out + 3, (unsigned long long)c.n_handoff);
+  }
 
   const bool single_life = p.single_life != 0;
   if (mode != ROUND_POWER_ON && mode != ROUND_RESET) {
@@ -948,6 +958,25 @@ extern "C" {
 
 const char* mn_last_error(void) { return g_err.c_str(); }
 
+// -DMN_CHECK builds only: the first recorded violation {code, value, value} (code 0 = none); -1 in a normal build
+int mn_check_report(unsigned int* out3) {
+#ifdef MN_CHECK
+  unsigned int v[8];
+  if (cudaMemcpyFromSymbol(v, g_mn_check, sizeof(v)) != cudaSuccess) return fail("mn_check_report: cudaMemcpyFromSymbol");
+  out3[0] = v[0]; out3[1] = v[1]; out3[2] = v[2];
+  return 0;
+#else
+  (void)out3; return -1;
+#endif
+}
+
+// MN_DIAG=2 runs: {lane-clocks waiting for a free buffer, waiting for blocking hand-offs, total lane-clocks, hand-offs}
+int mn_diag_counters(mn_handle h, unsigned long long* out4) {
+  if (!h || !out4) return fail("mn_diag_counters: null argument");
+  CU(cudaMemcpy(out4, h->d.diag_out, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int mn_palette(uint8_t* gray128_host, uint8_t* rgb128x3_host) { host_palette(gray128_host, rgb128x3_host); return 0; }
 
 int mn_start_noops(uint32_t seed, uint32_t global_env, uint32_t episode) { return int(start_noops(seed, global_env, episode)); }
@@ -1008,6 +1037,8 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
   d.draw_all_frames = cfg->draw_all_frames;
   d.sync_slack = 4;
   if (const char* ev = getenv("MN_SYNC_SLACK")) d.sync_slack = atoi(ev) < 0 ? 0x3FFFFFFF : atoi(ev);
+  d.diag = 0;
+  if (const char* ev = getenv("MN_DIAG")) d.diag = atoi(ev);
   d.fifo_high = MN_FIFO_HIGH;
   if (const char* ev = getenv("MN_FIFO_HIGH")) { const int v = atoi(ev); if (v >= 1 && v <= MN_FIFO_HIGH) d.fifo_high = v; }
   h->max_rep = 0;
@@ -1075,6 +1106,7 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
   rc |= dev_alloc(h, &d.error, size_t(1));
   rc |= dev_alloc(h, &d.total_next, size_t(1));
   rc |= dev_alloc(h, &d.redo_count, size_t(1));
+  rc |= dev_alloc(h, &d.diag_out, size_t(8));
   rc |= dev_alloc(h, &d.total_instr, size_t(1));
   d.memo_enabled = (cfg->random_start == 0 && cfg->no_reset_memo == 0) ? 1 : 0;
   d.memo_entry_bytes = int32_t(memo_hdr_bytes() + 2 * MN_FRAME_BYTES + size_t(MN_STACK) * MN_PLANE * D);

@@ -53,6 +53,13 @@ def main():
     ins = pool.total_instructions() - i0
     print("game=%s envs=%d epw=%d steps=%d next_calls=%d seconds=%.3f frames_per_s=%.1f instr_per_next=%.0f Minstr_per_s=%.1f redo=%d"
           % (a.game, a.envs, a.envs_per_warp, a.steps, fr, dt, fr / dt, ins / max(fr, 1), ins / dt / 1e6, pool.redo_count()))
+    if os.environ.get("MN_DIAG") == "2":
+        import ctypes as C
+        from manette_b200 import _native
+        out = (C.c_ulonglong * 4)()
+        _native.load().mn_diag_counters(pool._h, out)
+        print("diag: waiting for a free buffer %.1f %%, for blocking hand-offs %.1f %% of the 6502 lanes' time; %d hand-offs"
+              % (100.0 * out[0] / max(out[2], 1), 100.0 * out[1] / max(out[2], 1), out[3]))
     pool.close()
 
 
