@@ -70,8 +70,13 @@ __constant__ uint32_t c_pal[128];
 static void host_palette(uint8_t* gray, uint8_t* rgb) {
   for (int i = 0; i < 128; ++i) {
     const uint8_t r = (h_ntsc[i] >> 16) & 0xFF, g = (h_ntsc[i] >> 8) & 0xFF, b = h_ntsc[i] & 0xFF;
-    // ALE's luminance: truncation of a double sum whose terms were float products
-    gray[i] = uint8_t(((float)r * 0.2989) + ((float)g * 0.5870) + ((float)b * 0.1140));
+    // ALE's luminance (ColourPalette::convertGrayscale of ALE >= 0.5): (uInt8) round(r * 0.2989 + g * 0.5870 + b * 0.1140)
+    // in double arithmetic -- MN_ALE_LUMA_ROUND 0 restores round 1's truncation (see oracle/ale.hpp)
+#ifndef MN_ALE_LUMA_ROUND
+#define MN_ALE_LUMA_ROUND 1
+#endif
+    const double lum = double(r) * 0.2989 + double(g) * 0.5870 + double(b) * 0.1140;
+    gray[i] = MN_ALE_LUMA_ROUND ? uint8_t(round(lum)) : uint8_t(lum);
     rgb[3 * i] = r; rgb[3 * i + 1] = g; rgb[3 * i + 2] = b;
   }
 }

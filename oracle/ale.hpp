@@ -11,6 +11,7 @@
 // pinned version either: atari_emulator.py:21 says ">= ALE 0.5.0"); this restates its
 // published behaviour from recollection.
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -110,10 +111,21 @@ inline const uint32_t* ntsc_palette() {   // 128 colours, index = TIA colour byt
       0x482c00, 0x694d14, 0x866a26, 0xa28638, 0xbb9f47, 0xd2b656, 0xe8cc63, 0xfce070};
   return p;
 }
+// ALE-ISM (named so that it can be found and flipped): getScreenGrayscale reads the gray value ALE's ColourPalette
+// stores beside every NTSC colour, `(uInt8) round(r * 0.2989 + g * 0.5870 + b * 0.1140)` in double arithmetic
+// (ColourPalette.cpp convertGrayscale of ALE >= 0.5, the version atari_emulator.py:21 asks for).
+// Round 1 of this repo truncated instead (the ALE 0.4 export path); both sides changed together in round 2.
+// Unverifiable here -- ALE is not installable -- and inside the +-1 tolerance either way.
+#define ORC_ALE_LUMA_ROUND 1
 inline uint8_t palette_gray(uint8_t tia_colour) {
   uint32_t px = ntsc_palette()[tia_colour >> 1];
-  uint8_t r = (px >> 16) & 0xFF, g = (px >> 8) & 0xFF, b = px & 0xFF;
-  return uint8_t(((float)r * 0.2989) + ((float)g * 0.5870) + ((float)b * 0.1140));
+  const double r = (px >> 16) & 0xFF, g = (px >> 8) & 0xFF, b = px & 0xFF;
+  const double lum = r * 0.2989 + g * 0.5870 + b * 0.1140;
+#if ORC_ALE_LUMA_ROUND
+  return uint8_t(std::round(lum));
+#else
+  return uint8_t(lum);
+#endif
 }
 
 // ----------------------------------------------------------------- environment
