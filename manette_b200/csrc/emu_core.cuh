@@ -300,8 +300,16 @@ MN_HD MN_FILL_ATTR void fill_px(uint8_t* p, int n, uint32_t value) {
   while (n > 0) { *p++ = uint8_t(value); --n; }
 }
 
+// The picture side runs on its own warp: its call tree no longer sits between the instructions of the 6502 loop, so
+// the leaves of the hot chain picture_process -> tia_apply -> tia_advance -> tia_render can be inlined again (call
+// overhead and the spills around it were a visible share of the partner's time).  -DMN_PIC_OUTLINE keeps them out.
+#ifdef MN_PIC_OUTLINE
+#define MN_PIC_INLINE MN_NOINLINE
+#else
+#define MN_PIC_INLINE MN_INLINE
+#endif
 // render `n` visible pixels of the current line starting at pixel `hpos`
-MN_HD MN_NOINLINE void tia_render(Ctx& c, int n, int hpos) {
+MN_HD MN_PIC_INLINE void tia_render(Ctx& c, int n, int hpos) {
   MN_CTX_SPACES(c);
   EnvState& s = *c.s;
   const bool pixels = (s.pflags & F_PIXELS) != 0;

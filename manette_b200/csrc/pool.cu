@@ -254,8 +254,10 @@ __device__ __forceinline__ void run_units(Ctx& c, const Mem& mm, Unit& u, Hot& h
     int now = work ? hot_time(hot) : 0x7FFFFFFF;
     if (MN_FILL(hot.cpu.fifo_n) >= fifo_high) now = -1;
     const int first = __reduce_min_sync(wmask, now);
-    if (first < 0) { hot_drain(c, hot); continue; }
-    if (first == 0x7FFFFFFF) break;
+    if (((uint32_t(first) + 1u) & 0x7FFFFFFFu) == 0u) {   // -1 or INT_MAX: one test (one branch) on the path every tick takes
+      if (first < 0) { hot_drain(c, hot); continue; }
+      break;
+    }
     unit_tick<TRACK, FLAT>(c, mm, u, hot, work && now - first <= sync_slack);
   }
 }
