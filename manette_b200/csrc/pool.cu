@@ -917,6 +917,7 @@ struct mn_pool {
   int64_t launches;
   std::vector<void*> allocs;
   uint8_t* pin_ram;
+  int* err_host;             // pinned: the device error word as of the last completed step (copied before `done` is recorded)
   std::vector<int> env_game_host;
   GameDev games_host[MN_MAX_GAMES];
   Tables* tables_dev;
@@ -995,6 +996,7 @@ int mn_destroy(mn_handle h) {
   for (void* p : h->allocs) cudaFree(p);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->done) cudaEventDestroy(h->done);
+  if (h->err_host) cudaFreeHost(h->err_host);
   delete h;
   return 0;
 }
@@ -1015,7 +1017,7 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
 
   mn_pool* h = new mn_pool();
   memset(&h->d, 0, sizeof(h->d));
-  h->device = cfg->device; h->done = nullptr; h->pending = false; h->launches = 0; h->pin_ram = nullptr;
+  h->device = cfg->device; h->done = nullptr; h->pending = false; h->launches = 0; h->pin_ram = nullptr; h->err_host = nullptr;
   h->profiling = false; h->ev_used = 0; h->hist_head = 0;
   PoolDev& d = h->d;
   int n = 0, max_actions = 0;
@@ -1145,6 +1147,8 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
   }
   memcpy(h->games_host, d.games, sizeof(d.games));
   CU(cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming));
+  CU(cudaMallocHost(&h->err_host, sizeof(int)));
+  *h->err_host = 0;
   // construct every AtariEmulator (atari_emulator.py:18-31): seed, RAM garbage, loadROM's reset
   {
     const int tb = 256, gb = (n + tb - 1) / tb > 1 ? (n + tb - 1) / tb : 1;
@@ -1255,6 +1259,7 @@ int mn_reset_all(mn_handle h, void* stream) {
   // over[] is zero here (k_fill_list), so nothing is wiped
   launch_emit(h, 0, n, 1, st, h->d.history ? h->hist_head : -1);
   CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(h->err_host, h->d.error, sizeof(int), cudaMemcpyDeviceToHost, st));
   CU(cudaEventRecord(h->done, st));
   h->pending = true;
   return 0;
@@ -1279,6 +1284,7 @@ int mn_step_async(mn_handle h, int use_indices, void* stream) {
   if (h->d.history) h->hist_head = (h->hist_head + 1) % h->d.history_depth;   // update_memory: shift, newest last
   launch_emit(h, 0, n, 1, st, h->d.history ? h->hist_head : -1);
   CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(h->err_host, h->d.error, sizeof(int), cudaMemcpyDeviceToHost, st));
   CU(cudaEventRecord(h->done, st));
   h->pending = true;
   return 0;
@@ -1289,8 +1295,7 @@ int mn_wait(mn_handle h) {
   CU(cudaSetDevice(h->device));
   if (h->pending) { CU(cudaEventSynchronize(h->done)); h->pending = false; }
   CU(cudaGetLastError());
-  int err = 0;
-  CU(cudaMemcpy(&err, h->d.error, sizeof(int), cudaMemcpyDeviceToHost));
+  const int err = *h->err_host;   // travelled with the step: no blocking copy here
   if (err == 2) return fail("internal error: a 6502 lane gave up waiting for its picture-side partner (hand-off protocol)");
   if (err) return fail("episode over right after reset ('This should never happen.', atari_emulator.py:108-109)");
   return 0;
@@ -1322,6 +1327,7 @@ int mn_env_reset(mn_handle h, int env, void* stream) {
   launch_initial_state(h, st);
   launch_emit(h, env, env + 1, 1, st);
   CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(h->err_host, h->d.error, sizeof(int), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   return mn_wait(h);
 }
