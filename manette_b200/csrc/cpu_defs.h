@@ -73,7 +73,8 @@ struct alignas(16) FastEnt {
   uint32_t dm, spd, cyc, seqinc;                 // register-file mask of the result, SP change << 24, base cycles, length
   uint32_t cmask, cconst, rotmask, nzmask;       // carry in = (C & cmask) | cconst; rotate-in = C & rotmask; nz <- result?
   uint32_t g, bm_nz, bm_p, pclr;                 // G_* flags; branch test over nz / over P; flag op: bits of P cleared ...
-  uint32_t pset, sel_pb, sel_padd, pad;          // ... and set; the byte pair's address = (byte sel_pb) + (byte sel_padd)
+  uint32_t pset, sel_pb, sel_padd, penbit;       // ... and set; the byte pair's address = (byte sel_pb) + (byte sel_padd);
+                                                 // penbit: 0xFF00 for indexed reads (+1 cycle across a page) | 0xC0 for BIT (N, V <- M)
 };
 enum : uint32_t {
   G_VALID = 1u << 0, G_NEEDPAIR = 1u << 1 /* both bytes of the pair must lie in RIOT RAM */, G_PTR = 1u << 2 /* base = the pair */,
@@ -336,6 +337,10 @@ constexpr FastEnt fast_decode_entry(int opc) {
   t.sel_pb = from_stack ? 0x5553u : 0x5554u;
   t.sel_padd = from_stack ? 0x4445u : (f & FX_PAIR_X) ? 0x4441u : 0x4444u;
   const uint32_t pcs = (f >> FX_PCS) & 3u;
+  // BIT runs through the datapath as A AND M without a destination: Z comes out of nz = A & M, N and V are copied from
+  // the operand by two masked moves (penbit low byte)
+  if (f & FX_BIT) { t.sel_a = uint32_t(SEL_A) | 0x7770u; t.sel_b = uint32_t(SEL_M) | 0x7770u; t.sel_fn = uint32_t(FN_AND) | 0x7770u; t.nzmask = 0xFFFFFFFFu; }
+  t.penbit = ((d & D_PAGEPEN) ? 0xFF00u : 0u) | ((f & FX_BIT) ? 0xC0u : 0u);
   t.g = ((f & FX_VALID) ? G_VALID : 0u) | ((f & FX_PAIR) ? G_NEEDPAIR : 0u) |
         (((f & (FX_PAIR | FX_PAIR_STACK)) == FX_PAIR) ? G_PTR : 0u) | ((f & FX_PULL) ? G_RA_P0 : 0u) |
         ((d & D_READ) ? G_READ : 0u) | ((d & D_WRITE) ? G_WRITE : 0u) | ((f & FX_PUSH) ? G_PUSH : 0u) |

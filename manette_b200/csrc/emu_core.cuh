@@ -46,6 +46,26 @@
 #endif
 #define MN_CTX_SPACES(c) do { MN_IN_SHARED((c).s); MN_IN_SHARED((c).ram); MN_IN_SHARED((c).fifo); MN_IN_SHARED((c).rom); MN_IN_GLOBAL((c).fb); } while (0)
 
+// Inlining of the picture-side call tree.  While the picture side ran between the instructions of the 6502 loop its
+// functions were kept out of line for the instruction caches' sake (round 1); on its own warp the whole tree inlined
+// into picture_process is fastest (B200, 16,384 Ms Pacman envs, k frames/s: none 694, tia_apply 710, + tia_advance 726,
+// + player / missile words 736; the words alone 632).  -DMN_PIC*_OUT put single levels back out of line.
+#ifdef MN_PICW_OUT
+#define MN_PICW_ATTR MN_NOINLINE
+#else
+#define MN_PICW_ATTR MN_INLINE
+#endif
+#ifdef MN_PICADV_OUT
+#define MN_PICADV_ATTR MN_NOINLINE
+#else
+#define MN_PICADV_ATTR MN_INLINE
+#endif
+#ifdef MN_PICAPP_OUT
+#define MN_PICAPP_ATTR MN_NOINLINE
+#else
+#define MN_PICAPP_ATTR MN_INLINE
+#endif
+
 namespace mn {
 
 // ------------------------------------------------------------------ constants
@@ -214,7 +234,7 @@ MN_HD MN_INLINE uint32_t copies_word(uint32_t pattern, int pos, int mode, bool s
   if (b >= 0) { int p = pos + b; if (p >= 160) p -= 160; m |= place(pattern, p, w); }
   return m;
 }
-MN_HD MN_NOINLINE uint32_t player_word(uint32_t grp, int nusiz, int pos, bool suppress, int w) {
+MN_HD MN_PICW_ATTR uint32_t player_word(uint32_t grp, int nusiz, int pos, bool suppress, int w) {
   int mode = nusiz & 7;
   if (mode == 5 || mode == 7) {        // double / quad sized single copy, drawn one pixel late
     if (suppress) return 0u;
@@ -224,7 +244,7 @@ MN_HD MN_NOINLINE uint32_t player_word(uint32_t grp, int nusiz, int pos, bool su
   }
   return copies_word(rev8(grp), pos, mode, suppress, w);
 }
-MN_HD MN_NOINLINE uint32_t missile_word(int nusiz, int pos, int w) {
+MN_HD MN_PICW_ATTR uint32_t missile_word(int nusiz, int pos, int w) {
   int mode = nusiz & 7;
   uint32_t pattern = (1u << (1 << ((nusiz >> 4) & 3))) - 1u;
   if (mode == 5 || mode == 7) mode = 0;
@@ -388,7 +408,7 @@ MN_HD MN_PIC_INLINE void tia_render(Ctx& c, int n, int hpos) {
 }
 
 // bring the picture up to colour clock `clock` (relative to the start of the frame)
-MN_HD MN_NOINLINE void tia_advance(Ctx& c, int32_t clock) {
+MN_HD MN_PICADV_ATTR void tia_advance(Ctx& c, int32_t clock) {
   MN_CTX_SPACES(c);
   EnvState& s = *c.s;
   const int32_t start = 228 * MN_YSTART;
@@ -486,7 +506,7 @@ static_assert(OB_P0 == 0 && OB_M0 == 1 && OB_P1 == 2 && OB_M1 == 3 && OB_BL == 4
 static_assert(F_REFP1 == F_REFP0 << 1 && F_ENAM1 == F_ENAM0 << 1 && F_ENABL == F_ENAM0 << 2 && F_VDELP1 == F_VDELP0 << 1,
               "tia_apply shifts these flag bits by the register offset");
 // ---- picture side: apply one queued register write (colour clock `rel` since the start of the frame)
-MN_HD MN_NOINLINE void tia_apply(Ctx& c, int32_t rel, uint32_t addr, uint32_t v) {
+MN_HD MN_PICAPP_ATTR void tia_apply(Ctx& c, int32_t rel, uint32_t addr, uint32_t v) {
   MN_CTX_SPACES(c);
   EnvState& s = *c.s;
   const int32_t hpos = rel % 228;
@@ -821,7 +841,7 @@ MN_HD MN_INLINE FastEnt fast_entry(maddr tab, uint32_t ir) {   // Tables::f foll
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+32];" : "=r"(t.dm), "=r"(t.spd), "=r"(t.cyc), "=r"(t.seqinc) : "r"(q) : "memory");
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+48];" : "=r"(t.cmask), "=r"(t.cconst), "=r"(t.rotmask), "=r"(t.nzmask) : "r"(q) : "memory");
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+64];" : "=r"(t.g), "=r"(t.bm_nz), "=r"(t.bm_p), "=r"(t.pclr) : "r"(q) : "memory");
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+80];" : "=r"(t.pset), "=r"(t.sel_pb), "=r"(t.sel_padd), "=r"(t.pad) : "r"(q) : "memory");
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+80];" : "=r"(t.pset), "=r"(t.sel_pb), "=r"(t.sel_padd), "=r"(t.penbit) : "r"(q) : "memory");
   return t;
 #elif defined(__CUDACC__)
   (void)tab; (void)ir; FastEnt t = {}; return t;
@@ -1053,7 +1073,7 @@ MN_HD MN_NOINLINE_DEV uint32_t cpu_special(Ctx& c, const Mem& mm, Cpu& r, uint32
   switch (op) {
     case O_ADC: op_adc(r, m); break;
     case O_SBC: op_sbc(r, m); break;
-    case O_BIT: r.nz = ((m & 0x80) << 1) | ((cpuA(r) & m) ? 1u : 0u); r.P = (r.P & ~0x40u) | (m & 0x40); break;
+    case O_BIT: r.nz = ((m & 0x80) << 1) | (cpuA(r) & m); r.P = (r.P & ~0x40u) | (m & 0x40); break;   // (Z from A & M, N = M's bit 7: the fast tick forms the same word)
     case O_LXA: { const uint32_t v = (cpuA(r) | 0xEE) & m; setA(r, v); setX(r, v); r.nz = v; break; }
     case O_ANC: { const uint32_t v = cpuA(r) & m; setA(r, v); r.nz = v; r.P = (r.P & ~1u) | (v >> 7); break; }
     case O_ALR: { uint32_t v = cpuA(r) & m; r.P = (r.P & ~1u) | (v & 1); v >>= 1; setA(r, v); r.nz = v; break; }
@@ -1237,7 +1257,7 @@ MN_HD MN_INLINE bool cpu_fast(const Mem& mm, Cpu& r, const bool go) {
   const uint32_t idx = perm8(r.axys, 0u, t.sel_idx);
   const uint32_t base = (g & G_PTR) ? pair : ((b1 | (b2 << 8)) & t.xm);
   const uint32_t ea = (base + idx) & t.xm;
-  cyc += int32_t(uint32_t((g & G_PAGEPEN) != 0u) & uint32_t(((base ^ ea) & 0xFF00u) != 0u));
+  cyc += int32_t(((base ^ ea) & t.penbit & 0xFF00u) != 0u);
   // ---- read phase: cartridge ROM away from the hot spots, RIOT RAM, or the RIOT timer before it underflows
   const uint32_t ra = (g & G_RA_P0) ? (0x100u | p0) : ea;
   const bool r_rom = (ra & 0x1000u) != 0u;
@@ -1270,9 +1290,10 @@ MN_HD MN_INLINE bool cpu_fast(const Mem& mm, Cpu& r, const bool go) {
   const uint32_t vbit = ((~(a ^ b)) & (a ^ sum) & 0x80u) >> 1;
   uint32_t P = (r.P & ~t.pm) | ((cout | vbit) & t.pm);
   uint32_t nz = (res & t.nzmask) | (r.nz & ~t.nzmask);
-  // BIT, flag ops (a couple of selects each)
-  nz = (g & G_BIT) ? (((m & 0x80u) << 1) | uint32_t((cpuA(r) & m) != 0u)) : nz;
-  P = (g & G_BIT) ? ((P & ~0x40u) | (m & 0x40u)) : P;
+  // BIT (the datapath computed A & M for Z): N and V are the operand's bits 7 and 6 (penbit = 0xC0 for BIT, else 0); flag ops
+  nz |= (m & t.penbit & 0x80u) << 1;
+  const uint32_t vsel = t.penbit & 0x40u;
+  P = (P & ~vsel) | (m & vsel);
   P = (P & ~t.pclr) | t.pset;
   const uint32_t axys = ((r.axys & ~t.dm) | ((res * 0x01010101u) & t.dm)) + t.spd;
   // ---- branches: taken <=> ((nz & mask) | (P & mask)) != 0, possibly inverted (Z: nz[7:0], N: nz[8:7], C, V in P)
