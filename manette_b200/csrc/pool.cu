@@ -217,19 +217,21 @@ __device__ __forceinline__ void picture_warp(Ctx& c, unsigned wmask, int diag) {
   uint32_t* mb = c.fifo + MN_MBOX;
   uint32_t pseq = 0;
   bool fin = false;
-  unsigned idle_ns = 64;
+  int idle = 0;
   for (;;) {
     const bool req = !fin && mbox_load(mb + MB_HAND) != pseq;
     if (!__any_sync(wmask, req)) {
       if (__all_sync(wmask, fin)) break;
       // An idle partner shares its SM sub-partition's issue slots with the 6502 warp it serves: poll rarely.  Hand-offs
-      // come ~60 us apart and only two kinds are waited for (collision-latch reads, the end of a unit), so a back-off
-      // up to ~0.5 us costs nothing that shows, while a tight poll took a third of all issued instructions (ncu).
-      __nanosleep(idle_ns);
-      if (idle_ns < 512) idle_ns += idle_ns;
+      // come ~50 us apart and only two kinds are waited for (collision-latch reads, the end of a unit).  ncu showed a
+      // single __nanosleep per poll to return after a few tens of ns -- the poll loop then issued a third of all the
+      // kernel's instructions -- so the wait is a counted run of them that grows while nothing arrives (<~ 1 us).
+      if (idle < 24) idle += 4;
+#pragma unroll 1
+      for (int k = 0; k < idle; ++k) __nanosleep(200);
       continue;
     }
-    idle_ns = 64;
+    idle = 0;
     if (req) {
       __threadfence_block();
       const int buf = int(pseq & (MN_FIFO_NBUF - 1));
