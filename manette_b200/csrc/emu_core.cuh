@@ -908,10 +908,13 @@ MN_HD MN_NOINLINE uint32_t make_segmap(const EnvState& s) {
   const uint32_t sliced = uint32_t(s.slice0) | (uint32_t(s.slice1) << 8) | (uint32_t(s.slice2) << 16) | (7u << 24);
   return (s.cart == CART_E0) ? sliced : (s.cart == CART_2K) ? 0x01000100u : banked;
 }
+// first window offset that may be a bank-switch hot spot: F8 $FF8-$FF9, F6 $FF6-$FF9, E0 $FE0-$FF7 (cart_touch); the stubs
+// that do the switching sit right below them and run on the fast paths like any other code
+MN_HD MN_INLINE uint32_t cart_hot_lo(uint32_t cart) { return cart == CART_F8 ? 0xFF8u : cart == CART_F6 ? 0xFF6u : cart == CART_E0 ? 0xFE0u : 0x1000u; }
 // does not touch fifo_n: that one is carried by the flat loop across frames
 MN_HD MN_INLINE void cpu_load(const EnvState& s, Cpu& r) {
   r.axys = uint32_t(s.A) | (uint32_t(s.X) << 8) | (uint32_t(s.Y) << 16) | (uint32_t(s.SP) << 24); r.PC = s.PC; r.P = s.P; r.nz = s.nz; r.dbus = s.dbus;
-  r.cycles = s.cycles; r.clk0 = s.clk_frame_start; r.cyc0 = s.clk_frame_start / 3; r.segmap = make_segmap(s); r.romw = (r.segmap & 0xFFu) << 10; r.hot_lo = (s.cart > CART_4K) ? 0xFE0u : 0x1000u;
+  r.cycles = s.cycles; r.clk0 = s.clk_frame_start; r.cyc0 = s.clk_frame_start / 3; r.segmap = make_segmap(s); r.romw = (r.segmap & 0xFFu) << 10; r.hot_lo = cart_hot_lo(s.cart);
   r.stop = (s.flags & F_STOP) != 0;
   r.def_lo = r.def_hi = r.dep_lo = r.dep_hi = 0; r.tainted = false;
 }
@@ -1238,7 +1241,7 @@ MN_HD MN_INLINE bool cpu_fast(const Mem& mm, Cpu& r, const bool go) {
   // decode entry arrives in the form it is used in, see FastEnt)
   const uint32_t pc = r.PC;
   // (the three bytes must not straddle a 1K page when pages need not be consecutive)
-  const uint32_t code_ok = uint32_t((pc & 0x1000u) != 0u) & uint32_t((pc & 0xFFFu) < 0xFDEu) & (FLAT ? 1u : uint32_t((pc & 0x3FFu) < 0x3FEu));
+  const uint32_t code_ok = uint32_t((pc & 0x1000u) != 0u) & uint32_t((pc & 0xFFFu) + 2u < r.hot_lo) & (FLAT ? 1u : uint32_t((pc & 0x3FFu) < 0x3FEu));
   const maddr ca = fast_rom_addr<FLAT>(mm, r, pc);
   const uint32_t ir = m8(ca), b1 = m8(ca + 1u), b2 = m8(ca + 2u);
   const FastEnt t = fast_entry(mm.tab, ir);

@@ -118,8 +118,8 @@ struct PoolDev {             // kernel argument block (by value)
   int32_t* error;            // sticky: 1 = episode over right after reset (atari_emulator.py:108-109)
   unsigned long long* total_next;
   // reset memoisation (see k_reset_prepare)
-  uint8_t* memo;             // n_games x 75 timer seeds x MN_MEMO_SLOTS entries of memo_entry_bytes
-  int32_t memo_entry_bytes, memo_enabled;
+  uint8_t* memo;             // n_games x 75 timer seeds x memo_slots entries of memo_entry_bytes
+  int32_t memo_entry_bytes, memo_enabled, memo_slots;
   uint32_t* reset_rnd;       // (N,) the RNG draw that seeds the RIOT timer of the reset in flight
   uint8_t* pre_ram;          // (N,128) RIOT RAM as it was before the reset in flight (memo key of a miss)
   int32_t* memo_hit;         // (N,) entry index the reset in flight is restored from
@@ -128,6 +128,8 @@ struct PoolDev {             // kernel argument block (by value)
   unsigned long long* memo_stats;   // hits, misses, inserts
   unsigned long long* total_instr;  // emulated 6502 instructions
   unsigned long long* diag_out;     // MN_DIAG=2 counters
+  // reset-memo warm-up (mn_reset_all): scratch for the envs that lend themselves to it
+  EnvState* warm_env; uint8_t* warm_ram; uint32_t* warm_episode;
   unsigned long long* redo_count;   // units re-run with every frame drawn (exact fallback of the pixel-less frames)
   uint8_t* history;          // (N, H, 84, 84, 4D) ring of the last H published states (paac.py:79-83,107-112), or null
   int32_t history_depth;
@@ -148,6 +150,8 @@ enum { ROUND_FIGAR = 0, ROUND_RESET = 1, ROUND_INITIAL = 2, ROUND_POWER_ON = 3, 
 struct MemoHdr {
   int32_t state;             // 0 empty, 1 being written, 2 valid
   int32_t n_acts;            // ALE act() calls inside the segment (2 RNG advances and one frame count each)
+  int32_t noops;             // start no-ops the segment ran (random_start; part of the key)
+  int32_t pad0;
   unsigned long long dep_lo, dep_hi, def_lo, def_hi;
   uint8_t dep_val[128];      // RAM before the reset (only the dep bytes matter)
   uint8_t ram[128];          // RAM after the segment (only the def bytes matter)
@@ -433,6 +437,46 @@ __global__ void k_clear_counts(PoolDev p, int which) {
   if (threadIdx.x < MN_MAX_GAMES) p.counts[which * MN_MAX_GAMES + threadIdx.x] = 0;
 }
 
+// ---- reset-memo warm-up.  A reset that misses the memo puts ~80 emulated frames on the critical path of the macro step
+// it falls into.  For the games whose reset depends on nothing but the RIOT timer seed (11 of the 12 README games) all
+// 75 possible results can be produced once, up front: the first min(n, 75) envs of every game lend themselves -- their
+// machine, RAM and episode counter are saved, they run the reset with a FORCED timer seed through the ordinary probe /
+// insert path, and are put back.  `pass` p covers seeds p*W .. p*W + W - 1 (W = envs lent by the game).
+__global__ void k_warm_begin(PoolDev p, int pass) {
+  const int gi = blockIdx.x, i = threadIdx.x;            // one block per game, one thread per lent env
+  const GameDev& G = p.games[gi];
+  const int W = G.n_envs < MN_TIMER_SEEDS ? G.n_envs : MN_TIMER_SEEDS;
+  __shared__ int s_count;
+  if (i == 0) s_count = 0;
+  __syncthreads();
+  const int seed = pass * W + i;
+  if (i < W && seed < MN_TIMER_SEEDS) {
+    const int e = G.env0 + i;
+    const int slot = gi * MN_TIMER_SEEDS + i;
+    p.warm_env[slot] = p.env[e];
+    p.warm_episode[slot] = p.episode[e];
+    for (int j = 0; j < 128; ++j) { const uint8_t v = p.ram[size_t(e) * 128 + j]; p.warm_ram[size_t(slot) * 128 + j] = v; p.pre_ram[size_t(e) * 128 + j] = v; }
+    p.reset_rnd[e] = uint32_t(seed);                     // console_reset: timer = 25 + rnd % 75
+    p.memo_hit[e] = -1;
+    const int k = atomicAdd(&s_count, 1);
+    p.lists[size_t(1) * p.n_envs + G.env0 + k] = e;
+  }
+  __syncthreads();
+  if (i == 0) { p.counts[1 * MN_MAX_GAMES + gi] = s_count; p.counts[0 * MN_MAX_GAMES + gi] = 0; }
+}
+__global__ void k_warm_end(PoolDev p, int pass) {
+  const int gi = blockIdx.x, i = threadIdx.x;
+  const GameDev& G = p.games[gi];
+  const int W = G.n_envs < MN_TIMER_SEEDS ? G.n_envs : MN_TIMER_SEEDS;
+  if (i < W && pass * W + i < MN_TIMER_SEEDS) {
+    const int e = G.env0 + i;
+    const int slot = gi * MN_TIMER_SEEDS + i;
+    p.env[e] = p.warm_env[slot];
+    p.episode[e] = p.warm_episode[slot];
+    for (int j = 0; j < 128; ++j) p.ram[size_t(e) * 128 + j] = p.warm_ram[size_t(slot) * 128 + j];
+  }
+}
+
 // Every env on the reset list draws the RNG value that seeds its RIOT timer (ALE's System::reset) and looks for
 // a memo entry it may be restored from: hits go to list 0, misses (to be emulated with the probe) to list 1.
 __global__ void k_reset_prepare(PoolDev p) {
@@ -446,12 +490,14 @@ __global__ void k_reset_prepare(PoolDev p) {
   p.reset_rnd[e] = rnd;
   int hit = -1;
   const unsigned long long* ram8 = reinterpret_cast<const unsigned long long*>(p.ram + size_t(e) * 128);
+  // the start no-ops the reset will run (k_round<RESET> computes the same): part of the key under random_start
+  const int noops = p.random_start ? int(start_noops(uint32_t(p.seed), uint32_t(p.env_id_offset + e), p.episode[e])) : 0;
   if (p.memo_enabled) {
-    const size_t bucket = (size_t(gi) * MN_TIMER_SEEDS + rnd % MN_TIMER_SEEDS) * MN_MEMO_SLOTS;
-    for (int sl = 0; sl < MN_MEMO_SLOTS && hit < 0; ++sl) {
+    const size_t bucket = (size_t(gi) * MN_TIMER_SEEDS + rnd % MN_TIMER_SEEDS) * size_t(p.memo_slots);
+    for (int sl = 0; sl < p.memo_slots && hit < 0; ++sl) {
       const MemoHdr* m = reinterpret_cast<const MemoHdr*>(p.memo + (bucket + sl) * size_t(p.memo_entry_bytes));
       if (*reinterpret_cast<const volatile int32_t*>(&m->state) != 2) continue;
-      bool same = true;
+      bool same = (m->noops == noops);
       if (m->dep_lo | m->dep_hi) {
         const unsigned long long* want = reinterpret_cast<const unsigned long long*>(m->dep_val);
         for (int w = 0; w < 16 && same; ++w) {
@@ -523,22 +569,24 @@ __global__ void __launch_bounds__(256) k_memo_insert(PoolDev p) {
   const int e = p.lists[size_t(1) * p.n_envs + pos];
   const unsigned long long* t = p.track + size_t(e) * 5;
   const int bucket_id = gi * MN_TIMER_SEEDS + int(p.reset_rnd[e] % MN_TIMER_SEEDS);
+  // (the reset round has moved the episode counter on: the no-ops it ran were those of episode - 1)
+  const int my_noops = p.random_start ? int(start_noops(uint32_t(p.seed), uint32_t(p.env_id_offset + e), p.episode[e] - 1u)) : 0;
   if (threadIdx.x == 0) {
     int slot = -1;
     // the RAM scrape must only have seen written bytes; one insertion per bucket at a time
     if (!(t[4] & 2ull) && atomicCAS(&p.memo_busy[bucket_id], 0, 1) == 0) {
-      const size_t bucket = size_t(bucket_id) * MN_MEMO_SLOTS;
+      const size_t bucket = size_t(bucket_id) * size_t(p.memo_slots);
       const uint8_t* pre = p.pre_ram + size_t(e) * 128;
       bool known = false;
-      for (int sl = 0; sl < MN_MEMO_SLOTS && !known; ++sl) {   // stored since k_reset_prepare looked?
+      for (int sl = 0; sl < p.memo_slots && !known; ++sl) {   // stored since k_reset_prepare looked?
         const MemoHdr* m = reinterpret_cast<const MemoHdr*>(p.memo + (bucket + sl) * size_t(p.memo_entry_bytes));
         if (*reinterpret_cast<const volatile int32_t*>(&m->state) != 2) continue;
-        bool same = true;
+        bool same = (m->noops == my_noops);
         for (int j = 0; j < 128 && same; ++j)
           if ((((j & 64) ? m->dep_hi : m->dep_lo) >> (j & 63)) & 1ull) same = (m->dep_val[j] == pre[j]);
         known = same;
       }
-      for (int sl = 0; sl < MN_MEMO_SLOTS && !known && slot < 0; ++sl) {
+      for (int sl = 0; sl < p.memo_slots && !known && slot < 0; ++sl) {
         MemoHdr* m = reinterpret_cast<MemoHdr*>(p.memo + (bucket + sl) * size_t(p.memo_entry_bytes));
         if (atomicCAS(&m->state, 0, 1) == 0) slot = int(bucket + sl);
       }
@@ -563,7 +611,8 @@ __global__ void __launch_bounds__(256) k_memo_insert(PoolDev p) {
   if (threadIdx.x == 0) {
     m->def_lo = t[0]; m->def_hi = t[1]; m->dep_lo = t[2]; m->dep_hi = t[3];
     m->env = p.env[e];
-    m->n_acts = MN_STACK * MN_ACTION_REPEAT;
+    m->n_acts = MN_STACK * MN_ACTION_REPEAT + my_noops;
+    m->noops = my_noops;
     m->ring_head = uint32_t(head);
     atomicAdd(p.memo_stats + 2, 1ull);
   }
@@ -919,6 +968,8 @@ struct mn_pool {
   int64_t launches;
   std::vector<void*> allocs;
   uint8_t* pin_ram;
+  bool memo_warm;            // the reset memo has been warmed up (first mn_reset_all)
+  int warm_passes;           // passes the warm-up takes (0 = off)
   int* err_host;             // pinned: the device error word as of the last completed step (copied before `done` is recorded)
   std::vector<int> env_game_host;
   GameDev games_host[MN_MAX_GAMES];
@@ -1118,10 +1169,27 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
   rc |= dev_alloc(h, &d.total_next, size_t(1));
   rc |= dev_alloc(h, &d.redo_count, size_t(1));
   rc |= dev_alloc(h, &d.diag_out, size_t(8));
+  rc |= dev_alloc(h, &d.warm_env, size_t(d.n_games) * MN_TIMER_SEEDS);
+  rc |= dev_alloc(h, &d.warm_ram, size_t(d.n_games) * MN_TIMER_SEEDS * 128);
+  rc |= dev_alloc(h, &d.warm_episode, size_t(d.n_games) * MN_TIMER_SEEDS);
   rc |= dev_alloc(h, &d.total_instr, size_t(1));
-  d.memo_enabled = (cfg->random_start == 0 && cfg->no_reset_memo == 0) ? 1 : 0;
+  // random_start: the start no-op count (0..30) joins the key, so a bucket needs room for 31 counts (x RAM-dependence
+  // variants): 40 slots instead of 8 (gray: 75 x 40 x 96 KB = 290 MB per game)
+  d.memo_enabled = (cfg->no_reset_memo == 0) ? 1 : 0;
+  d.memo_slots = cfg->random_start ? 40 : MN_MEMO_SLOTS;
+  // warm-up: on when every game lends at least 38 envs (at most two extra reset passes at creation); MN_WARM_MEMO=0/1 overrides
+  h->memo_warm = false; h->warm_passes = 0;
+  if (d.memo_enabled && !cfg->random_start) {   // (under random_start the memo fills as episodes end: 75 x 31 keys per game)
+    int min_envs = 1 << 30;
+    for (int g = 0; g < d.n_games; ++g) if (d.games[g].n_envs < min_envs) min_envs = d.games[g].n_envs;
+    const int W = min_envs < MN_TIMER_SEEDS ? min_envs : MN_TIMER_SEEDS;
+    const int passes = (MN_TIMER_SEEDS + W - 1) / W;
+    bool on = passes <= 2;
+    if (const char* ev = getenv("MN_WARM_MEMO")) on = atoi(ev) != 0;
+    h->warm_passes = on ? passes : 0;
+  }
   d.memo_entry_bytes = int32_t(memo_hdr_bytes() + 2 * MN_FRAME_BYTES + size_t(MN_STACK) * MN_PLANE * D);
-  rc |= dev_alloc(h, &d.memo, d.memo_enabled ? size_t(d.n_games) * MN_TIMER_SEEDS * MN_MEMO_SLOTS * size_t(d.memo_entry_bytes) : size_t(16));
+  rc |= dev_alloc(h, &d.memo, d.memo_enabled ? size_t(d.n_games) * MN_TIMER_SEEDS * size_t(d.memo_slots) * size_t(d.memo_entry_bytes) : size_t(16));
   rc |= dev_alloc(h, &d.reset_rnd, N);
   rc |= dev_alloc(h, &d.pre_ram, N * 128);
   rc |= dev_alloc(h, &d.memo_hit, N);
@@ -1251,6 +1319,20 @@ int mn_reset_all(mn_handle h, void* stream) {
   CU(cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n = h->d.n_envs, tb = 256, gb = (n + tb - 1) / tb;
+  if (!h->memo_warm && h->warm_passes > 0) {   // once: all 75 timer seeds of every game into the reset memo
+    for (int pass = 0; pass < h->warm_passes; ++pass) {
+      k_warm_begin<<<h->d.n_games, 96, 0, st>>>(h->d, pass);
+      launch_round(h, ROUND_RESET, 1, -1, st, true);
+      for (int i = 0; i < MN_STACK; ++i) {
+        launch_round(h, ROUND_INITIAL, 1, (i == MN_STACK - 1) ? -1 : -2, st, true);
+        launch_push(h, 1, st);
+      }
+      if (h->d.depth == 1) k_memo_insert<1><<<n, 256, 0, st>>>(h->d); else k_memo_insert<3><<<n, 256, 0, st>>>(h->d);
+      k_warm_end<<<h->d.n_games, 96, 0, st>>>(h->d, pass);
+      h->launches += 3;
+    }
+    h->memo_warm = true;
+  }
   k_fill_list<<<gb, tb, 0, st>>>(h->d, 2);
   h->launches++;
   launch_initial_state(h, st);

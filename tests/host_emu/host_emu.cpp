@@ -46,7 +46,33 @@ static void run_unit(HostEnv* e, int kind, int action, int count, uint32_t seed,
   }
 }
 
+// get_initial_state() the way the kernels probe it: the reset unit and the four NOOP next() units with the RAM-dependence
+// probe carried from one to the next (k_round<true> RESET, then 4 x INITIAL).  out4 = def_lo def_hi dep_lo dep_hi
+static void tracked_initial_state(HostEnv* e, uint32_t rnd, uint64_t* out4) {
+  uint64_t def_lo = 0, def_hi = 0, dep_lo = 0, dep_hi = 0; bool tainted = false;
+  for (int k = 0; k < 5; ++k) {
+    e->c.all_pixels = true;
+    Unit u;
+    unit_init(e->c, u, k == 0 ? U_RESET : U_ACTS, 0, k == 0 ? 0 : 4, rnd);
+    Hot hot;
+    hot_init(e->c, u, hot);
+    hot.def_lo = def_lo; hot.def_hi = def_hi; hot.dep_lo = dep_lo; hot.dep_hi = dep_hi; hot.tainted = tainted;
+    const Mem mm = mem_of(e->c);
+    while (hot_has_work(hot)) {
+      unit_tick<true>(e->c, mm, u, hot);
+      if (MN_FILL(hot.cpu.fifo_n) >= e->drain_at) hot_drain(e->c, hot);
+    }
+    unit_finish(e->c, hot);
+    def_lo = hot.def_lo; def_hi = hot.def_hi; dep_lo = hot.dep_lo; dep_hi = hot.dep_hi; tainted = hot.tainted;
+  }
+  out4[0] = def_lo; out4[1] = def_hi; out4[2] = dep_lo; out4[3] = dep_hi;
+}
+
 extern "C" {
+void he_tracked_initial_state(void* h, uint64_t* out4) {
+  HostEnv* e = (HostEnv*)h;
+  tracked_initial_state(e, rng_next(e->s.rng), out4);
+}
 void* he_create(const uint8_t* rom, int n, const char* game, uint32_t seed, int skip_frames) {
   HostEnv* e = new HostEnv();
   memset(&e->s, 0, sizeof(e->s));

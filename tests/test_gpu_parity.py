@@ -164,3 +164,65 @@ def test_memo_off_equals_memo_on():
     finally:
         for p in pools:
             p.close()
+
+
+@pytest.mark.parametrize("game", ["breakout", "ms_pacman"])
+def test_warmed_reset_memo_restores_every_first_reset(game):
+    """mn_reset_all warms the reset memo with all 75 timer seeds (envs lent and put back): every get_initial_state of
+    the pool -- the first ones included -- is then restored by copy, and must equal the oracle's emulated one."""
+    n, k = 80, 11
+    ora = util.ParallelOraclePool(game, range(n), nb_choices=k, max_repetition=10)
+    pool = _device_pool(game, n, tab_rep=ora.tab_rep)
+    try:
+        import torch
+        pool.reset_all()
+        assert np.array_equal(pool.states.cpu().numpy(), ora.initial_states())
+        hits, misses, stored = pool.memo_stats()
+        assert (hits, misses) == (n, 0) and stored == 75, (hits, misses, stored)
+        rng = np.random.RandomState(5)
+        for t in range(6):
+            acts, reps = rng.randint(0, ora.num_actions, n), rng.randint(0, k, n)
+            out = ora.macro_step(acts, reps, taps=True)
+            pool.action_idx.copy_(torch.as_tensor(acts.astype(np.int32)))
+            pool.repetition_idx.copy_(torch.as_tensor(reps.astype(np.int32)))
+            pool.step_async(use_indices=True)
+            pool.wait()
+            assert np.array_equal(pool.states.cpu().numpy(), out[0]), t
+            assert np.array_equal(pool.rewards.cpu().numpy(), out[1]) and np.array_equal(pool.terminals.cpu().numpy(), out[2])
+        for e in range(0, n, 7):
+            assert np.array_equal(pool.ram(e), out[4][e]) and np.array_equal(pool.screen(e), out[5][e])
+    finally:
+        pool.close()
+        ora.close()
+
+
+def test_random_start_resets_are_memoised_exactly():
+    """random_start: the start no-op count (0..30) is part of the reset memo's key.  Single-life Breakout ends episodes
+    every few steps: hundreds of resets, so (timer seed, no-op count) pairs recur and are restored by copy -- every
+    state must still equal the oracle's, which emulates every reset."""
+    import manette_b200 as mb
+    import torch
+    game, n, k, seed, steps = "breakout", 48, 11, 3, 70
+    ora = OraclePool(game, n, nb_choices=k, max_repetition=10, single_life=True, random_start=True, seed=seed,
+                     noops=lambda gid, ep: mb.start_noops(seed, gid, ep))
+    pool = mb.DevicePool([(game, rom_bytes(game), n)], tab_rep=ora.tab_rep, single_life_episodes=True, random_start=True,
+                         random_seed=seed)
+    try:
+        pool.reset_all()
+        assert np.array_equal(pool.states.cpu().numpy(), ora.initial_states())
+        acts, reps = util.schedule(31, steps, n, ora.num_actions, k)
+        for t in range(steps):
+            ws, wr, wt, _ = ora.macro_step(acts[t], reps[t])
+            pool.action_idx.copy_(torch.as_tensor(acts[t].astype(np.int32)))
+            pool.repetition_idx.copy_(torch.as_tensor(reps[t].astype(np.int32)))
+            pool.step_async(use_indices=True)
+            pool.wait()
+            assert np.array_equal(pool.rewards.cpu().numpy(), wr) and np.array_equal(pool.terminals.cpu().numpy(), wt), t
+            assert np.array_equal(pool.states.cpu().numpy(), ws), t
+        hits, misses, stored = pool.memo_stats()
+        assert hits + misses > 300 and hits > 5, (hits, misses, stored)
+        for e in range(0, n, 5):
+            assert np.array_equal(pool.ram(e), ora.emus[e].ale.getRAM())
+            assert np.array_equal(pool.screen(e), ora.emus[e].ale.getScreen())
+    finally:
+        pool.close()

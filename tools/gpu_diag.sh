@@ -1,7 +1,4 @@
 mkdir -p gpurun_out
-cp manette_b200/libmanette_b200.so /tmp/lib_keep.so
-for defs in "" "-DMN_PICAPP_IN" "-DMN_PICW_IN" "-DMN_PICAPP_IN -DMN_PICW_IN" "-DMN_PICAPP_IN -DMN_PICADV_IN" "-DMN_PICAPP_IN -DMN_PICADV_IN -DMN_PICW_IN"; do
-  MN_BUILD_DEFS="$defs" python -m manette_b200.build > /dev/null 2>&1 || echo "build failed: $defs"
-  echo "defs: [$defs]"; timeout 300 python tools/profile_step.py --envs 16384 --decorrelate 24 --steps 3 2>&1 | tail -1 | cut -c1-110
-done
-cp /tmp/lib_keep.so manette_b200/libmanette_b200.so
+timeout 900 python -m pytest tests/test_gpu_runners.py tests/test_gpu_properties.py tests/test_gpu_parity.py -x -q -k "random_start or sharded or memo or warmed" 2>&1 | tail -3
+timeout 900 python bench.py --workload breakout_figar10_n256 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --random-start --steady-state 600 > gpurun_out/steady_c2_rs.json 2> gpurun_out/steady_c2_rs.err; python -c "
+import json; d=json.loads(open('gpurun_out/steady_c2_rs.json').read().strip().splitlines()[-1]); print('C2 random_start', int(d['value']), d['steady_state'], d['reset_memo'])"
