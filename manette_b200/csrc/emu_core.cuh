@@ -910,7 +910,11 @@ MN_HD MN_NOINLINE uint32_t make_segmap(const EnvState& s) {
 }
 // first window offset that may be a bank-switch hot spot: F8 $FF8-$FF9, F6 $FF6-$FF9, E0 $FE0-$FF7 (cart_touch); the stubs
 // that do the switching sit right below them and run on the fast paths like any other code
+#ifdef MN_OLD_HOTLO
+MN_HD MN_INLINE uint32_t cart_hot_lo(uint32_t cart) { return cart > CART_4K ? 0xFE0u : 0x1000u; }
+#else
 MN_HD MN_INLINE uint32_t cart_hot_lo(uint32_t cart) { return cart == CART_F8 ? 0xFF8u : cart == CART_F6 ? 0xFF6u : cart == CART_E0 ? 0xFE0u : 0x1000u; }
+#endif
 // does not touch fifo_n: that one is carried by the flat loop across frames
 MN_HD MN_INLINE void cpu_load(const EnvState& s, Cpu& r) {
   r.axys = uint32_t(s.A) | (uint32_t(s.X) << 8) | (uint32_t(s.Y) << 16) | (uint32_t(s.SP) << 24); r.PC = s.PC; r.P = s.P; r.nz = s.nz; r.dbus = s.dbus;
@@ -1234,6 +1238,11 @@ template <bool FLAT>
 MN_HD MN_INLINE maddr fast_rom_addr(const Mem& mm, const Cpu& r, uint32_t addr) {
   return FLAT ? (mm.rom + r.romw + (addr & 0xFFFu)) : rom_addr(mm, r.segmap, addr);
 }
+#ifdef MN_OLD_HOTLO
+#define MN_CODE_HI(r) 0xFE0u
+#else
+#define MN_CODE_HI(r) (r).hot_lo
+#endif
 template <bool TRACK, bool FLAT>
 MN_HD MN_INLINE bool cpu_fast(const Mem& mm, Cpu& r, const bool go) {
   if (TRACK) return false;   // the RAM-dependence probe instruments the general path only
@@ -1241,7 +1250,7 @@ MN_HD MN_INLINE bool cpu_fast(const Mem& mm, Cpu& r, const bool go) {
   // decode entry arrives in the form it is used in, see FastEnt)
   const uint32_t pc = r.PC;
   // (the three bytes must not straddle a 1K page when pages need not be consecutive)
-  const uint32_t code_ok = uint32_t((pc & 0x1000u) != 0u) & uint32_t((pc & 0xFFFu) + 2u < r.hot_lo) & (FLAT ? 1u : uint32_t((pc & 0x3FFu) < 0x3FEu));
+  const uint32_t code_ok = uint32_t((pc & 0x1000u) != 0u) & uint32_t((pc & 0xFFFu) + 2u < MN_CODE_HI(r)) & (FLAT ? 1u : uint32_t((pc & 0x3FFu) < 0x3FEu));
   const maddr ca = fast_rom_addr<FLAT>(mm, r, pc);
   const uint32_t ir = m8(ca), b1 = m8(ca + 1u), b2 = m8(ca + 2u);
   const FastEnt t = fast_entry(mm.tab, ir);
@@ -1632,18 +1641,22 @@ MN_HD MN_INLINE int32_t hot_time(const Hot& h) { return h.in_frame ? ((h.jobs <<
 // host test build only: 0 = general path only, 1 = fast tick first (what the kernels do), 2 = run both on every
 // instruction the fast tick accepts and abort on the first difference
 static int g_fast_mode = 1;
+// host test build: use the flat-window instantiation of the fast tick (what the kernels run for every cartridge type
+// but E0); the harness stages 2K images twice, as the kernels do
+static int g_fast_flat = 0;
 static unsigned long long g_fast_taken = 0, g_fast_refused = 0;
 // one instruction the way the kernels run it (mode 1), or with the fast tick checked against the general path (mode 2);
 // returns false if the general path has to run it
 static inline bool cpu_fast_host(Ctx& c, const Mem& mm, Cpu& r) {
   if (g_fast_mode == 0) return false;
-  if (g_fast_mode == 1) return cpu_fast<false, false>(mm, r, true);
+  const bool flat = g_fast_flat != 0 && c.s->cart != CART_E0;
+  if (g_fast_mode == 1) return flat ? cpu_fast<false, true>(mm, r, true) : cpu_fast<false, false>(mm, r, true);
   const Cpu before = r;
   const EnvState s_before = *c.s;
   uint8_t ram0[128], ram1[128]; uint32_t fifo0[MN_MBOX], fifo1[MN_MBOX];
   for (int j = 0; j < 128; ++j) ram0[j] = ram_at(c, j);
   for (int j = 0; j < MN_MBOX; ++j) fifo0[j] = c.fifo[j];
-  if (!cpu_fast<false, false>(mm, r, true)) { ++g_fast_refused; return false; }
+  if (!(flat ? cpu_fast<false, true>(mm, r, true) : cpu_fast<false, false>(mm, r, true))) { ++g_fast_refused; return false; }
   const Cpu fast = r;
   for (int j = 0; j < 128; ++j) { ram1[j] = ram_at(c, j); ram_at(c, j) = ram0[j]; }
   for (int j = 0; j < MN_MBOX; ++j) { fifo1[j] = c.fifo[j]; c.fifo[j] = fifo0[j]; }

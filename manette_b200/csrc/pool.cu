@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(MN_THREADS, 1) k_round(PoolDev p, int mode, in
   {
     const uint4* src = reinterpret_cast<const uint4*>(p.roms + G.rom_off);
     uint4* dst = reinterpret_cast<uint4*>(s_rom);
-    for (int i = threadIdx.x; i < rom_bytes / 16; i += blockDim.x) dst[i] = src[i];
+    for (int i = threadIdx.x; i < ((G.rom_size + 15) & ~15) / 16; i += blockDim.x) dst[i] = src[i];   // (the image, not the window: a 2K image is 2 KB in HBM)
     // a 2K image a second time behind itself: the cartridge window is then 4 KB of consecutive bytes like any other
     if (G.rom_size == 2048) for (int i = threadIdx.x; i < 2048 / 16; i += blockDim.x) dst[2048 / 16 + i] = src[i];
     const uint32_t* ts = reinterpret_cast<const uint32_t*>(p.tables);

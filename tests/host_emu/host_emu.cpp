@@ -78,7 +78,8 @@ void* he_create(const uint8_t* rom, int n, const char* game, uint32_t seed, int 
   memset(&e->s, 0, sizeof(e->s));
   build_tables(&e->tab);
   e->rom.assign(rom, rom + n);
-  e->rom.resize(size_t(n) + 16, 0);   // the fast tick fetches operand bytes speculatively (up to 2 bytes past the image)
+  if (n == 2048) e->rom.insert(e->rom.end(), rom, rom + n);   // 2K images twice, as k_round stages them (flat 4 KB window)
+  e->rom.resize(e->rom.size() + 16, 0);   // the fast tick fetches operand bytes speculatively (up to 2 bytes past the image)
   e->fb.assign(2 * MN_FRAME_BYTES, 0);
   int g = game_id_from_name(game);
   e->s.game = (uint8_t)g; e->s.cart = (uint8_t)detect_cart(rom, n); e->s.ctrl = (uint8_t)game_db(g).ctrl;
@@ -119,7 +120,8 @@ void* he_console_create(const uint8_t* rom, int n) {
   memset(e->ram, 0, 128);
   build_tables(&e->tab);
   e->rom.assign(rom, rom + n);
-  e->rom.resize(size_t(n) + 16, 0);   // the fast tick fetches operand bytes speculatively (up to 2 bytes past the image)
+  if (n == 2048) e->rom.insert(e->rom.end(), rom, rom + n);   // 2K images twice, as k_round stages them (flat 4 KB window)
+  e->rom.resize(e->rom.size() + 16, 0);   // the fast tick fetches operand bytes speculatively (up to 2 bytes past the image)
   e->fb.assign(2 * MN_FRAME_BYTES, 0);
   e->s.game = 0; e->s.cart = (uint8_t)detect_cart(rom, n); e->s.ctrl = 0;
   e->c.s = &e->s; e->c.rom = e->rom.data(); e->c.ram = e->ram; e->c.fb = e->fb.data(); e->c.tab = &e->tab;
@@ -149,6 +151,7 @@ void he_console_step(void* h, int n_instr) {
 }
 // 0 = general path only, 1 = fast tick first (the kernels' flow), 2 = both on every instruction, abort on a difference
 void he_set_fast_mode(int mode) { g_fast_mode = mode; }
+void he_set_fast_flat(int on) { g_fast_flat = on; }
 void he_fast_stats(uint64_t* out2) { out2[0] = g_fast_taken; out2[1] = g_fast_refused; }
 int he_state_size() { return (int)sizeof(EnvState); }
 void he_get_state(void* h, uint8_t* out) { memcpy(out, &((HostEnv*)h)->s, sizeof(EnvState)); }

@@ -125,12 +125,15 @@ def test_next_with_pixel_less_frames_matches_oracle(libs, game):
     L.orc_destroy(o); H.he_destroy(h)
 
 
+@pytest.mark.parametrize("flat", [0, 1])
 @pytest.mark.parametrize("game", GAMES12)
-def test_fast_tick_equals_general_path(libs, game):
+def test_fast_tick_equals_general_path(libs, game, flat):
     """cpu_fast (the branch-free tick the kernels try first) against cpu_step (the general path, the definition) on
     EVERY instruction the fast tick accepts: registers, status, cycles, data bus, RIOT RAM, the TIA write FIFO and the
-    untouched rest of the machine.  The host build aborts on the first difference (he_set_fast_mode(2))."""
+    untouched rest of the machine.  The host build aborts on the first difference (he_set_fast_mode(2)).
+    flat = 1: the flat-cartridge-window instantiation the kernels use for every cartridge type but E0."""
     L, H = libs
+    H.he_set_fast_flat(flat)
     H.he_fast_stats.argtypes = [C.c_void_p]
     rom = rom_bytes(game)
     H.he_set_fast_mode(2)
@@ -153,6 +156,7 @@ def test_fast_tick_equals_general_path(libs, game):
         H.he_destroy(h)
     finally:
         H.he_set_fast_mode(1)
+        H.he_set_fast_flat(0)
 
 
 @pytest.mark.parametrize("mode", [0, 2])

@@ -1,4 +1,24 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_runners.py tests/test_gpu_properties.py tests/test_gpu_parity.py -x -q -k "random_start or sharded or memo or warmed" 2>&1 | tail -3
-timeout 900 python bench.py --workload breakout_figar10_n256 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --random-start --steady-state 600 > gpurun_out/steady_c2_rs.json 2> gpurun_out/steady_c2_rs.err; python -c "
-import json; d=json.loads(open('gpurun_out/steady_c2_rs.json').read().strip().splitlines()[-1]); print('C2 random_start', int(d['value']), d['steady_state'], d['reset_memo'])"
+cat > /tmp/seq.py <<'PY'
+import sys, os
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+import torch, manette_b200 as mb
+from manette_b200.learner import PAACLearner
+from util import rom_bytes
+tab = mb.tab_repetitions(10, 11)
+os.environ.pop("MN_DIAG", None)
+pool = mb.DevicePool([("pong", rom_bytes("pong"), 32)], tab_rep=tab)
+pool.reset_all()
+L = PAACLearner(pool, arch="NIPS", seed=5)
+L.train_rollout()
+L.close(); pool.close()
+os.environ["MN_DIAG"] = sys.argv[1]
+game, n, hist = sys.argv[2], int(sys.argv[3]), int(sys.argv[4])
+try:
+    p2 = mb.DevicePool([(game, rom_bytes(game), n)], tab_rep=tab, history=hist)
+    print("diag", sys.argv[1:], "second pool ok")
+except Exception as e:
+    print("diag", sys.argv[1:], "FAIL", str(e)[:90])
+PY
+for d in 0 32 36 40 48; do CUDA_LAUNCH_BLOCKING=1 timeout 120 python /tmp/seq.py $d breakout 8 5 2>&1 | tail -1; done
+for cfg in "breakout 8 0" "breakout 32 0" "pong 8 0" "pong 32 5" "breakout 64 5"; do CUDA_LAUNCH_BLOCKING=1 timeout 120 python /tmp/seq.py 0 $cfg 2>&1 | tail -1; done
