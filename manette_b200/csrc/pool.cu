@@ -1102,7 +1102,7 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
   d.diag = 0;
   if (const char* ev = getenv("MN_DIAG")) d.diag = atoi(ev);
   d.fifo_high = MN_FIFO_HIGH;
-  if (const char* ev = getenv("MN_FIFO_HIGH")) { const int v = atoi(ev); if (v >= 1 && v <= MN_FIFO_HIGH) d.fifo_high = v; }
+  if (const char* ev = getenv("MN_FIFO_HIGH")) { const int v = atoi(ev); if (v >= 1 && v < MN_FIFO_CAP) d.fifo_high = v; }
   h->max_rep = 0;
   for (int i = 0; i < cfg->nb_choices; ++i) {
     if (cfg->tab_rep[i] < 0 || cfg->tab_rep[i] > 1000) { delete h; return fail("mn_create: tab_rep entries must be 0..1000"); }

@@ -118,3 +118,50 @@ def test_exploration_policy_numpy_in_numpy_out():
     greedy = mb.ExplorationPolicy(args, test=True)
     a, r = greedy.choose_next_actions(pi, rho, 6)
     assert np.array_equal(a.argmax(1), pi.argmax(1)) and np.array_equal(r.argmax(1), rho.argmax(1))
+
+
+def test_emulator_runner_loop_equals_the_batched_macro_step():
+    """EmulatorRunner._run (emulator_runner.py:19-42 restated in process, one AtariEmulator.next() at a time) against
+    Runners.update_environments() (every environment at once on the GPU) on twin pools: the same states, rewards and
+    terminals after every instruction, in-loop resets included."""
+    import queue
+    import manette_b200 as mb
+    game, n, k, steps = "breakout", 6, 11, 14
+    args = util.args_for(game, max_repetition=10, nb_choices=k, single_life_episodes=True)
+    mb.release_pools()
+    creator = mb.EnvironmentCreator(args)
+    explo = mb.ExplorationPolicy(args)
+    # pool A: driven through Runners
+    emus_a = [creator.create_environment(i) for i in range(n)]
+    states_a = np.asarray([e.get_initial_state() for e in emus_a], dtype=np.uint8)
+    var_a = [states_a, np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros((n, creator.num_actions), np.float32),
+             np.zeros((n, k), np.float32)]
+    runners = mb.Runners(explo.tab_rep, mb.EmulatorRunner, emus_a, 2, var_a)
+    runners.start()
+    sv = runners.get_shared_variables()
+    # pool B: its own device pool, driven by one in-process EmulatorRunner
+    pool_b = mb.DevicePool([(game, rom_bytes(game), n)], tab_rep=explo.tab_rep, single_life_episodes=True)
+    emus_b = mb.emulators_for_pool(pool_b)
+    var_b = [np.asarray([e.get_initial_state() for e in emus_b], dtype=np.uint8), np.zeros(n, np.float32), np.zeros(n, np.float32),
+             np.zeros((n, creator.num_actions), np.float32), np.zeros((n, k), np.float32)]
+    assert np.array_equal(var_b[0], states_a)
+    q, barrier = queue.Queue(), queue.Queue()
+    worker = mb.EmulatorRunner(explo.tab_rep, 0, emus_b, var_b, q, barrier)
+    acts, reps = util.schedule(41, steps, n, creator.num_actions, k)
+    terminals = 0
+    for t in range(steps):
+        for z in range(n):
+            sv[3][z] = var_b[3][z] = np.eye(creator.num_actions)[acts[t][z]]
+            sv[4][z] = var_b[4][z] = np.eye(k)[reps[t][z]]
+        runners.update_environments()
+        runners.wait_updated()
+        q.put(True); q.put(None)
+        worker._run()                                   # one instruction, then the stop marker
+        assert barrier.get_nowait() is True
+        assert np.array_equal(var_b[1], sv[1]) and np.array_equal(var_b[2], sv[2]), t
+        assert np.array_equal(var_b[0], sv[0]), t
+        terminals += int(sv[2].sum())
+    assert terminals > 0
+    runners.stop()
+    pool_b.close()
+    mb.release_pools()
