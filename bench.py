@@ -73,6 +73,18 @@ def load_counters(path):
     return doc, None
 
 
+def pack_episode_stats(st):
+    """K6's running statistics (count, sum of returns, sum of lengths, min return, max return, global steps) as the two
+    vectors the ranks all-reduce: one with SUM, one with MAX (the minimum travels negated)."""
+    import torch
+    return torch.stack([st[0], st[1], st[2], st[5]]), torch.stack([-st[3], st[4]])
+
+
+def unpack_episode_stats(stat_sum, stat_max):
+    """(count, sum of returns, sum of lengths, min, max, global steps) of all ranks from the reduced vectors."""
+    return (float(stat_sum[0]), float(stat_sum[1]), float(stat_sum[2]), -float(stat_max[0]), float(stat_max[1]), float(stat_sum[3]))
+
+
 def k3_bytes(depth):
     return 2 * 210 * 160 + 84 * 84 * depth
 
@@ -422,9 +434,9 @@ def main():
         ea.record(stream)
         dist.all_reduce(grad)
         grad.div_(world)
-        st = rollout.stats                                   # count, sum reward, sum length, min, max, global_step
-        stat_sum.copy_(torch.stack([st[0], st[1], st[2], st[5]]))
-        stat_max.copy_(torch.stack([-st[3], st[4]]))
+        ps, pm = pack_episode_stats(rollout.stats)           # count, sum reward, sum length, min, max, global_step
+        stat_sum.copy_(ps)
+        stat_max.copy_(pm)
         dist.all_reduce(stat_sum)
         dist.all_reduce(stat_max, op=dist.ReduceOp.MAX)
         eb.record(stream)

@@ -39,8 +39,13 @@ def _worker(rank, world, port, out):
     dist.all_reduce(grad)
     gathered = [None] * world
     dist.all_gather_object(gathered, seeds.tolist())
+    # the episode statistics of bench.py's collective step: count, sum return, sum length, min, max, global steps
+    st = torch.tensor([3.0 + rank, 10.0 * (rank + 1), 100.0, -5.0 + 7 * rank, 20.0 - 30 * rank, 640.0], dtype=torch.float64)
+    ps, pm = bench.pack_episode_stats(st)
+    dist.all_reduce(ps)
+    dist.all_reduce(pm, op=dist.ReduceOp.MAX)
     if rank == 0:
-        out.put((float(mx[0]), float(sm[1]), float(grad[0]), gathered))
+        out.put((float(mx[0]), float(sm[1]), float(grad[0]), gathered, bench.unpack_episode_stats(ps, pm)))
     dist.destroy_process_group()
 
 
@@ -52,7 +57,7 @@ def test_two_rank_sharding_and_reduction():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    ms_max, frames_all, g, seeds = q.get(timeout=120)
+    ms_max, frames_all, g, seeds, stats = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -60,6 +65,28 @@ def test_two_rank_sharding_and_reduction():
     flat = [s for part in seeds for s in part]
     assert flat == [3 * (i + 1) for i in range(16)]          # global, gap-free, no overlap
     assert frames_all / (ms_max / 1000.0) == 3000.0 / 0.110  # whole-job frames / max-over-ranks time
+    # episodes 3 + 4, returns 10 + 20, lengths 100 + 100, min(-5, 2), max(20, -10), global steps 640 + 640
+    assert stats == (7.0, 30.0, 200.0, -5.0, 20.0, 1280.0)
+
+
+def test_stale_profile_counters_are_refused(tmp_path):
+    """The ncu-derived counters bench.py quotes carry the hash of the sources they were profiled on: another hash (or no
+    file) gives no numbers and says why; the committed ones belong to the committed sources."""
+    import json
+    from manette_b200 import build as mb_build
+    doc, why = bench.load_counters(str(tmp_path / "nothing.json"))
+    assert doc is None and "no " in why
+    stale = tmp_path / "stale.json"
+    stale.write_text(json.dumps({"source_hash": "0" * 16, "warp_inst_per_next": 1.0, "dram_bytes_per_next": 1.0, "launches": []}))
+    doc, why = bench.load_counters(str(stale))
+    assert doc is None and why.startswith("stale")
+    good = tmp_path / "good.json"
+    good.write_text(json.dumps({"source_hash": mb_build.source_hash(), "warp_inst_per_next": 2.0, "dram_bytes_per_next": 3.0, "launches": []}))
+    doc, why = bench.load_counters(str(good))
+    assert why is None and doc["warp_inst_per_next"] == 2.0
+    for path in (bench.ROUND_COUNTERS, bench.K3_COUNTERS):
+        doc, why = bench.load_counters(path)
+        assert why is None, why          # profiles/ was regenerated after the last change to csrc/
 
 
 def test_split_games_covers_every_env():
