@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
-for hh in 12 14; do for s in 4 8; do
-  echo "fifo_high=$hh slack=$s"; MN_FIFO_HIGH=$hh MN_SYNC_SLACK=$s timeout 300 python tools/profile_step.py --envs 16384 --decorrelate 24 --steps 4 2>&1 | tail -1 | cut -c1-110
-done; done
+python -c "import __graft_entry__ as g; g.build(); g.smoke()" 2>&1 | tail -2
+python bench.py > gpurun_out/bench_default_final.json 2> gpurun_out/bench_default_final.err; python -c "
+import json; d=json.loads(open('gpurun_out/bench_default_final.json').read().strip().splitlines()[-1])
+print(int(d['value']), int(d['e2e']['value']), d['steps'], d['warmup'], d['roofline']['frac'], d['roofline']['counters']['source_hash'], d['clocks'], d['cpu_baseline']['value'])"
