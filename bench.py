@@ -534,7 +534,7 @@ def main():
     # and misses -- 80 emulated frames on the step's critical path -- where the memo cannot help)
     steady = None
     if args.steady_state > 0:
-        m0 = pool.memo_stats()
+        m0, l10 = pool.memo_stats(), pool.memo_level1_hits()
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steady_state + 1)]
         term = torch.zeros((), device=dev)
         with torch.cuda.stream(stream):
@@ -552,7 +552,8 @@ def main():
         steady = {"steps": args.steady_state, "ms_p50": float(np.percentile(lat, 50)), "ms_p99": float(np.percentile(lat, 99)),
                   "ms_max": float(lat.max()), "p99_over_p50": float(np.percentile(lat, 99) / np.percentile(lat, 50)),
                   "episodes_ended": float(term), "random_start": bool(args.random_start),
-                  "resets_restored_from_memo": int(m1[0] - m0[0]), "resets_emulated": int(m1[1] - m0[1])}
+                  "resets_restored_from_memo": int(m1[0] - m0[0]), "resets_emulated": int(m1[1] - m0[1]),
+                  "of_which_only_the_start_frames": int(pool.memo_level1_hits() - l10)}
 
     # ---- end-to-end leg through Runners with host arrays
     e2e = None
@@ -600,7 +601,9 @@ def main():
         e2e = {"value": fr_all / dt_max, "unit": "frames/s",
                "h2d_bytes_per_step": int(world * n * (pool.num_actions + pool.nb_choices) * 4),
                "d2h_bytes_per_step": int(world * n * (84 * 84 * 4 * pool.depth + 8)), "ms_per_step": 1000.0 * dt_max / args.steps,
-               "api": "Runners.update_environments()/wait_updated() with pinned host arrays"}
+               "api": "Runners.update_environments()/wait_updated() with pinned host arrays",
+               "states_path": "the pool's kernels write each env's new state into the pinned host array as soon as the env has "
+                              "finished its repeats (mn_set_host_states): the D2H bytes cross PCIe underneath the remaining rounds"}
         runners.stop()
 
     # ---- second end-to-end figure: mn_step_host, the single C call INTEGRATION.md shows a maintainer, with PAGEABLE

@@ -82,6 +82,12 @@ int mn_reset_all(mn_handle h, void* stream);
 int mn_step_async(mn_handle h, int use_indices, void* stream);
 /* Runners.wait_updated(): blocks until the macro step finished; reports sticky CUDA / emulator errors */
 int mn_wait(mn_handle h);
+/* The reference's shared `states` array lives in host memory (runners.py:30, paac.py:97).  Register the caller's
+ * PAGE-LOCKED copy of it (N,84,84,4*depth) u8 and every later mn_reset_all / mn_step_async / mn_env_* writes the states
+ * it publishes into that array as well as into the device buffer -- during the step, as environments finish their
+ * repeats, not in one copy after it.  The array is complete when mn_wait returns.  NULL unregisters.  The memory must
+ * stay allocated while registered.  Blocks until a step in flight has finished. */
+int mn_set_host_states(mn_handle h, uint8_t* states_pinned_host);
 /* same macro step with HOST arrays, copies inside: actions (N,A) f32, repetitions (N,K) f32 in;
  * states (N,84,84,4*depth) u8, rewards (N,) f32, terminals (N,) f32 out.  Blocking. */
 int mn_step_host(mn_handle h, const float* actions_host, const float* repetitions_host, uint8_t* states_host,
@@ -98,6 +104,7 @@ int mn_get_cpu_state(mn_handle h, int env, int32_t* out10_host);            /* A
 int mn_get_lives(mn_handle h, int env, int* lives, int* game_over, int* frame_number);
 int mn_total_next_calls(mn_handle h, int64_t* out);                         /* since creation */
 int mn_memo_stats(mn_handle h, int64_t* out3);          /* get_initial_state() calls restored from the memo, emulated, stored */
+int mn_memo_level1_hits(mn_handle h, int64_t* out);     /* of the emulated ones: restored to the end of the reset unit (only the 4 start frames emulated) */
 int mn_total_instructions(mn_handle h, int64_t* out);   /* emulated 6502 instructions since creation */
 int mn_redo_count(mn_handle h, int64_t* out);   /* units re-run with every frame drawn (exact fallback), since creation */
 int mn_palette(uint8_t* gray128_host, uint8_t* rgb128x3_host);

@@ -52,6 +52,7 @@ SYMBOLS = {
     "mn_reset_all": (_I, [_VP, _VP]),
     "mn_step_async": (_I, [_VP, _I, _VP]),
     "mn_wait": (_I, [_VP]),
+    "mn_set_host_states": (_I, [_VP, _VP]),
     "mn_step_host": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "mn_env_reset": (_I, [_VP, _I, _VP]),
     "mn_env_next": (_I, [_VP, _I, _I, C.POINTER(_F), C.POINTER(_I), _VP]),
@@ -61,6 +62,7 @@ SYMBOLS = {
     "mn_get_lives": (_I, [_VP, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "mn_total_next_calls": (_I, [_VP, C.POINTER(C.c_int64)]),
     "mn_memo_stats": (_I, [_VP, C.POINTER(C.c_int64)]),
+    "mn_memo_level1_hits": (_I, [_VP, C.POINTER(C.c_int64)]),
     "mn_total_instructions": (_I, [_VP, C.POINTER(C.c_int64)]),
     "mn_redo_count": (_I, [_VP, C.POINTER(C.c_int64)]),
     "mn_palette": (_I, [_VP, _VP]),

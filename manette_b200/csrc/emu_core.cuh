@@ -163,7 +163,9 @@ struct Ctx {
 // renders the other.  A hand-off (tia_handoff) publishes the filled buffer through a four-word mailbox per env --
 // per LANE, so that a lane inside a divergent slow path (a collision-latch read) can hand off and wait on its own.
 #define MN_FIFO_BUF 16    // entries per buffer (a power of two)
-#define MN_FIFO_NBUF 4    // buffers per env (a power of two): the 6502 side may run up to NBUF - 1 hand-offs ahead
+#ifndef MN_FIFO_NBUF
+#define MN_FIFO_NBUF 8    // buffers per env (a power of two): the 6502 side may run up to NBUF - 1 hand-offs ahead
+#endif                    // (measured, Ms Pacman 16,384 envs: 2 / 4 / 8 buffers = 16 / 7.4 / 6.4 % of the lanes' time waiting for one)
 #define MN_FIFO_CAP 15    // usable entries: the fill count must stay below MN_FIFO_BUF
 #define MN_FIFO_HIGH 12   // a warp hands off when one of its envs has this many pending writes
 #define MN_MBOX (MN_FIFO_NBUF * MN_FIFO_BUF)

@@ -103,6 +103,7 @@ struct PoolDev {             // kernel argument block (by value)
   uint8_t* frames;           // (N,2,210,160)
   uint8_t* ring;             // (N,4,84,84,D)
   uint8_t* states;           // (N,84,84,4D)
+  uint8_t* states_host;      // the caller's pinned host copy of `states` as the device sees it (mn_set_host_states), or null
   float *rewards, *terminals, *actions, *repetitions;
   int32_t *action_idx, *repetition_idx, *next_calls;
   // per-step bookkeeping
@@ -113,13 +114,15 @@ struct PoolDev {             // kernel argument block (by value)
   uint8_t* push_info;        // bits 0-1 ring slot, bits 2-3 pool mode (0 both, 1 buffer 0 only, 2 buffer 1 only)
   uint32_t* episode;         // episodes started so far (start no-op schedule)
   uint8_t* env_game;
-  int32_t* lists;            // 3 x N : work list A, work list B, reset list   (regions per game = env id ranges)
-  int32_t* counts;           // 3 x MN_MAX_GAMES
+  int32_t* lists;            // 4 x N : work list A, work list B, reset list, level-1 memo hits   (regions per game = env id ranges)
+  int32_t* counts;           // 4 x MN_MAX_GAMES
   int32_t* error;            // sticky: 1 = episode over right after reset (atari_emulator.py:108-109)
   unsigned long long* total_next;
   // reset memoisation (see k_reset_prepare)
   uint8_t* memo;             // n_games x 75 timer seeds x memo_slots entries of memo_entry_bytes
   int32_t memo_entry_bytes, memo_enabled, memo_slots;
+  // level 1 of the memo: the machine right after the reset UNIT (before the four start frames), see k_reset_prepare
+  uint8_t* memo1; int32_t memo1_entry_bytes; int32_t* memo1_busy;
   uint32_t* reset_rnd;       // (N,) the RNG draw that seeds the RIOT timer of the reset in flight
   uint8_t* pre_ram;          // (N,128) RIOT RAM as it was before the reset in flight (memo key of a miss)
   int32_t* memo_hit;         // (N,) entry index the reset in flight is restored from
@@ -227,9 +230,11 @@ __device__ __forceinline__ void picture_warp(Ctx& c, unsigned wmask, int diag) {
     if (!__any_sync(wmask, req)) {
       if (__all_sync(wmask, fin)) break;
       // An idle partner shares its SM sub-partition's issue slots with the 6502 warp it serves: poll rarely.  Hand-offs
-      // come ~50 us apart and only two kinds are waited for (collision-latch reads, the end of a unit).  ncu showed a
-      // single __nanosleep per poll to return after a few tens of ns -- the poll loop then issued a third of all the
-      // kernel's instructions -- so the wait is a counted run of them that grows while nothing arrives (<~ 1 us).
+      // come ~50 us apart and only two kinds are waited for (collision-latch reads, the end of a unit).  Measured alone
+      // (tools/sleep_probe.cu): __nanosleep(20) = 115 cycles, (200) = 502, (512...1000) = 2,008 -- so the counted run below
+      // sleeps 1 us after the first empty poll and up to 6 us once nothing has arrived for a while.  (The per-line
+      // instruction counts ncu attributes to this loop are inflated: its instrumented passes stretch the kernel, not the
+      // sleeps.)  A finer first back-off (8 polls of __nanosleep(20)) measured no gain, Pong included.
       if (idle < 24) idle += 4;
 #pragma unroll 1
       for (int k = 0; k < idle; ++k) __nanosleep(200);
@@ -418,6 +423,8 @@ __global__ void __launch_bounds__(MN_THREADS, 1) k_round(PoolDev p, int mode, in
           p.rep_left[e] = left - 1;
           const int k = atomicAdd(&p.counts[out * MN_MAX_GAMES + gi], 1);
           p.lists[size_t(out) * p.n_envs + G.env0 + k] = e;
+        } else {
+          p.rep_left[e] = -p.next_calls[e];   // done, not terminal: -(round + 1) tells k_emit_early which round it was
         }
       }
     }
@@ -477,8 +484,33 @@ __global__ void k_warm_end(PoolDev p, int pass) {
   }
 }
 
-// Every env on the reset list draws the RNG value that seeds its RIOT timer (ALE's System::reset) and looks for
-// a memo entry it may be restored from: hits go to list 0, misses (to be emulated with the probe) to list 1.
+// one bucket of a memo table: the entry whose key (start no-ops, values of its dependence bytes) the env matches, or -1
+__device__ __forceinline__ int memo_find(const uint8_t* table, int entry_bytes, int slots, size_t bucket, int noops,
+                                         const unsigned long long* ram8) {
+  for (int sl = 0; sl < slots; ++sl) {
+    const MemoHdr* m = reinterpret_cast<const MemoHdr*>(table + (bucket + sl) * size_t(entry_bytes));
+    if (*reinterpret_cast<const volatile int32_t*>(&m->state) != 2) continue;
+    bool same = (m->noops == noops);
+    if (m->dep_lo | m->dep_hi) {
+      const unsigned long long* want = reinterpret_cast<const unsigned long long*>(m->dep_val);
+      for (int w = 0; w < 16 && same; ++w) {
+        const unsigned long long bits = ((w < 8) ? m->dep_lo : m->dep_hi) >> ((w & 7) * 8);
+        unsigned long long mask = 0;   // one 0xFF per dependent byte of this 8-byte word
+        for (int b = 0; b < 8; ++b) if ((bits >> b) & 1ull) mask |= 0xFFull << (8 * b);
+        same = ((ram8[w] ^ want[w]) & mask) == 0ull;
+      }
+    }
+    if (same) return int(bucket + sl);
+  }
+  return -1;
+}
+
+// Every env on the reset list draws the RNG value that seeds its RIOT timer (ALE's System::reset) and looks for a memo
+// entry it may be restored from.  Two levels: (2) the whole of get_initial_state() -- hits go to list 0 and are restored by
+// copy; (1) the reset UNIT alone (reset_game and the start no-ops, 64+ of the 80 frames) -- hits go to list 3, are restored
+// to that point and only emulate the four start frames.  Level 1 exists for games whose start frames read RAM the reset
+// unit does not (Yars' Revenge: a pseudo-random byte, so level 2 almost never recurs, while the reset unit depends on
+// two bytes with a handful of values).  Misses (list 1) are emulated with the probe and stored at both levels.
 __global__ void k_reset_prepare(PoolDev p) {
   const int pos = blockIdx.x * blockDim.x + threadIdx.x;
   if (pos >= p.n_envs) return;
@@ -488,34 +520,25 @@ __global__ void k_reset_prepare(PoolDev p) {
   const int e = p.lists[size_t(2) * p.n_envs + pos];
   const uint32_t rnd = rng_next(p.env[e].rng);
   p.reset_rnd[e] = rnd;
-  int hit = -1;
+  int hit = -1, which = 1;
   const unsigned long long* ram8 = reinterpret_cast<const unsigned long long*>(p.ram + size_t(e) * 128);
   // the start no-ops the reset will run (k_round<RESET> computes the same): part of the key under random_start
   const int noops = p.random_start ? int(start_noops(uint32_t(p.seed), uint32_t(p.env_id_offset + e), p.episode[e])) : 0;
   if (p.memo_enabled) {
     const size_t bucket = (size_t(gi) * MN_TIMER_SEEDS + rnd % MN_TIMER_SEEDS) * size_t(p.memo_slots);
-    for (int sl = 0; sl < p.memo_slots && hit < 0; ++sl) {
-      const MemoHdr* m = reinterpret_cast<const MemoHdr*>(p.memo + (bucket + sl) * size_t(p.memo_entry_bytes));
-      if (*reinterpret_cast<const volatile int32_t*>(&m->state) != 2) continue;
-      bool same = (m->noops == noops);
-      if (m->dep_lo | m->dep_hi) {
-        const unsigned long long* want = reinterpret_cast<const unsigned long long*>(m->dep_val);
-        for (int w = 0; w < 16 && same; ++w) {
-          const unsigned long long bits = ((w < 8) ? m->dep_lo : m->dep_hi) >> ((w & 7) * 8);
-          unsigned long long mask = 0;   // one 0xFF per dependent byte of this 8-byte word
-          for (int b = 0; b < 8; ++b) if ((bits >> b) & 1ull) mask |= 0xFFull << (8 * b);
-          same = ((ram8[w] ^ want[w]) & mask) == 0ull;
-        }
-      }
-      if (same) hit = int(bucket + sl);
+    hit = memo_find(p.memo, p.memo_entry_bytes, p.memo_slots, bucket, noops, ram8);
+    if (hit >= 0) which = 0;
+    else {
+      hit = memo_find(p.memo1, p.memo1_entry_bytes, p.memo_slots, bucket, noops, ram8);
+      if (hit >= 0) which = 3;
     }
   }
   p.memo_hit[e] = hit;
-  const int which = (hit >= 0) ? 0 : 1;
   const int k = atomicAdd(&p.counts[which * MN_MAX_GAMES + gi], 1);
   p.lists[size_t(which) * p.n_envs + p.games[gi].env0 + k] = e;
-  atomicAdd(p.memo_stats + which, 1ull);
-  if (hit < 0) {
+  atomicAdd(p.memo_stats + (which == 0 ? 0 : 1), 1ull);
+  if (which == 3) atomicAdd(p.memo_stats + 3, 1ull);
+  if (which != 0) {
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(p.pre_ram + size_t(e) * 128);
     for (int w = 0; w < 16; ++w) dst[w] = ram8[w];
   }
@@ -558,9 +581,48 @@ __global__ void __launch_bounds__(256) k_reset_restore(PoolDev p) {
   }
 }
 
-// after the probe emulated the misses (list 1): store what it found
-template <int D>
+// level-1 hits (list 3): the machine, RAM and frame buffers as the reset unit left them, the probe's sets as they stood
+// there; the envs then join list 1 for the four start frames (and are stored at level 2 like the emulated ones)
+__global__ void __launch_bounds__(256) k_reset_restore_l1(PoolDev p) {
+  const int pos = blockIdx.x;
+  int gi = 0;
+  while (gi + 1 < p.n_games && pos >= p.games[gi + 1].env0) ++gi;
+  if (pos - p.games[gi].env0 >= p.counts[3 * MN_MAX_GAMES + gi]) return;
+  const int e = p.lists[size_t(3) * p.n_envs + pos];
+  const uint8_t* entry = p.memo1 + size_t(p.memo_hit[e]) * size_t(p.memo1_entry_bytes);
+  const MemoHdr* m = reinterpret_cast<const MemoHdr*>(entry);
+  const uint4* src = reinterpret_cast<const uint4*>(entry + memo_hdr_bytes());
+  uint4* fb = reinterpret_cast<uint4*>(p.frames + size_t(e) * (2 * MN_FRAME_BYTES));
+  for (int i = threadIdx.x; i < 2 * MN_FRAME_BYTES / 16; i += blockDim.x) fb[i] = src[i];
+  if (threadIdx.x < 128) {
+    const int j = threadIdx.x;
+    const bool def = (((j & 64) ? m->def_hi : m->def_lo) >> (j & 63)) & 1ull;
+    if (def) p.ram[size_t(e) * 128 + j] = m->ram[j];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    EnvState own = p.env[e];
+    EnvState s = m->env;
+    for (int i = 0; i < 4; ++i) s.rng[i] = own.rng[i];
+    for (int i = 0; i < 2 * m->n_acts; ++i) rng_advance(s.rng);     // the start no-ops are act() calls
+    s.frame_number = own.frame_number + m->n_acts;
+    s.ring_head = own.ring_head;
+    p.env[e] = s;
+    p.episode[e] += 1;
+    unsigned long long* t = p.track + size_t(e) * 5;
+    t[0] = m->def_lo; t[1] = m->def_hi; t[2] = m->dep_lo; t[3] = m->dep_hi; t[4] = (m->dep_lo | m->dep_hi) ? 1ull : 0ull;
+    const int k = atomicAdd(&p.counts[1 * MN_MAX_GAMES + gi], 1);
+    p.lists[size_t(1) * p.n_envs + p.games[gi].env0 + k] = e;
+  }
+}
+
+// after the probe emulated the misses (list 1): store what it found.  LEVEL 2: after the four start frames (machine, RAM,
+// frame buffers, ring planes); LEVEL 1: right after the reset unit (machine, RAM, frame buffers)
+template <int D, int LEVEL>
 __global__ void __launch_bounds__(256) k_memo_insert(PoolDev p) {
+  uint8_t* const table = (LEVEL == 2) ? p.memo : p.memo1;
+  const int entry_bytes = (LEVEL == 2) ? p.memo_entry_bytes : p.memo1_entry_bytes;
+  int32_t* const busy = (LEVEL == 2) ? p.memo_busy : p.memo1_busy;
   __shared__ int s_slot;
   const int pos = blockIdx.x;
   int gi = 0;
@@ -574,12 +636,12 @@ __global__ void __launch_bounds__(256) k_memo_insert(PoolDev p) {
   if (threadIdx.x == 0) {
     int slot = -1;
     // the RAM scrape must only have seen written bytes; one insertion per bucket at a time
-    if (!(t[4] & 2ull) && atomicCAS(&p.memo_busy[bucket_id], 0, 1) == 0) {
+    if (!(t[4] & 2ull) && atomicCAS(&busy[bucket_id], 0, 1) == 0) {
       const size_t bucket = size_t(bucket_id) * size_t(p.memo_slots);
       const uint8_t* pre = p.pre_ram + size_t(e) * 128;
       bool known = false;
       for (int sl = 0; sl < p.memo_slots && !known; ++sl) {   // stored since k_reset_prepare looked?
-        const MemoHdr* m = reinterpret_cast<const MemoHdr*>(p.memo + (bucket + sl) * size_t(p.memo_entry_bytes));
+        const MemoHdr* m = reinterpret_cast<const MemoHdr*>(table + (bucket + sl) * size_t(entry_bytes));
         if (*reinterpret_cast<const volatile int32_t*>(&m->state) != 2) continue;
         bool same = (m->noops == my_noops);
         for (int j = 0; j < 128 && same; ++j)
@@ -587,23 +649,23 @@ __global__ void __launch_bounds__(256) k_memo_insert(PoolDev p) {
         known = same;
       }
       for (int sl = 0; sl < p.memo_slots && !known && slot < 0; ++sl) {
-        MemoHdr* m = reinterpret_cast<MemoHdr*>(p.memo + (bucket + sl) * size_t(p.memo_entry_bytes));
+        MemoHdr* m = reinterpret_cast<MemoHdr*>(table + (bucket + sl) * size_t(entry_bytes));
         if (atomicCAS(&m->state, 0, 1) == 0) slot = int(bucket + sl);
       }
-      if (slot < 0) atomicExch(&p.memo_busy[bucket_id], 0);
+      if (slot < 0) atomicExch(&busy[bucket_id], 0);
     }
     s_slot = slot;
   }
   __syncthreads();
   if (s_slot < 0) return;
-  uint8_t* entry = p.memo + size_t(s_slot) * size_t(p.memo_entry_bytes);
+  uint8_t* entry = table + size_t(s_slot) * size_t(entry_bytes);
   MemoHdr* m = reinterpret_cast<MemoHdr*>(entry);
   uint4* dst = reinterpret_cast<uint4*>(entry + memo_hdr_bytes());
   const uint4* fb = reinterpret_cast<const uint4*>(p.frames + size_t(e) * (2 * MN_FRAME_BYTES));
   for (int i = threadIdx.x; i < 2 * MN_FRAME_BYTES / 16; i += blockDim.x) dst[i] = fb[i];
   dst += 2 * MN_FRAME_BYTES / 16;
   const int head = p.env[e].ring_head;
-  for (int k = 0; k < MN_STACK; ++k) {
+  if (LEVEL == 2) for (int k = 0; k < MN_STACK; ++k) {
     const uint4* src = reinterpret_cast<const uint4*>(p.ring + (size_t(e) * MN_STACK + ((head + k) & 3)) * (MN_PLANE * D));
     for (int i = threadIdx.x; i < MN_PLANE * D / 16; i += blockDim.x) dst[size_t(k) * (MN_PLANE * D / 16) + i] = src[i];
   }
@@ -611,10 +673,10 @@ __global__ void __launch_bounds__(256) k_memo_insert(PoolDev p) {
   if (threadIdx.x == 0) {
     m->def_lo = t[0]; m->def_hi = t[1]; m->dep_lo = t[2]; m->dep_hi = t[3];
     m->env = p.env[e];
-    m->n_acts = MN_STACK * MN_ACTION_REPEAT + my_noops;
+    m->n_acts = (LEVEL == 2 ? MN_STACK * MN_ACTION_REPEAT : 0) + my_noops;
     m->noops = my_noops;
     m->ring_head = uint32_t(head);
-    atomicAdd(p.memo_stats + 2, 1ull);
+    if (LEVEL == 2) atomicAdd(p.memo_stats + 2, 1ull);
   }
   __threadfence();
   __syncthreads();
@@ -622,7 +684,7 @@ __global__ void __launch_bounds__(256) k_memo_insert(PoolDev p) {
     __threadfence();
     *reinterpret_cast<volatile int32_t*>(&m->state) = 2;
     __threadfence();
-    atomicExch(&p.memo_busy[bucket_id], 0);
+    atomicExch(&busy[bucket_id], 0);
   }
 }
 
@@ -724,13 +786,17 @@ __global__ void __launch_bounds__(256) k_preprocess(const uint8_t* __restrict__ 
 // `hist_slot` >= 0: also the learner's observation history (PAACLearner.update_memory, paac.py:79-83): the new state
 // goes into ring slot `hist_slot` of the env's H-deep history; an env whose episode ended in this step has its whole
 // history zeroed AFTER that -- newest entry included -- exactly as paac.py:200-201 does.
+//
+// With a host copy registered (mn_set_host_states) every 16-byte store is made twice: into `states` in HBM and, through the
+// mapped pinned allocation, straight into the caller's host array -- so the states of environments that are done early
+// in a macro step cross PCIe while the remaining FiGAR rounds still run (k_emit_early) instead of in one 462 MB copy
+// at the end of the step.
 template <int D>
-__global__ void __launch_bounds__(256) k_emit(PoolDev p, int env_lo, int env_hi, int publish, int hist_slot) {
-  const int e = env_lo + blockIdx.x;
-  if (e >= env_hi) return;
+__device__ __forceinline__ void emit_env(const PoolDev& p, int e, int publish, int hist_slot) {
   const int head = p.env[e].ring_head;
   const uint8_t* ring = p.ring + size_t(e) * MN_STACK * (MN_PLANE * D);
   uint4* out = reinterpret_cast<uint4*>(p.states + size_t(e) * (MN_PLANE * D * MN_STACK));
+  uint4* hostout = p.states_host ? reinterpret_cast<uint4*>(p.states_host + size_t(e) * (MN_PLANE * D * MN_STACK)) : nullptr;
   const bool hist = hist_slot >= 0 && p.history != nullptr;
   const bool wipe = hist && publish && p.over[e];
   const size_t state_q = size_t(MN_PLANE) * D * MN_STACK / 16;   // uint4 per stacked state
@@ -752,6 +818,7 @@ __global__ void __launch_bounds__(256) k_emit(PoolDev p, int env_lo, int env_hi,
       o.x = __byte_perm(ab_lo, cd_lo, 0x5410); o.y = __byte_perm(ab_lo, cd_lo, 0x7632);
       o.z = __byte_perm(ab_hi, cd_hi, 0x5410); o.w = __byte_perm(ab_hi, cd_hi, 0x7632);
       out[q] = o;
+      if (hostout) hostout[q] = o;
       if (hist && !wipe) hout[q] = o;
     } else {
       // 4 pixels x (3 colours x 4 steps) = 48 bytes = 3 x uint4
@@ -769,6 +836,7 @@ __global__ void __launch_bounds__(256) k_emit(PoolDev p, int env_lo, int env_hi,
                           (uint32_t(bytes[2][px * 3 + d]) << 16) | (uint32_t(bytes[3][px * 3 + d]) << 24);
       const uint4 o0 = make_uint4(w[0], w[1], w[2], w[3]), o1 = make_uint4(w[4], w[5], w[6], w[7]), o2 = make_uint4(w[8], w[9], w[10], w[11]);
       out[3 * q + 0] = o0; out[3 * q + 1] = o1; out[3 * q + 2] = o2;
+      if (hostout) { hostout[3 * q + 0] = o0; hostout[3 * q + 1] = o1; hostout[3 * q + 2] = o2; }
       if (hist && !wipe) { hout[3 * q + 0] = o0; hout[3 * q + 1] = o1; hout[3 * q + 2] = o2; }
     }
   }
@@ -780,6 +848,30 @@ __global__ void __launch_bounds__(256) k_emit(PoolDev p, int env_lo, int env_hi,
   if (publish && threadIdx.x == 0) {
     p.rewards[e] = float(p.reward_acc[e]);
     p.terminals[e] = p.over[e] ? 1.0f : 0.0f;
+  }
+}
+
+// An env whose repeats ran out in FiGAR round r < `last_tag` - 1 without a terminal (k_round left rep_left = -(r + 1)) is
+// final from then on -- no later round and no reset touches it -- and is published by k_emit_early<r>; k_emit publishes
+// the rest at the end of the step (last round's, and the terminal ones after their get_initial_state()).
+__device__ __forceinline__ bool emitted_early(const PoolDev& p, int e, int last_tag) {
+  const int left = p.rep_left[e];
+  return !p.over[e] && left < 0 && -left < last_tag;
+}
+// one block per env of [env_lo, env_hi); `last_tag` = 0: every env, else only those k_emit_early did not publish
+template <int D>
+__global__ void __launch_bounds__(256) k_emit(PoolDev p, int env_lo, int env_hi, int publish, int hist_slot, int last_tag) {
+  const int e = env_lo + blockIdx.x;
+  if (e >= env_hi) return;
+  if (last_tag > 0 && emitted_early(p, e, last_tag)) return;
+  emit_env<D>(p, e, publish, hist_slot);
+}
+// runs on the pool's side stream beside the next FiGAR round: the envs that finished in the round tagged `tag`
+template <int D>
+__global__ void __launch_bounds__(256) k_emit_early(PoolDev p, int tag, int hist_slot) {
+  for (int e = blockIdx.x; e < p.n_envs; e += gridDim.x) {
+    if (p.over[e] || p.rep_left[e] != -tag) continue;   // block-uniform
+    emit_env<D>(p, e, 1, hist_slot);
   }
 }
 
@@ -965,6 +1057,10 @@ struct mn_pool {
   int round_grid;
   cudaEvent_t done;
   bool pending;
+  // early publication (k_emit_early): a side stream, one event per FiGAR round, the join
+  cudaStream_t side;
+  cudaEvent_t ev_round[32], ev_side;
+  int early_emit, early_grid;
   int64_t launches;
   std::vector<void*> allocs;
   uint8_t* pin_ram;
@@ -1049,6 +1145,9 @@ int mn_destroy(mn_handle h) {
   for (void* p : h->allocs) cudaFree(p);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->done) cudaEventDestroy(h->done);
+  if (h->ev_side) cudaEventDestroy(h->ev_side);
+  for (cudaEvent_t e : h->ev_round) if (e) cudaEventDestroy(e);
+  if (h->side) cudaStreamDestroy(h->side);
   if (h->err_host) cudaFreeHost(h->err_host);
   delete h;
   return 0;
@@ -1136,9 +1235,20 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
   h->round_smem = ((max_rom + 15) & ~size_t(15)) + sizeof(Tables) +
                   size_t(MN_WARPS_PER_BLOCK) * slots * (MN_CORE_WORDS * 4 + MN_RAM_PITCH + MN_FIFO_WORDS * 4);
   if (h->round_smem > size_t(prop.sharedMemPerBlockOptin)) { delete h; return fail("mn_create: shared memory budget exceeded"); }
+  // A pool that fits one block per SM must GET one block per SM: below half of the SM's shared memory two blocks fit one
+  // SM, and whenever the block scheduler finds some SMs busy at launch (k_emit_early runs beside the rounds) it doubles
+  // blocks up on the others -- measured: every round 36 % slower, whatever the size of the other kernel.  Asking for
+  // more than half makes the placement independent of what else is resident.
+  if (blk <= prop.multiProcessorCount) {
+    const size_t more_than_half = size_t(prop.sharedMemPerMultiprocessor) / 2 + 1024;
+    if (h->round_smem < more_than_half && more_than_half <= size_t(prop.sharedMemPerBlockOptin)) h->round_smem = more_than_half;
+  }
   // the attribute belongs to the function, not to this pool: several pools with different needs may coexist
   CU(cudaFuncSetAttribute(k_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(prop.sharedMemPerBlockOptin)));
   CU(cudaFuncSetAttribute(k_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(prop.sharedMemPerBlockOptin)));
+  // the side-stream kernel shares SMs with k_round blocks: same carve-out, so no SM has to drain to be reconfigured
+  CU(cudaFuncSetAttribute(k_emit_early<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CU(cudaFuncSetAttribute(k_emit_early<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 
   const size_t N = size_t(n), D = size_t(d.depth);
   uint8_t* roms = nullptr;
@@ -1163,8 +1273,8 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
   rc |= dev_alloc(h, &d.push_info, N);
   rc |= dev_alloc(h, &d.episode, N);
   rc |= dev_alloc(h, &d.env_game, N);
-  rc |= dev_alloc(h, &d.lists, 3 * N);
-  rc |= dev_alloc(h, &d.counts, size_t(3 * MN_MAX_GAMES));
+  rc |= dev_alloc(h, &d.lists, 4 * N);
+  rc |= dev_alloc(h, &d.counts, size_t(4 * MN_MAX_GAMES));
   rc |= dev_alloc(h, &d.error, size_t(1));
   rc |= dev_alloc(h, &d.total_next, size_t(1));
   rc |= dev_alloc(h, &d.redo_count, size_t(1));
@@ -1194,6 +1304,9 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
   rc |= dev_alloc(h, &d.pre_ram, N * 128);
   rc |= dev_alloc(h, &d.memo_hit, N);
   rc |= dev_alloc(h, &d.memo_busy, size_t(d.n_games) * MN_TIMER_SEEDS);
+  d.memo1_entry_bytes = int32_t(memo_hdr_bytes() + 2 * MN_FRAME_BYTES);
+  rc |= dev_alloc(h, &d.memo1, d.memo_enabled ? size_t(d.n_games) * MN_TIMER_SEEDS * size_t(d.memo_slots) * size_t(d.memo1_entry_bytes) : size_t(16));
+  rc |= dev_alloc(h, &d.memo1_busy, size_t(d.n_games) * MN_TIMER_SEEDS);
   rc |= dev_alloc(h, &d.track, N * 5);
   rc |= dev_alloc(h, &d.memo_stats, size_t(4));
   rc |= dev_alloc(h, &h->tables_dev, size_t(1));
@@ -1217,6 +1330,13 @@ int mn_create(const mn_config* cfg, mn_handle* out) {
   }
   memcpy(h->games_host, d.games, sizeof(d.games));
   CU(cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming));
+  CU(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming));
+  for (cudaEvent_t& e : h->ev_round) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  h->early_emit = 1;
+  h->early_grid = 16;   // measured (e2e, 16,384 envs, k frames/s): 8 / 16 / 32 / 74 / 148 / 296 blocks = 747 / 748 / 740 / 738 / 722 / 714 (off: 705): PCIe-bound, must not crowd the rounds
+  if (const char* ev = getenv("MN_EARLY_EMIT")) h->early_emit = atoi(ev) != 0;
+  if (const char* ev = getenv("MN_EARLY_GRID")) { const int v = atoi(ev); if (v >= 1 && v <= 65535) h->early_grid = v; }
   CU(cudaMallocHost(&h->err_host, sizeof(int)));
   *h->err_host = 0;
   // construct every AtariEmulator (atari_emulator.py:18-31): seed, RAM garbage, loadROM's reset
@@ -1277,36 +1397,53 @@ static void launch_round(mn_pool* h, int mode, int in, int out, cudaStream_t st,
   prof_mark(h, PK_ROUND, st, false);
   h->launches++;
 }
-static void launch_emit(mn_pool* h, int lo, int hi, int publish, cudaStream_t st, int hist_slot = -1) {
+static void launch_emit(mn_pool* h, int lo, int hi, int publish, cudaStream_t st, int hist_slot = -1, int last_tag = 0) {
   prof_mark(h, PK_EMIT, st, true);
-  if (h->d.depth == 1) k_emit<1><<<hi - lo, 256, 0, st>>>(h->d, lo, hi, publish, hist_slot);
-  else k_emit<3><<<hi - lo, 256, 0, st>>>(h->d, lo, hi, publish, hist_slot);
+  if (h->d.depth == 1) k_emit<1><<<hi - lo, 256, 0, st>>>(h->d, lo, hi, publish, hist_slot, last_tag);
+  else k_emit<3><<<hi - lo, 256, 0, st>>>(h->d, lo, hi, publish, hist_slot, last_tag);
   prof_mark(h, PK_EMIT, st, false);
   h->launches++;
+}
+// after FiGAR round `r` and its K3 on `st`: publish the envs that finished in it, on the side stream
+static int launch_emit_early(mn_pool* h, int r, cudaStream_t st, int hist_slot) {
+  CU(cudaEventRecord(h->ev_round[r], st));
+  CU(cudaStreamWaitEvent(h->side, h->ev_round[r], 0));
+  if (h->d.depth == 1) k_emit_early<1><<<h->early_grid, 256, 0, h->side>>>(h->d, r + 1, hist_slot);
+  else k_emit_early<3><<<h->early_grid, 256, 0, h->side>>>(h->d, r + 1, hist_slot);
+  h->launches++;
+  return 0;
 }
 // get_initial_state() for the envs on the reset list (list 2) (atari_emulator.py:102-110): memo hits are restored
 // by copy, misses are emulated with the RAM-dependence probe and then stored
 static void launch_initial_state(mn_pool* h, cudaStream_t st) {
   const int n = h->d.n_envs;
+  const bool memo = h->d.memo_enabled != 0;
   prof_mark(h, PK_OTHER, st, true);
   k_clear_counts<<<1, 32, 0, st>>>(h->d, 0);
   k_clear_counts<<<1, 32, 0, st>>>(h->d, 1);
+  k_clear_counts<<<1, 32, 0, st>>>(h->d, 3);
   k_reset_prepare<<<(n + 255) / 256, 256, 0, st>>>(h->d);
-  if (h->d.memo_enabled) {
+  if (memo) {
     if (h->d.depth == 1) k_reset_restore<1><<<n, 256, 0, st>>>(h->d); else k_reset_restore<3><<<n, 256, 0, st>>>(h->d);
     h->launches++;
   }
   prof_mark(h, PK_OTHER, st, false);
-  h->launches += 3;
-  const bool track = h->d.memo_enabled != 0;
-  launch_round(h, ROUND_RESET, 1, -1, st, track);
+  h->launches += 4;
+  launch_round(h, ROUND_RESET, 1, -1, st, memo);
+  if (memo) {   // level 1: what the reset unit left (stored for the misses, restored for the level-1 hits, which join list 1)
+    prof_mark(h, PK_OTHER, st, true);
+    if (h->d.depth == 1) k_memo_insert<1, 1><<<n, 256, 0, st>>>(h->d); else k_memo_insert<3, 1><<<n, 256, 0, st>>>(h->d);
+    k_reset_restore_l1<<<n, 256, 0, st>>>(h->d);
+    prof_mark(h, PK_OTHER, st, false);
+    h->launches += 2;
+  }
   for (int i = 0; i < MN_STACK; ++i) {
-    launch_round(h, ROUND_INITIAL, 1, (i == MN_STACK - 1) ? -1 : -2, st, track);
+    launch_round(h, ROUND_INITIAL, 1, (i == MN_STACK - 1) ? -1 : -2, st, memo);
     launch_push(h, 1, st);
   }
-  if (h->d.memo_enabled) {
+  if (memo) {
     prof_mark(h, PK_OTHER, st, true);
-    if (h->d.depth == 1) k_memo_insert<1><<<n, 256, 0, st>>>(h->d); else k_memo_insert<3><<<n, 256, 0, st>>>(h->d);
+    if (h->d.depth == 1) k_memo_insert<1, 2><<<n, 256, 0, st>>>(h->d); else k_memo_insert<3, 2><<<n, 256, 0, st>>>(h->d);
     prof_mark(h, PK_OTHER, st, false);
     h->launches++;
   }
@@ -1327,7 +1464,7 @@ int mn_reset_all(mn_handle h, void* stream) {
         launch_round(h, ROUND_INITIAL, 1, (i == MN_STACK - 1) ? -1 : -2, st, true);
         launch_push(h, 1, st);
       }
-      if (h->d.depth == 1) k_memo_insert<1><<<n, 256, 0, st>>>(h->d); else k_memo_insert<3><<<n, 256, 0, st>>>(h->d);
+      if (h->d.depth == 1) k_memo_insert<1, 2><<<n, 256, 0, st>>>(h->d); else k_memo_insert<3, 2><<<n, 256, 0, st>>>(h->d);
       k_warm_end<<<h->d.n_games, 96, 0, st>>>(h->d, pass);
       h->launches += 3;
     }
@@ -1356,21 +1493,42 @@ int mn_step_async(mn_handle h, int use_indices, void* stream) {
   const int n = h->d.n_envs, tb = 256, gb = (n + tb - 1) / tb;
   k_begin_step<<<gb, tb, 0, st>>>(h->d, use_indices);
   h->launches++;
+  if (h->d.history) h->hist_head = (h->hist_head + 1) % h->d.history_depth;   // update_memory: shift, newest last
+  const int hist_slot = h->d.history ? h->hist_head : -1;
+  const bool early = h->early_emit && h->max_rep > 0 && h->max_rep <= 32;
   int in = 0;
   for (int r = 0; r <= h->max_rep; ++r) {
     const int out = in ^ 1;
     launch_round(h, ROUND_FIGAR, in, out, st);
     launch_push(h, in, st);
     if (r < h->max_rep) { k_clear_counts<<<1, 32, 0, st>>>(h->d, in); h->launches++; }
+    if (early && r < h->max_rep && launch_emit_early(h, r, st, hist_slot)) return -1;
     in = out;
   }
   launch_initial_state(h, st);
-  if (h->d.history) h->hist_head = (h->hist_head + 1) % h->d.history_depth;   // update_memory: shift, newest last
-  launch_emit(h, 0, n, 1, st, h->d.history ? h->hist_head : -1);
+  if (early) {   // the rest, once the side stream is through
+    CU(cudaEventRecord(h->ev_side, h->side));
+    CU(cudaStreamWaitEvent(st, h->ev_side, 0));
+  }
+  launch_emit(h, 0, n, 1, st, hist_slot, early ? h->max_rep + 1 : 0);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(h->err_host, h->d.error, sizeof(int), cudaMemcpyDeviceToHost, st));
   CU(cudaEventRecord(h->done, st));
   h->pending = true;
+  return 0;
+}
+
+int mn_set_host_states(mn_handle h, uint8_t* states_pinned_host) {
+  if (!h) return fail("mn_set_host_states: null handle");
+  CU(cudaSetDevice(h->device));
+  if (h->pending) { CU(cudaEventSynchronize(h->done)); }   // no step in flight may still write through the old pointer
+  if (!states_pinned_host) { h->d.states_host = nullptr; return 0; }
+  void* dev = nullptr;
+  if (cudaHostGetDevicePointer(&dev, states_pinned_host, 0) != cudaSuccess || !dev) {
+    cudaGetLastError();
+    return fail("mn_set_host_states: not page-locked, device-mapped host memory (cudaHostAlloc / cudaHostRegister / torch pin_memory)");
+  }
+  h->d.states_host = static_cast<uint8_t*>(dev);
   return 0;
 }
 
@@ -1520,6 +1678,15 @@ int mn_memo_stats(mn_handle h, int64_t* out3) {
   unsigned long long v[4] = {0, 0, 0, 0};
   CU(cudaMemcpy(v, h->d.memo_stats, sizeof(v), cudaMemcpyDeviceToHost));
   out3[0] = int64_t(v[0]); out3[1] = int64_t(v[1]); out3[2] = int64_t(v[2]);
+  return 0;
+}
+
+int mn_memo_level1_hits(mn_handle h, int64_t* out) {
+  if (!h || !out) return fail("mn_memo_level1_hits: null argument");
+  CU(cudaSetDevice(h->device));
+  unsigned long long v = 0;
+  CU(cudaMemcpy(&v, h->d.memo_stats + 3, sizeof(v), cudaMemcpyDeviceToHost));
+  *out = int64_t(v);
   return 0;
 }
 

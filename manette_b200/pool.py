@@ -136,6 +136,20 @@ class DevicePool(object):
         if wait:
             self.wait()
 
+    def set_host_states(self, pinned):
+        """Register `pinned` -- a page-locked uint8 host tensor shaped like `states` -- as the host copy of the states: every
+        later reset / macro step writes what it publishes there too, while the step runs (mn_set_host_states).  None
+        unregisters.  The pool keeps a reference to the tensor for as long as it is registered."""
+        if pinned is None:
+            _native.check(self._L.mn_set_host_states(self._h, None), "mn_set_host_states")
+            self._host_states = None
+            return
+        if not (pinned.is_pinned() and pinned.is_contiguous() and pinned.dtype == torch.uint8
+                and tuple(pinned.shape) == tuple(self.states.shape)):
+            raise ValueError("set_host_states needs a pinned, contiguous uint8 tensor of shape %s" % (tuple(self.states.shape),))
+        _native.check(self._L.mn_set_host_states(self._h, C.c_void_p(pinned.data_ptr())), "mn_set_host_states")
+        self._host_states = pinned
+
     def step_async(self, use_indices=False, stream=None):
         _native.check(self._L.mn_step_async(self._h, int(bool(use_indices)), self._stream_ptr(stream)), "mn_step_async")
 
@@ -197,6 +211,13 @@ class DevicePool(object):
         v = (C.c_int64 * 3)()
         _native.check(self._L.mn_memo_stats(self._h, v), "mn_memo_stats")
         return int(v[0]), int(v[1]), int(v[2])
+
+    def memo_level1_hits(self):
+        """Of the emulated get_initial_state() calls: those restored to the end of the reset unit from the memo's level 1
+        (only the four start frames were emulated)."""
+        v = C.c_int64()
+        _native.check(self._L.mn_memo_level1_hits(self._h, C.byref(v)), "mn_memo_level1_hits")
+        return v.value
 
     def total_instructions(self):
         v = C.c_int64()

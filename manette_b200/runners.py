@@ -11,7 +11,10 @@ blocks until it has finished.
 
 Two ways to read the results:
 * host mirror (default, what paac.py expects): get_shared_variables() returns pinned host numpy arrays;
-  update_environments() uploads actions/repetitions and downloads states/rewards/terminals around the step;
+  update_environments() uploads actions/repetitions before the step and downloads rewards/terminals after it; the
+  states array is registered with the pool (mn_set_host_states), whose kernels write each environment's new state into
+  it as soon as that environment has finished its repeats -- the 28 KB x N of a step cross PCIe underneath the remaining
+  FiGAR rounds instead of in one copy after them;
 * zero-copy: get_device_variables() returns torch CUDA tensors aliasing the pool's buffers; with
   `host_mirror=False` no host copies are made at all (the learner reads and writes the device tensors).
 """
@@ -66,6 +69,8 @@ class Runners(object):
     def stop(self):
         self._started = False
         torch.cuda.synchronize(self.pool.device)
+        if self.host_mirror and getattr(self.pool, "_host_states", None) is self._pinned[0]:
+            self.pool.set_host_states(None)
 
     def get_shared_variables(self):
         if not self.host_mirror:
@@ -82,12 +87,13 @@ class Runners(object):
             self._group.fresh[:] = False
         stream = pool.stream
         if self.host_mirror:
+            if getattr(pool, "_host_states", None) is not self._pinned[0]:
+                pool.set_host_states(self._pinned[0])
             with torch.cuda.stream(stream):
                 if not use_indices:
                     pool.actions.copy_(self._pinned[3], non_blocking=True)
                     pool.repetitions.copy_(self._pinned[4], non_blocking=True)
-                pool.step_async(use_indices, stream)
-                self._pinned[0].copy_(pool.states, non_blocking=True)
+                pool.step_async(use_indices, stream)     # publishes the states into self._pinned[0] as it goes
                 self._pinned[1].copy_(pool.rewards, non_blocking=True)
                 self._pinned[2].copy_(pool.terminals, non_blocking=True)
         else:

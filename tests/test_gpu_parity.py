@@ -133,8 +133,12 @@ def test_memoised_resets_match_oracle(game):
                 assert np.array_equal(pool.cpu_state(e)[:7], ora.emus[e].ale.getCPU()[:7]), (game, rep, e, "cpu")
         hits, misses, stored = pool.memo_stats()
         assert hits + misses == n * 46 and stored >= 1
-        if game != "yars_revenge":   # its reset reads two RAM bytes that differ every time: exact, but never reusable
+        if game != "yars_revenge":
             assert hits > 40, (hits, misses, stored)
+        else:
+            # its four start frames read a pseudo-random byte the game keeps across resets: the whole-segment key almost
+            # never recurs, but the reset unit itself (level 1 of the memo) depends on two bytes with a handful of values
+            assert pool.memo_level1_hits() > 10, (hits, misses, stored, pool.memo_level1_hits())
     finally:
         pool.close()
 

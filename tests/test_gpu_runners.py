@@ -35,6 +35,7 @@ def _drive(game, n, workers, rgb=False, k=11, max_rep=10, single_life=False, ran
         for z in range(n):                                   # paac.py:159-161
             s_actions[z] = np.eye(creator.num_actions)[acts[t][z]]
             s_rep[z] = np.eye(k)[reps[t][z]]
+        s_states[...] = 0xA5        # every env's state must be rewritten by the step (the pool's kernels write this array)
         runners.update_environments()
         runners.wait_updated()
         ws, wr, wt, _ = ora.macro_step(acts[t], reps[t])
