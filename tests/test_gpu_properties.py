@@ -118,3 +118,35 @@ def test_mixed_game_pool_matches_single_game_pools():
             p.close()
     finally:
         mixed.close()
+
+
+def test_host_states_mirror_follows_every_publication():
+    """mn_set_host_states: a registered pinned array receives every state the pool publishes -- at reset, during the
+    macro step as envs finish their repeats (k_emit_early), and at its end (last round, terminals after their reset) --
+    and is exactly the device array once the step has been waited for.  Pageable memory is refused; unregistering stops
+    the writes."""
+    import torch
+    import manette_b200 as mb
+    n, k = 96, 11
+    pool = mb.DevicePool([("breakout", rom_bytes("breakout"), 64), ("pong", rom_bytes("pong"), 32)], tab_rep=list(range(k)))
+    try:
+        with pytest.raises(ValueError):
+            pool.set_host_states(torch.zeros(tuple(pool.states.shape), dtype=torch.uint8))
+        pinned = torch.zeros(tuple(pool.states.shape), dtype=torch.uint8).pin_memory()
+        pool.set_host_states(pinned)
+        pool.reset_all()
+        assert np.array_equal(pinned.numpy(), pool.states.cpu().numpy())
+        acts, reps = util.schedule(23, 60, n, 4, k)
+        terminals = 0
+        for t in range(60):
+            pinned.fill_(0xA5)
+            _step(pool, acts[t], reps[t])
+            assert np.array_equal(pinned.numpy(), pool.states.cpu().numpy()), t
+            terminals += int(pool.terminals.sum())
+        assert terminals > 0
+        pool.set_host_states(None)
+        pinned.fill_(0xA5)
+        _step(pool, acts[0], reps[0])
+        assert bool((pinned == 0xA5).all())
+    finally:
+        pool.close()
