@@ -9,7 +9,9 @@ and in-step reset on terminal, then the stacked states / rewards / terminals are
 
 Prints ONE JSON line (rank 0).  `value` = next() calls of all ranks / max-over-ranks device time with the
 policy's choices already in HBM; `e2e` = the same through Runners with HOST arrays (H2D of the one-hot
-actions/repetitions and D2H of states/rewards/terminals every step inside the timed region).
+actions/repetitions and D2H of states/rewards/terminals every step inside the timed region; the states are
+written into the pinned host array by the pool's kernels as environments finish their repeats, not copied
+after the step -- the bytes are the same, they cross PCIe underneath the remaining FiGAR rounds).
 `--impl reference` times the CPU restatement of the reference's own worker pool (oracle/host_path.py
 PortRunners over the C++ oracle emulator) on all host cores.
 """
