@@ -1,6 +1,9 @@
 mkdir -p gpurun_out
-python -c "import __graft_entry__ as g; g.build(); g.smoke()" 2>&1 | tail -2
-bash tools/gpu_bench_lines.sh r2h
-python bench.py > gpurun_out/bench_default_final.json 2> gpurun_out/bench_default_final.err; python -c "
-import json; d=json.loads(open('gpurun_out/bench_default_final.json').read().strip().splitlines()[-1])
-print(int(d['value']), int(d['e2e']['value']), d['steps'], d['warmup'], d['roofline']['frac'], d['roofline']['counters']['source_hash'], d['clocks'], d['cpu_baseline']['value'])"
+run() { tag=$1; shift; env "$@" timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/knob_$tag.json 2> gpurun_out/knob_$tag.err; python -c "
+import json; d=json.loads(open('gpurun_out/knob_$tag.json').read().strip().splitlines()[-1]); print('$tag', int(d['value']), d['ms_per_step'])"; }
+run base MN_EARLY_EMIT=1
+run high6 MN_FIFO_HIGH=6
+run high8 MN_FIFO_HIGH=8
+run high10 MN_FIFO_HIGH=10
+run high14 MN_FIFO_HIGH=14
+run slack8 MN_SYNC_SLACK=8
