@@ -1,9 +1,9 @@
+# ncu --set full of the publication kernels with a host copy registered: k_emit_early of round 2 and the final k_emit
 mkdir -p gpurun_out
-run() { tag=$1; shift; env "$@" timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/knob_$tag.json 2> gpurun_out/knob_$tag.err; python -c "
-import json; d=json.loads(open('gpurun_out/knob_$tag.json').read().strip().splitlines()[-1]); print('$tag', int(d['value']), d['ms_per_step'])"; }
-run base MN_EARLY_EMIT=1
-run high6 MN_FIFO_HIGH=6
-run high8 MN_FIFO_HIGH=8
-run high10 MN_FIFO_HIGH=10
-run high14 MN_FIFO_HIGH=14
-run slack8 MN_SYNC_SLACK=8
+python tools/profile_step.py --envs 16384 --decorrelate 24 --steps 1 --host-mirror 2>&1 | tail -1
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_emit_early -s 2 -c 1 -f -o gpurun_out/decor_r2_emit_early \
+    python tools/profile_step.py --envs 16384 --decorrelate 24 --steps 1 --host-mirror > gpurun_out/decor_ncu_r2_emit_early.log 2>&1
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'k_emit<' -s 0 -c 1 -f -o gpurun_out/decor_r2_emit_final \
+    python tools/profile_step.py --envs 16384 --decorrelate 24 --steps 1 --host-mirror > gpurun_out/decor_ncu_r2_emit_final.log 2>&1
+tail -2 gpurun_out/decor_ncu_r2_emit_early.log gpurun_out/decor_ncu_r2_emit_final.log
+ls -la gpurun_out/decor_r2_emit_*.ncu-rep

@@ -23,10 +23,13 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--envs-per-warp", type=int, default=0)
     ap.add_argument("--max-rep", type=int, default=10)
+    ap.add_argument("--host-mirror", action="store_true", help="register a pinned host copy of the states (mn_set_host_states)")
     a = ap.parse_args()
     k = a.max_rep + 1
     pool = mb.DevicePool([(a.game, mb.load_rom(ROMS, a.game), a.envs)], rgb=a.rgb, tab_rep=list(range(k)),
                          envs_per_warp=a.envs_per_warp)
+    if a.host_mirror:
+        pool.set_host_states(torch.zeros(tuple(pool.states.shape), dtype=torch.uint8).pin_memory())
     pool.reset_all()
     g = torch.Generator(device="cuda")
     g.manual_seed(7)
