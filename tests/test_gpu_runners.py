@@ -166,3 +166,35 @@ def test_emulator_runner_loop_equals_the_batched_macro_step():
     runners.stop()
     pool_b.close()
     mb.release_pools()
+
+
+def test_step_host_with_pageable_arrays_equals_the_device_step():
+    """mn_step_host -- the single call INTEGRATION.md section 2 shows, with ordinary (pageable) numpy arrays -- returns
+    exactly what the asynchronous device step leaves in the pool's buffers: twin pools, 40 FiGAR macro steps with
+    episodes ending inside them, every env's state rewritten by every call."""
+    import torch
+    import manette_b200 as mb
+    n, k = 48, 11
+    tab = list(range(k))
+    mk = lambda: mb.DevicePool([("breakout", rom_bytes("breakout"), 32), ("seaquest", rom_bytes("seaquest"), 16)],
+                               tab_rep=tab, single_life_episodes=True)
+    a, b = mk(), mk()
+    try:
+        a.reset_all(); b.reset_all()
+        A = a.num_actions
+        acts, reps = util.schedule(29, 40, n, 4, k)
+        hs = np.zeros(tuple(b.states.shape), np.uint8); hr = np.zeros(n, np.float32); ht = np.zeros(n, np.float32)
+        terminals = 0
+        for t in range(40):
+            oa = np.eye(A, dtype=np.float32)[acts[t]]; orr = np.eye(k, dtype=np.float32)[reps[t]]
+            a.actions.copy_(torch.as_tensor(oa)); a.repetitions.copy_(torch.as_tensor(orr))
+            a.step_async(use_indices=False); a.wait()
+            hs[...] = 0xA5
+            b.step_host(oa, orr, hs, hr, ht)
+            assert np.array_equal(hs, a.states.cpu().numpy()), t
+            assert np.array_equal(hr, a.rewards.cpu().numpy()) and np.array_equal(ht, a.terminals.cpu().numpy()), t
+            assert np.array_equal(hs, b.states.cpu().numpy()), t
+            terminals += int(ht.sum())
+        assert terminals > 0
+    finally:
+        a.close(); b.close()
